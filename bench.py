@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200-native SplitFXM hot path.
+
+Workload (BASELINE.json configs[1], batched as configs[3]): finite-difference sparse-Jacobian assembly of the
+nx = 250, 3-variable advection-diffusion problem (benchmark/test_jac_benchmark.py:14-61 shape, FDM CENTRAL,
+1+1 ghost cells, split [1]) for an ensemble of `--members` independent (c, nu) members per GPU.
+One step = one assembly of every member's block-banded Jacobian (one kernel launch).
+
+  value      assemblies/s, inputs resident in HBM, CUDA-event time, max over ranks
+  e2e        same metric through EnsembleSimulation.jacobian with HOST buffers (pinned H2D of the states and
+             D2H of the banded Jacobians inside the timed region)
+  roofline   the Jacobian kernel's algorithmic bytes / its CUDA-event duration vs the measured HBM peak
+  cpu_baseline  oracle port (NumPy, 1 core) on a bounded sample of the same members
+
+`--impl reference` times the reference's CPU algorithm (oracle port - the reference is Python and cannot
+travel to the GPU box) on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NX, NV, W = 250, 3, 3
+COMPS = ["u", "v", "w"]
+ICS = {"u": "gaussian", "v": "rarefaction", "w": "tophat"}
+# benchmark BCs as main.py:14-27 except u, which is dirichlet so that every block is non-singular and the same
+# ensemble can also be Newton-solved
+BCS = {"u": {"left": {"dirichlet": 0.0}, "right": {"dirichlet": 0.0}},
+       "v": {"left": {"dirichlet": 3}, "right": {"dirichlet": 4}},
+       "w": {"left": {"dirichlet": 2}, "right": "periodic"}}
+SPLIT, LOCS = True, [1]
+METRIC = "jacobian_assemblies_per_s"
+UNIT = "assemblies/s (nx=250, nv=3, FDM CENTRAL, split [1])"
+
+
+def member_params(first, count, total):
+    """(c, nu) of members [first, first+count) of a sqrt(total) x sqrt(total) sweep grid."""
+    side = max(int(round(total ** 0.5)), 1)
+    k = np.arange(first, first + count)
+    c = np.linspace(0.05, 0.5, side)[(k // side) % side]
+    nu = np.logspace(-4, -2, side)[k % side]
+    return c, nu
+
+
+def initial_state():
+    """Flat split-major initial vector [750] of the benchmark problem (host, NumPy)."""
+    from oracle import core
+    x = np.linspace(0.0, 1.0, NX)
+    U = np.stack([core.initial_condition(x, ICS[c]) for c in COMPS], axis=1)
+    return x, core.to_flat(U, SPLIT, LOCS)
+
+
+def member_states(y0, first, count):
+    """Deterministic per-member perturbation of the initial state (no RNG: a smooth function of member id)."""
+    k = np.arange(first, first + count, dtype=np.float64)
+    q = np.arange(y0.shape[0], dtype=np.float64)
+    return y0[:, None] + 1e-3 * np.sin(0.37 * q[:, None] + 0.011 * k[None, :])
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: oracle port
+# ------------------------------------------------------------------------------------------------
+def _cpu_assemble(args):
+    first, count, total = args
+    from oracle import core
+    x, y0 = initial_state()
+    c, nu = member_params(first, count, total)
+    Y = member_states(y0, first, count)
+    acc = 0.0
+    for k in range(count):
+        P = core.Problem(core.AdvectionDiffusion(c[k], nu[k]), "FDM", "CENTRAL", x, 1, 1, BCS, COMPS)
+        Jb = P.jacobian_banded(core.to_block(Y[:, k], NX, NV, SPLIT, LOCS))
+        acc += float(Jb[0, 1, 0, 0])
+    return acc
+
+
+def cpu_baseline(sample, total):
+    t0 = time.perf_counter()
+    _cpu_assemble((0, sample, total))
+    dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{sample} members of the same ensemble, oracle/core.py Problem.jacobian_banded (NumPy colour "
+                      f"passes), {dt:.2f} s on 1 core; the reference itself (per-cell Python loops, simulation.py:"
+                      "270-394) took 0.16 s per assembly in the build container (BASELINE.md)"}
+
+
+def run_reference(args):
+    """Reference arm: the CPU algorithm on all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_proc = max(args.ref_members // cores, 1)
+    sample = per_proc * cores
+    total = args.members * args.gpus
+    jobs = [(i * per_proc, per_proc, total) for i in range(cores)]
+    with mp.get_context("fork").Pool(cores) as pool:
+        for _ in range(args.warmup):
+            pool.map(_cpu_assemble, jobs)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_cpu_assemble, jobs)
+        dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"Jacobian assembly nx={NX} nv={NV} FDM CENTRAL split {LOCS}, "
+                                   f"{sample} members per step (bounded sample of the {total}-member ensemble)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample} members per step over {cores} processes (oracle/core.py)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([f.strip() for f in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except ValueError:
+                continue
+            for name, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import splitfxm_b200 as sf
+    from splitfxm_b200 import _lib
+    from splitfxm_b200.ensemble import EnsembleSimulation
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = torch.device(f"cuda:{local}")
+    B = args.members
+    total = B * world
+    x, y0 = initial_state()
+    c, nu = member_params(rank * B, B, total)          # members shard across ranks: no data-path collective
+    d = sf.Domain.from_size(NX, 1, 1, COMPS)
+    ens = EnsembleSimulation(d, "ad", {"c": c, "nu": nu}, BCS, sf.FDSchemes.CENTRAL, method="FDM", device=dev)
+    eng = ens.eng
+    Y_host = torch.from_numpy(member_states(y0, rank * B, B)).pin_memory()
+    Y = Y_host.to(dev, non_blocking=True)
+    J = eng.jacobian_buffer()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing --------------------------------------------------------------------
+    for _ in range(args.warmup):
+        eng.jacobian(Y, SPLIT, LOCS, J=J)
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    _lib.LAUNCHES[0] = 0
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for k in range(args.steps):
+        eng.jacobian(Y, SPLIT, LOCS, J=J)
+        ev[k + 1].record()
+    barrier()
+    launches = _lib.LAUNCHES[0]
+    if sampler:
+        sampler.stop_flag.set()
+        sampler.join()
+    elapsed_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t[0])
+    value = total * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- roofline of the Jacobian kernel (this rank's launches) ------------------------------------
+    # algorithmic bytes per launch: read U (nv*8 per cell-member) + x (8 per cell, shared by members), write the
+    # same-segment entries of the band: split [1] -> segments of 1 and 2 variables -> (1 + 4) * W entries
+    seg_entries = sum(s * s for s in (LOCS[0], NV - LOCS[0]))
+    alg_bytes = B * NX * (NV * 8 + W * seg_entries * 8) + NX * 8
+    kern_ms = float(np.mean(per_launch_ms))
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("jacobian_kernel_dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "jacobian_kernel<ModelAD<3>, FD_CENTRAL, 3, 3>",
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms, "peak_source": peak_src}
+
+    # ---- end to end through the public API with host buffers --------------------------------------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    Jh = torch.empty(J.shape, dtype=torch.float64).pin_memory()
+    for _ in range(1):
+        Jd = ens.jacobian(Y_host, SPLIT, LOCS, out=J)
+        Jh.copy_(Jd, non_blocking=True)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(e2e_steps):
+        Jd = ens.jacobian(Y_host, SPLIT, LOCS, out=J)      # H2D of the states inside
+        Jh.copy_(Jd, non_blocking=True)                     # D2H of the banded Jacobians
+    t1.record()
+    barrier()
+    te = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = {"value": total * e2e_steps / (float(te[0]) * 1e-3), "unit": UNIT,
+           "h2d_bytes_per_step": int(Y_host.numel() * 8), "d2h_bytes_per_step": int(Jh.numel() * 8),
+           "steps": e2e_steps, "api": "EnsembleSimulation.jacobian(host states) + D2H of the banded Jacobians"}
+    del Jh
+
+    # ---- extras: Newton iterations on the same ensemble, single-mesh sweep -------------------------
+    extra = {}
+    if rank == 0 and not args.no_extra:
+        extra = extras(torch, sf, ens, Y, dev, peak)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": value / (1.0 / 0.6), "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"configs[1] sparse-Jacobian benchmark shape (nx={NX}, nv={NV}, FDM CENTRAL, "
+                                       f"nb 1/1, split {LOCS}) for an ensemble of {B} members per GPU "
+                                       f"(configs[3] sweep over c, nu; {total} members in total)",
+                           "members_per_gpu": B, "parallelism": f"ensemble-sharded x{world}, no collective",
+                           "l2": "inputs+outputs per launch (%.1f GB) exceed the 126 MB L2" % (alg_bytes / 1e9),
+                           "vs_baseline_note": "BASELINE.md published sparse Jacobian ~0.6 s per assembly at N=250 "
+                                               "(README.md:100-105, hardware unstated)"},
+                "gpu_launches": launches, "roofline": roofline, "e2e": e2e,
+                "cpu_baseline": cpu_baseline(args.cpu_sample, total),
+                "clocks": sampler.summary() if sampler else None, "extra": extra}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extras(torch, sf, ens, Y, dev, peak):
+    """Secondary numbers (not the headline): Newton iteration throughput on the ensemble, residual and Jacobian
+    on one large mesh."""
+    from splitfxm_b200.models.advection_diffusion import AdvectionDiffusion
+    out = {}
+    eng = ens.eng
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    B = eng.batch
+    r = torch.empty_like(Y)
+    s = torch.zeros_like(Y)
+    J = eng.jacobian_buffer()
+    status = torch.zeros(B, dtype=torch.int32, device=dev)
+    ms_res = timed(lambda: eng.residual(Y, r, SPLIT, LOCS), 5)
+    ms_solve = timed(lambda: eng.solve(J, r, s, SPLIT, LOCS, status=status), 3)
+    out["ensemble_residual"] = {"ms": ms_res, "GBps": B * NX * 48 / ms_res / 1e6, "frac": B * NX * 48 / ms_res / 1e6 / peak}
+    solve_bytes = B * NX * ((1 + 4) * W * 8 + 24 + 24)
+    out["ensemble_block_tridiag_solve"] = {"ms": ms_solve, "GBps": solve_bytes / ms_solve / 1e6,
+                                           "frac": solve_bytes / ms_solve / 1e6 / peak,
+                                           "solves_per_s": B / (ms_solve * 1e-3)}
+    t0 = time.perf_counter()
+    Yf, its = ens.steady_state(Y, split=SPLIT, split_locs=LOCS)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    res = float(torch.max(torch.abs(eng.residual(Yf, None, SPLIT, LOCS))))
+    out["ensemble_split_newton"] = {"members": B, "seconds": dt, "steady_states_per_s": B / dt,
+                                    "iterations_min_max": [int(its.min()), int(its.max())], "max_abs_residual": res}
+    sweep = []
+    for nx in (1000, 10000, 100000, 1000000):
+        d = sf.Domain.from_size(nx, 1, 1, COMPS)
+        sim = sf.Simulation(d, AdvectionDiffusion(0.2, 0.001, "FDM"), ICS, BCS, sf.FDSchemes.CENTRAL)
+        e1 = sim._engine()
+        y = e1.to_device(d.listify_interior(SPLIT, LOCS))
+        Jb = e1.jacobian_buffer()
+        rr = torch.empty_like(y)
+        ms_j = timed(lambda: e1.jacobian(y, SPLIT, LOCS, J=Jb), 5)
+        ms_r = timed(lambda: e1.residual(y, rr, SPLIT, LOCS), 5)
+        sweep.append({"nx": nx, "jacobian_ms": ms_j, "jacobian_assemblies_per_s": 1e3 / ms_j,
+                      "jacobian_GBps": nx * (24 + 8 + 15 * 8) / ms_j / 1e6, "residual_ms": ms_r,
+                      "residual_GBps": nx * 56 / ms_r / 1e6})
+    out["single_mesh_sweep"] = sweep
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--members", type=int, default=65536, help="ensemble members per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=256)
+    ap.add_argument("--ref-members", type=int, default=4096, help="members per step of the reference arm")
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,134 @@
+/* sfxm_b200.h - C ABI of the B200-native SplitFXM hot path.
+ *
+ * The reference (gpavanb1/SplitFXM v0.5.2) has no FFI for this path: its only native boundary is
+ * Python -> Cython `def` wrappers (splitfxm/flux.pyx:42,302; splitfxm/derivatives.pyx:196-281) called from
+ * splitfxm/equations/fv_transport.py:56-57 and fd_transport.py:46-50, driven by the pure-Python loops in
+ * splitfxm/system.py:58-65 and splitfxm/simulation.py:150-202, 270-394.  The entry points below are what a
+ * ctypes binding placed at those call sites would bind (INTEGRATION.md shows the stub); each one cites the
+ * reference code it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the caller owns all memory; calls are asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value 0 = OK, non-zero = error (sfxm_last_error() gives the text; Python raises SFXM);
+ *   - no global state except the last-error string.
+ *
+ * Data layout in HBM ("member-fastest"): an ensemble of `batch` independent members shares one mesh.
+ *   flat vectors   y[ flat(p, j) * batch + m ]       p = interior cell, j = variable, m = member
+ *                  flat(p, j) = var_base[j] + p * var_stride[j] + var_off[j]
+ *                  (unsplit: base 0, stride nv, off j  == the reference's cell-major vector,
+ *                   simulation.py:143; split: segment-major, simulation.py:137-140, 192-200)
+ *   positions      x_int[nx]  (interior only; ghost positions are recomputed, bc.py:56-151)
+ *   parameters     params[ k * param_stride + m ]   (param_stride = 0: one set shared by all members)
+ *   Jacobian       J[ (((i * W + d) * nv + r) * nv + c) * batch + m ],  W = nbl + nbr + 1,
+ *                  = d r_(i,r) / d U_((i - nbl + d) mod nx, c)  (block band with cyclic wrap slots)
+ * With batch = 1 these are exactly the reference's flat vector and a block-banded matrix.
+ */
+#ifndef SFXM_B200_H
+#define SFXM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFXM_MAX_NV 4
+#define SFXM_MAX_NB 2
+#define SFXM_MAX_PARAMS 4
+#define SFXM_RK_MAX_STAGES 8
+
+/* models (models/advection_diffusion.py:28-31, tutorials/sod_shock/euler1d.py:27-50,
+ * tutorials/conservative_sod_shock/euler1d.py:28-63) */
+enum { SFXM_MODEL_AD = 0, SFXM_MODEL_EULER_PRIM = 1, SFXM_MODEL_EULER_CONS = 2 };
+/* schemes (schemes.py:4-14) */
+enum { SFXM_FV_LAX_FRIEDRICHS = 0, SFXM_FV_CENTRAL = 1, SFXM_FV_UPWIND = 2, SFXM_FD_CENTRAL = 3,
+       SFXM_FD_RIGHT_BIAS = 4 };
+/* boundary types (bc.py:47-153); KEEP = variable/side has no entry in `bcs`, ghost keeps its value */
+enum { SFXM_BC_PERIODIC = 0, SFXM_BC_OUTFLOW = 1, SFXM_BC_NEUMANN = 2, SFXM_BC_DIRICHLET = 3, SFXM_BC_KEEP = 4 };
+/* which rule wrote the shared ghost positions last (bc.py:56,64 periodic; :73,87,114,127,141,151 mirror) */
+enum { SFXM_GX_PERIODIC = 0, SFXM_GX_MIRROR = 1, SFXM_GX_KEEP = 2 };
+
+typedef struct sfxm_problem {
+  int32_t model, scheme;
+  int32_t nv, nbl, nbr;
+  int32_t n_params;
+  int64_t nx;    /* interior cells */
+  int64_t batch; /* ensemble members sharing the mesh */
+  double xmin, xmax;
+  /* per variable, per side */
+  int32_t bc_ltype[SFXM_MAX_NV], bc_rtype[SFXM_MAX_NV];
+  double bc_lval[SFXM_MAX_NV][SFXM_MAX_NB], bc_rval[SFXM_MAX_NV][SFXM_MAX_NB]; /* dirichlet/neumann value; KEEP: per ghost */
+  int32_t gx_left, gx_right;                               /* SFXM_GX_* */
+  double gx_keep_left[SFXM_MAX_NB], gx_keep_right[SFXM_MAX_NB];
+  /* flat-vector layout (split permutation) */
+  int64_t var_base[SFXM_MAX_NV];
+  int32_t var_stride[SFXM_MAX_NV], var_off[SFXM_MAX_NV], var_seg[SFXM_MAX_NV];
+} sfxm_problem_t;
+
+int sfxm_abi_version(void);
+const char *sfxm_last_error(void);
+
+/* r = f(y).  Replaces Simulation.get_residuals_from_list (simulation.py:150-202): initialize_from_list
+ * (:107-148) + apply_BC for every variable (bc.py:6-159) + System.residuals (system.py:28-70) +
+ * FV/FDTransportEquation.residuals (fv_transport.py:27-59, fd_transport.py:26-51) + flux.pyx / derivatives.pyx
+ * + the split-major re-ordering (:192-200), fused into one launch.
+ * If y_out != NULL also writes y_out = y + dt * f(y) (the explicit Euler update, simulation.py:455-463). */
+int sfxm_residual(const sfxm_problem_t *prob, const double *x_int, const double *params, int64_t param_stride,
+                  const double *y, double *r, double *y_out, double dt, void *stream);
+
+/* Materialise the Domain view: x_all[nbl+nx+nbr], U_all[(nbl+nx+nbr) * nv * batch] (cell-major, unsplit,
+ * member-fastest) with ghosts filled.  Replaces initialize_from_list + apply_BC (simulation.py:171-175). */
+int sfxm_fill_domain(const sfxm_problem_t *prob, const double *x_int, const double *y, double *x_all, double *U_all,
+                     void *stream);
+
+/* Block-banded finite-difference Jacobian; all perturbations in one pass.  Replaces Simulation.jacobian
+ * (simulation.py:270-394) incl. get_periodic_bcs / extend_band (bc.py:162-240).  Split mode writes
+ * same-segment entries only (simulation.py:373-392); the others are left untouched (keep J zero-filled).
+ * r0 (optional) receives the unperturbed residual in flat order. */
+int sfxm_jacobian(const sfxm_problem_t *prob, const double *x_int, const double *params, int64_t param_stride,
+                  const double *y, double eps, double *J, double *r0, void *stream);
+
+/* Solve, for every member and every variable segment, (J_seg + shift_m I) s = -f  with the block-tridiagonal
+ * (cyclic if wrap slots are non-zero) J from sfxm_jacobian; W must be 3.  `shift` is per member (NULL = 0):
+ * the pseudo-transient term of Newton's method.  `active` (NULL = all) masks members.  `work` needs
+ * sfxm_solve_workspace_bytes().  status[m] = 0 ok, 1 = singular pivot.  The linear algebra behind
+ * splitnewton.newton / split_newton as called at simulation.py:515-523. */
+int64_t sfxm_solve_workspace_bytes(const sfxm_problem_t *prob);
+int sfxm_block_tridiag_solve(const sfxm_problem_t *prob, const double *J, const double *f, const double *shift,
+                             const int32_t *active, int32_t seg_lo, int32_t seg_hi, double *s, double *work,
+                             int32_t *status, void *stream);
+
+/* Per-member sums of squares over a flat-index range [lo, hi): out[m] = sum v[q*batch+m]^2, accumulated in a
+ * fixed order (deterministic).  work: sfxm_sumsq_workspace_bytes(hi - lo, batch).  The norms of
+ * splitnewton's convergence criterion. */
+int64_t sfxm_sumsq_workspace_bytes(int64_t n, int64_t batch);
+int sfxm_sumsq(const double *v, int64_t lo, int64_t hi, int64_t batch, double *out, double *work, void *stream);
+
+/* y[q, m] += alpha[m] * s[q, m] for q in [lo, hi) and members with active[m] != 0. */
+int sfxm_axpy_masked(double *y, const double *s, const double *alpha, const int32_t *active, int64_t lo, int64_t hi,
+                     int64_t batch, void *stream);
+
+/* ---- explicit Runge-Kutta vector kernels for Simulation.evolve (simulation.py:396-472, which calls
+ * scipy.integrate.solve_ivp at :468-469; arithmetic order of scipy/integrate/_ivp/rk.py + common.py).
+ * K holds the stages: K_s = K + s * stage_stride, each a flat [n * batch] vector; `total` = n * batch. ---- */
+
+/* out = y + (sum_{s<nstage} K_s coef[s]) * h                     (rk.py rk_step) */
+int sfxm_rk_lincomb(const double *y, const double *K, int64_t stage_stride, const double *coef_host, int32_t nstage,
+                    double h, double *out, int64_t total, void *stream);
+/* out = y_old + h * sum_k (sum_s K_s P[s][k]),  P_host[nstage][4]  (RkDenseOutput._call_impl at x = 1) */
+int sfxm_rk_dense_end(const double *y_old, const double *K, int64_t stage_stride, const double *P_host, int32_t nstage,
+                      double h, double *out, int64_t total, void *stream);
+/* out[m] = sum_q ((a - a2) / (atol + |b| rtol))^2   (a2 may be NULL; select_initial_step's d0, d1, d2) */
+int64_t sfxm_scaled_sumsq_workspace_bytes(int64_t n, int64_t batch);
+int sfxm_scaled_diff_sumsq(const double *a, const double *a2, const double *b, double atol, double rtol, int64_t n,
+                           int64_t batch, double *out, double *work, void *stream);
+/* out[m] = sum_q (((sum_s K_s E[s]) * h) / (atol + max(|y|, |y_new|) rtol))^2   (_estimate_error_norm) */
+int sfxm_rk_error_sumsq(const double *K, int64_t stage_stride, const double *E_host, int32_t nstage, double h,
+                        const double *y, const double *y_new, double atol, double rtol, int64_t n, int64_t batch,
+                        double *out, double *work, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFXM_B200_H */

@@ -1,0 +1,101 @@
+"""ctypes binding of libsfxm_b200.so (the C ABI in include/sfxm_b200.h).
+
+There is no CPU fallback: importing this module without the built library, or calling into it without a
+CUDA device, raises.  Build with ``splitfxm_b200/csrc/build.sh`` (or ``__graft_entry__.build()``).
+"""
+import ctypes
+import os
+
+from .error import SFXM
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libsfxm_b200.so")
+
+MAX_NV, MAX_NB, MAX_PARAMS = 4, 2, 4
+
+MODEL_AD, MODEL_EULER_PRIM, MODEL_EULER_CONS = 0, 1, 2
+FV_LAX_FRIEDRICHS, FV_CENTRAL, FV_UPWIND, FD_CENTRAL, FD_RIGHT_BIAS = 0, 1, 2, 3, 4
+BC_PERIODIC, BC_OUTFLOW, BC_NEUMANN, BC_DIRICHLET, BC_KEEP = 0, 1, 2, 3, 4
+GX_PERIODIC, GX_MIRROR, GX_KEEP = 0, 1, 2
+
+c_i32, c_i64, c_f64, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
+
+
+class Problem(ctypes.Structure):
+    """struct sfxm_problem (include/sfxm_b200.h)."""
+    _fields_ = [
+        ("model", c_i32), ("scheme", c_i32),
+        ("nv", c_i32), ("nbl", c_i32), ("nbr", c_i32),
+        ("n_params", c_i32),
+        ("nx", c_i64), ("batch", c_i64),
+        ("xmin", c_f64), ("xmax", c_f64),
+        ("bc_ltype", c_i32 * MAX_NV), ("bc_rtype", c_i32 * MAX_NV),
+        ("bc_lval", (c_f64 * MAX_NB) * MAX_NV), ("bc_rval", (c_f64 * MAX_NB) * MAX_NV),
+        ("gx_left", c_i32), ("gx_right", c_i32),
+        ("gx_keep_left", c_f64 * MAX_NB), ("gx_keep_right", c_f64 * MAX_NB),
+        ("var_base", c_i64 * MAX_NV),
+        ("var_stride", c_i32 * MAX_NV), ("var_off", c_i32 * MAX_NV), ("var_seg", c_i32 * MAX_NV),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/sfxm_b200.h declares
+_PP = ctypes.POINTER(Problem)
+SIGNATURES = {
+    "sfxm_abi_version": (ctypes.c_int, []),
+    "sfxm_last_error": (ctypes.c_char_p, []),
+    "sfxm_residual": (ctypes.c_int, [_PP, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_f64, c_vp]),
+    "sfxm_fill_domain": (ctypes.c_int, [_PP, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_jacobian": (ctypes.c_int, [_PP, c_vp, c_vp, c_i64, c_vp, c_f64, c_vp, c_vp, c_vp]),
+    "sfxm_solve_workspace_bytes": (c_i64, [_PP]),
+    "sfxm_block_tridiag_solve": (ctypes.c_int, [_PP, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_sumsq_workspace_bytes": (c_i64, [c_i64, c_i64]),
+    "sfxm_sumsq": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "sfxm_axpy_masked": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
+    "sfxm_rk_lincomb": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_f64), c_i32, c_f64, c_vp, c_i64, c_vp]),
+    "sfxm_rk_dense_end": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_f64), c_i32, c_f64, c_vp, c_i64, c_vp]),
+    "sfxm_scaled_sumsq_workspace_bytes": (c_i64, [c_i64, c_i64]),
+    "sfxm_scaled_diff_sumsq": (ctypes.c_int, [c_vp, c_vp, c_vp, c_f64, c_f64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "sfxm_rk_error_sumsq": (ctypes.c_int, [c_vp, c_i64, ctypes.POINTER(c_f64), c_i32, c_f64, c_vp, c_vp, c_f64, c_f64,
+                                           c_i64, c_i64, c_vp, c_vp, c_vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises SFXM if it has not been built - never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SFXM(f"{LIB_PATH} is missing: build it with splitfxm_b200/csrc/build.sh "
+                   "(there is no CPU fallback for the hot path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        msg = load().sfxm_last_error().decode("utf-8", "replace")
+        raise SFXM(msg or f"libsfxm_b200 error {status}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+LAUNCHES = [0]   # number of kernel launches issued through the C ABI (bench.py reports it)
+
+
+def count(n=1):
+    LAUNCHES[0] += n

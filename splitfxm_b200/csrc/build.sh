@@ -1,0 +1,16 @@
+#!/bin/bash
+# Build libsfxm_b200.so for sm_100a (B200).  -fmad=false: the parity target is the reference's plain IEEE
+# multiply/add order; fused multiply-adds would change the last bit of every residual.
+set -e
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC ${SFXM_NVCC_EXTRA}"
+cd "$HERE"
+for f in sfxm_host sfxm_kernels sfxm_solve sfxm_ode; do
+  if [ ! -f "$f.o" ] || [ "$f.cu" -nt "$f.o" ] || [ sfxm_device.cuh -nt "$f.o" ] || [ ../../include/sfxm_b200.h -nt "$f.o" ] || [ sfxm_host.h -nt "$f.o" ]; then
+    "$NVCC" $FLAGS -c "$f.cu" -o "$f.o" &
+  fi
+done
+wait
+"$NVCC" -shared -o libsfxm_b200.so sfxm_host.o sfxm_kernels.o sfxm_solve.o sfxm_ode.o -lcudart
+echo "built $HERE/libsfxm_b200.so"

@@ -1,0 +1,341 @@
+// sfxm_device.cuh - device-side building blocks of the SplitFXM hot path (sm_100a, FP64).
+//
+// Everything here is arithmetic that must reproduce the reference's IEEE operation order
+// (SURVEY.md 8a); the translation unit is compiled with -fmad=false so no multiply-add is fused.
+// Citations are to the reference tree (gpavanb1/SplitFXM v0.5.2).
+#pragma once
+#include <cstdint>
+#include "../../include/sfxm_b200.h"
+
+namespace sfxm {
+
+// ------------------------------------------------------------------------------------------------
+// State access: flat vector, member-fastest (include/sfxm_b200.h "Data layout")
+// ------------------------------------------------------------------------------------------------
+struct View {
+  const double *__restrict__ y;   // flat state
+  const double *__restrict__ x;   // interior positions
+  int64_t m;                      // member
+  int64_t pc;                     // perturbed cell (-1: none)   simulation.py:337
+  int pv;                         // perturbed variable
+  double eps;
+};
+
+__device__ __forceinline__ int64_t flat_index(const sfxm_problem_t &P, int64_t cell, int var) {
+  return P.var_base[var] + cell * (int64_t)P.var_stride[var] + P.var_off[var];
+}
+
+__device__ __forceinline__ double ld_u(const sfxm_problem_t &P, const View &v, int64_t cell, int var) {
+  double val = __ldg(v.y + flat_index(P, cell, var) * P.batch + v.m);
+  if (cell == v.pc && var == v.pv) val = val + v.eps;   // current_value + epsilon, simulation.py:337
+  return val;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ghost cells (bc.py:6-159).  Ghost g = 0 is the one nearest the interior (domain.py:167-177).
+// ------------------------------------------------------------------------------------------------
+// position an outflow/neumann/dirichlet variable writes before it computes its value
+__device__ __forceinline__ double mirror_x_left(const sfxm_problem_t &P, const double *x, int g) {
+  return P.xmin - (__ldg(x + g + 1) - P.xmin);                       // bc.py:72-73, 113-114, 140-141
+}
+__device__ __forceinline__ double mirror_x_right(const sfxm_problem_t &P, const double *x, int g) {
+  return P.xmax + (P.xmax - __ldg(x + P.nx - 2 - g));                // bc.py:86-87, 126-127, 150-151
+}
+// position finally stored in the (shared) ghost cell: the last variable in `bcs` order wins
+__device__ __forceinline__ double ghost_x_left(const sfxm_problem_t &P, const double *x, int g) {
+  if (P.gx_left == SFXM_GX_PERIODIC) return P.xmin - (P.xmax - __ldg(x + P.nx - 2 - g));   // bc.py:55-56
+  if (P.gx_left == SFXM_GX_MIRROR) return mirror_x_left(P, x, g);
+  return P.gx_keep_left[g];
+}
+__device__ __forceinline__ double ghost_x_right(const sfxm_problem_t &P, const double *x, int g) {
+  if (P.gx_right == SFXM_GX_PERIODIC) return P.xmax + (__ldg(x + g + 1) - P.xmin);         // bc.py:63-64
+  if (P.gx_right == SFXM_GX_MIRROR) return mirror_x_right(P, x, g);
+  return P.gx_keep_right[g];
+}
+
+__device__ inline double ghost_u_left(const sfxm_problem_t &P, const View &v, int g, int j) {
+  const int t = P.bc_ltype[j];
+  if (t == SFXM_BC_PERIODIC) return ld_u(P, v, P.nx - 1 - g, j);            // bc.py:57
+  if (t == SFXM_BC_DIRICHLET || t == SFXM_BC_KEEP) return P.bc_lval[j][g];  // bc.py:143
+  const double u0 = ld_u(P, v, 0, j);
+  double slope;
+  if (t == SFXM_BC_NEUMANN) {
+    slope = P.bc_lval[j][0];                                                // bc.py:110
+  } else {                                                                  // outflow, bc.py:75-76
+    const double dy = ld_u(P, v, 1, j) - u0;
+    const double dx = __ldg(v.x + 1) - __ldg(v.x);
+    slope = dy / dx;
+  }
+  double prev = u0, px = __ldg(v.x), val = u0;
+  for (int i = 0; i <= g; ++i) {                                            // bc.py:77-80, 116-119
+    const double xg = mirror_x_left(P, v.x, i);
+    val = prev - slope * (px - xg);
+    prev = val;
+    px = xg;
+  }
+  return val;
+}
+
+__device__ inline double ghost_u_right(const sfxm_problem_t &P, const View &v, int g, int j) {
+  const int t = P.bc_rtype[j];
+  if (t == SFXM_BC_PERIODIC) return ld_u(P, v, g, j);                       // bc.py:65
+  if (t == SFXM_BC_DIRICHLET || t == SFXM_BC_KEEP) return P.bc_rval[j][g];  // bc.py:153
+  const int64_t ihi = P.nx - 1;
+  const double uh = ld_u(P, v, ihi, j);
+  double slope;
+  if (t == SFXM_BC_NEUMANN) {
+    slope = P.bc_rval[j][0];                                                // bc.py:123
+  } else {                                                                  // outflow, bc.py:89-90
+    const double dy = uh - ld_u(P, v, ihi - 1, j);
+    const double dx = __ldg(v.x + ihi) - __ldg(v.x + ihi - 1);
+    slope = dy / dx;
+  }
+  double prev = uh, px = __ldg(v.x + ihi), val = uh;
+  for (int i = 0; i <= g; ++i) {                                            // bc.py:91-94, 129-132
+    const double xg = mirror_x_right(P, v.x, i);
+    val = prev + slope * (xg - px);
+    prev = val;
+    px = xg;
+  }
+  return val;
+}
+
+// stencil slot s of cell i -> position and values (system.py:58-61: cells[i - nbl .. i + nbr])
+template <int NV>
+__device__ __forceinline__ void load_slot(const sfxm_problem_t &P, const View &v, int64_t pos, double &xs,
+                                          double (&u)[NV]) {
+  if (pos < 0) {
+    const int g = (int)(-pos - 1);
+    xs = ghost_x_left(P, v.x, g);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) u[j] = ghost_u_left(P, v, g, j);
+  } else if (pos >= P.nx) {
+    const int g = (int)(pos - P.nx);
+    xs = ghost_x_right(P, v.x, g);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) u[j] = ghost_u_right(P, v, g, j);
+  } else {
+    xs = __ldg(v.x + pos);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) u[j] = ld_u(P, v, pos, j);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Models: F (advective flux), D (diffusive quantity), spectral radius of dFdU.  S = 0 for all three.
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+struct ModelAD {   // models/advection_diffusion.py:28-31 ; params = (c, nu)
+  static constexpr int kParams = 2;
+  static constexpr bool kDiagonalDFDU = true;
+  static constexpr bool kHasDiffusion = true;
+  __device__ __forceinline__ static void F(const double *p, const double (&u)[NV], double (&f)[NV]) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) f[j] = p[0] * u[j];
+  }
+  __device__ __forceinline__ static void D(const double *p, const double (&u)[NV], double (&d)[NV]) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) d[j] = p[1] * u[j];
+  }
+  // max |eigvals(diag(c))| = |c| exactly (flux.pyx:98-99)
+  __device__ __forceinline__ static double sigma(const double *p, const double (&)[NV]) { return fabs(p[0]); }
+  __device__ __forceinline__ static double eig(const double *p, const double (&)[NV], int) { return p[0]; }
+};
+
+// one real root of l^3 - t l^2 + m l - d, polished; then deflation -> max modulus of the three roots
+__device__ inline double spectral_radius_cubic(double t, double m, double d) {
+  const double third = 1.0 / 3.0;
+  const double sh = t * third;
+  const double p = m - t * t * third;
+  const double q = -2.0 * sh * sh * sh + sh * m - d;
+  const double disc = 0.25 * q * q + p * p * p / 27.0;
+  double z;
+  if (disc > 0.0) {
+    const double sq = sqrt(disc);
+    z = cbrt(-0.5 * q + sq) + cbrt(-0.5 * q - sq);
+  } else if (p < 0.0) {
+    const double rr = sqrt(-p * third);
+    double arg = 1.5 * q / (p * rr);
+    arg = fmin(1.0, fmax(-1.0, arg));
+    z = 2.0 * rr * cos(acos(arg) * third);
+  } else {
+    z = 0.0;
+  }
+  double l1 = z + sh;
+  for (int it = 0; it < 3; ++it) {   // Newton polish on the characteristic polynomial
+    const double f = ((l1 - t) * l1 + m) * l1 - d;
+    const double fp = (3.0 * l1 - 2.0 * t) * l1 + m;
+    if (fp != 0.0) l1 -= f / fp;
+  }
+  const double b = l1 - t;          // (l - l1)(l^2 + b l + c)
+  const double c = m + l1 * b;
+  const double dq = b * b - 4.0 * c;
+  double other;
+  if (dq < 0.0) {
+    other = sqrt(fmax(c, 0.0));     // complex pair: |l|^2 = c
+  } else {
+    const double s = sqrt(dq);
+    other = fmax(fabs(0.5 * (-b + s)), fabs(0.5 * (-b - s)));
+  }
+  return fmax(fabs(l1), other);
+}
+
+struct ModelEulerPrim {   // tutorials/sod_shock/euler1d.py:27-50 ; params = (gamma); W = (rho, u, p)
+  static constexpr int kParams = 1;
+  static constexpr bool kDiagonalDFDU = false;
+  static constexpr bool kHasDiffusion = false;
+  __device__ __forceinline__ static void F(const double *pr, const double (&w)[3], double (&f)[3]) {
+    const double g = pr[0], rho = w[0], u = w[1], p = w[2];
+    const double u2 = u * u;
+    const double E = p / (g - 1.0) + 0.5 * rho * u2;
+    f[0] = rho * u;
+    f[1] = rho * u2 + p;
+    f[2] = u * (E + p);
+  }
+  __device__ __forceinline__ static void D(const double *, const double (&)[3], double (&d)[3]) {
+    d[0] = d[1] = d[2] = 0.0;
+  }
+  // max |eigvals(dF/dW)| - LAPACK dgeev in the reference (flux.pyx:98-99); closed-form cubic here
+  __device__ __forceinline__ static double sigma(const double *pr, const double (&w)[3]) {
+    const double g = pr[0], rho = w[0], u = w[1], p = w[2];
+    const double u2 = u * u;
+    const double a00 = u, a01 = rho;                                   // a02 = 0
+    const double a10 = u2, a11 = 2.0 * rho * u, a12 = 1.0;
+    const double a20 = 0.5 * (u2 * u), a21 = 1.5 * rho * u2 + g * p / (g - 1.0), a22 = g * u / (g - 1.0);
+    const double t = a00 + a11 + a22;
+    const double m = (a00 * a11 - a01 * a10) + (a00 * a22) + (a11 * a22 - a12 * a21);
+    const double d = a00 * (a11 * a22 - a12 * a21) - a01 * (a10 * a22 - a12 * a20);
+    return spectral_radius_cubic(t, m, d);
+  }
+  __device__ __forceinline__ static double eig(const double *, const double (&)[3], int) { return 0.0; }
+};
+
+struct ModelEulerCons {   // tutorials/conservative_sod_shock/euler1d.py:28-63 ; params = (gamma)
+  static constexpr int kParams = 1;
+  static constexpr bool kDiagonalDFDU = false;
+  static constexpr bool kHasDiffusion = false;
+  __device__ __forceinline__ static void F(const double *pr, const double (&U)[3], double (&f)[3]) {
+    const double g = pr[0], U1 = U[0], U2 = U[1], U3 = U[2];
+    f[0] = U2;
+    f[1] = 0.5 * (3.0 - g) * (U2 * U2) / U1 + (g - 1.0) * U3;
+    f[2] = g * U2 * U3 / U1 - 0.5 * (g - 1.0) * ((U2 * U2 * U2) / (U1 * U1));
+  }
+  __device__ __forceinline__ static void D(const double *, const double (&)[3], double (&d)[3]) {
+    d[0] = d[1] = d[2] = 0.0;
+  }
+  // eigenvalues of dF/dU are u, u +- a: spectral radius |u| + a (LAPACK in the reference, flux.pyx:98-99;
+  // agreement ~1e-15 relative)
+  __device__ __forceinline__ static double sigma(const double *pr, const double (&U)[3]) {
+    const double g = pr[0];
+    const double u = U[1] / U[0];
+    const double p = (g - 1.0) * (U[2] - 0.5 * U[1] * u);
+    return fabs(u) + sqrt(g * p / U[0]);
+  }
+  __device__ __forceinline__ static double eig(const double *, const double (&)[3], int) { return 0.0; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Per-cell residual (fv_transport.py:49-58, fd_transport.py:46-50, flux.pyx, derivatives.pyx)
+// u[s][j], xs[s] : stencil slots s = 0..W-1 (slot nbl is the centre for the FV schemes, fv_transport.py:49)
+// ------------------------------------------------------------------------------------------------
+template <class Model, int SCHEME, int NV, int W>
+__device__ __forceinline__ void cell_residual(const double *prm, const double (&u)[W][NV], const double (&xs)[W],
+                                              double (&r)[NV]) {
+  if constexpr (SCHEME == SFXM_FV_LAX_FRIEDRICHS || SCHEME == SFXM_FV_CENTRAL || SCHEME == SFXM_FV_UPWIND) {
+    static_assert(W == 3 || SCHEME > SFXM_FV_UPWIND, "FV schemes use a 3-cell stencil");
+    const double dxw = xs[1] - xs[0];
+    const double dxe = xs[2] - xs[1];
+    const double dx = 0.5 * (dxw + dxe);                    // fv_transport.py:50-52
+    const double inv = 1.0 / dx;                            // fv_transport.py:58 "(1 / dx)"
+    double Fl[NV], Fc[NV], Fr[NV], Fw[NV], Fe[NV];
+    Model::F(prm, u[0], Fl);
+    Model::F(prm, u[1], Fc);
+    Model::F(prm, u[2], Fr);
+    if constexpr (SCHEME == SFXM_FV_LAX_FRIEDRICHS) {
+      const double hs = 0.5 * Model::sigma(prm, u[1]);      // flux.pyx:98-99, "0.5 * sigma * u_diff"
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        Fw[j] = 0.5 * (Fl[j] + Fc[j]) - hs * (u[1][j] - u[0][j]);   // flux.pyx:154-160
+        Fe[j] = 0.5 * (Fc[j] + Fr[j]) - hs * (u[2][j] - u[1][j]);   // flux.pyx:163-167
+      }
+    } else if constexpr (SCHEME == SFXM_FV_CENTRAL) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        Fw[j] = 0.5 * (Fl[j] + Fc[j]);                      // flux.pyx:253-255
+        Fe[j] = 0.5 * (Fc[j] + Fr[j]);
+      }
+    } else {                                                // UPWIND, diagonal dFdU only (R = I)
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const bool pos = Model::eig(prm, u[1], j) > 0.0;    // flux.pyx:209-218
+        Fw[j] = pos ? Fl[j] : Fc[j];
+        Fe[j] = pos ? Fc[j] : Fr[j];
+      }
+    }
+    if constexpr (Model::kHasDiffusion) {
+      double Dl[NV], Dc[NV], Dr[NV];
+      Model::D(prm, u[0], Dl);
+      Model::D(prm, u[1], Dc);
+      Model::D(prm, u[2], Dr);
+      const double hw = 0.5 * (xs[1] - xs[0]);              // flux.pyx:285 (note the 0.5)
+      const double he = 0.5 * (xs[2] - xs[1]);              // flux.pyx:294
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const double DFw = (Dc[j] - Dl[j]) / hw;
+        const double DFe = (Dr[j] - Dc[j]) / he;
+        r[j] = (0.0 - inv * (Fe[j] - Fw[j])) + inv * (DFe - DFw);   // fv_transport.py:58
+      }
+    } else {
+      // D == 0: (Dc-Dl)/hw = +0, DFe-DFw = +0, inv*0 = 0, and a + 0 = a
+#pragma unroll
+      for (int j = 0; j < NV; ++j) r[j] = (0.0 - inv * (Fe[j] - Fw[j])) + 0.0;
+    }
+  } else if constexpr (SCHEME == SFXM_FD_CENTRAL) {
+    double Fl[NV], Fr[NV];
+    Model::F(prm, u[0], Fl);
+    Model::F(prm, u[2], Fr);
+    const double dx2 = xs[2] - xs[0];                       // derivatives.pyx:78
+    const double dxw = xs[1] - xs[0];                       // derivatives.pyx:99
+    const double dxe = xs[2] - xs[1];                       // derivatives.pyx:106
+    const double dxm = (dxw + dxe) / 2.0;                   // derivatives.pyx:111
+    double Dl[NV], Dc[NV], Dr[NV];
+    Model::D(prm, u[0], Dl);
+    Model::D(prm, u[1], Dc);
+    Model::D(prm, u[2], Dr);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const double dF = (Fr[j] - Fl[j]) / dx2;
+      double d2 = 0.0;
+      if constexpr (Model::kHasDiffusion) {
+        const double Dw = (Dc[j] - Dl[j]) / dxw;
+        const double De = (Dr[j] - Dc[j]) / dxe;
+        d2 = (De - Dw) / dxm;
+      }
+      r[j] = (0.0 - dF) + d2;                               // fd_transport.py:46-50
+    }
+  } else {                                                  // FD RIGHT_BIAS, 4 slots
+    static_assert(W == 4 || SCHEME != SFXM_FD_RIGHT_BIAS, "RIGHT_BIAS uses a 4-cell stencil");
+    double F0[NV], F1[NV], F2[NV], F3[NV];
+    Model::F(prm, u[0], F0);
+    Model::F(prm, u[1], F1);
+    Model::F(prm, u[2], F2);
+    Model::F(prm, u[W - 1], F3);
+    const double h = xs[1] - xs[0];                         // only the first spacing, derivatives.pyx:89,120
+    const double den1 = 4.0 * h;
+    const double den2 = 2.0 * (h * h);
+    double D0[NV], D1[NV], D2[NV], D3[NV];
+    Model::D(prm, u[0], D0);
+    Model::D(prm, u[1], D1);
+    Model::D(prm, u[2], D2);
+    Model::D(prm, u[W - 1], D3);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const double dF = (((-F0[j] - F1[j]) + F2[j]) + F3[j]) / den1;      // derivatives.pyx:88-90
+      double d2 = 0.0;
+      if constexpr (Model::kHasDiffusion) d2 = (((D0[j] - D1[j]) - D2[j]) + D3[j]) / den2;   // :119-121
+      r[j] = (0.0 - dF) + d2;
+    }
+  }
+}
+
+}  // namespace sfxm

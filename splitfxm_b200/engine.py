@@ -1,0 +1,224 @@
+"""Device engine: one mesh, one model, ``batch`` ensemble members - tensors in HBM plus the C-ABI calls.
+
+Both front ends sit on it: ``Simulation`` (batch = 1, the reference's API) and ``EnsembleSimulation``
+(batch = many independent members, no reference equivalent).  PyTorch is used for memory, streams and the
+tiny per-member control vectors only; all arithmetic on the state is in csrc/*.cu.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .error import SFXM
+
+
+def split_segments(nv, split, split_locs):
+    """[(offset, size)] of the variable segments (simulation.py:126-140, 183-196)."""
+    if not split:
+        return [(0, nv)]
+    if split_locs is None:
+        raise SFXM("Split location must be specified in this case")
+    locs = sorted(set(int(s) for s in split_locs))
+    if len(locs) == 0:
+        raise SFXM("Split location must be specified in this case")
+    if locs[-1] > nv or locs[0] < 0:
+        raise SFXM("Split locations must be between 0 and nv-1")
+    edges = [0] + locs + [nv]
+    return [(edges[k], edges[k + 1] - edges[k]) for k in range(len(edges) - 1)]
+
+
+def flat_index_table(nx, nv, segs):
+    """idx[p, j] = position of unknown (cell p, variable j) in the flat vector."""
+    idx = np.empty((nx, nv), dtype=np.int64)
+    for (o, s) in segs:
+        for j in range(o, o + s):
+            idx[:, j] = o * nx + np.arange(nx, dtype=np.int64) * s + (j - o)
+    return idx
+
+
+class Engine:
+    def __init__(self, model_id, scheme_id, nv, nbl, nbr, x_int, xmin, xmax, params, batch=1, device=None):
+        if not torch.cuda.is_available():
+            raise SFXM("splitfxm_b200 needs a CUDA device (there is no CPU fallback)")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.nv, self.nbl, self.nbr = int(nv), int(nbl), int(nbr)
+        self.W = self.nbl + self.nbr + 1
+        self.batch = int(batch)
+        self.model_id, self.scheme_id = int(model_id), int(scheme_id)
+        self.xmin, self.xmax = float(xmin), float(xmax)
+        self.set_mesh(x_int)
+        self.set_params(params)
+        self._bc_filler = None
+        self._probs = {}
+        self._work = {}
+
+    # -- configuration -------------------------------------------------------------------------------
+    def set_mesh(self, x_int):
+        x_int = np.ascontiguousarray(x_int, dtype=np.float64)
+        self.nx = int(x_int.shape[0])
+        self.n = self.nx * self.nv
+        self.x_int = torch.from_numpy(x_int).to(self.device)
+        self._probs = {}
+        self._work = {}
+
+    def set_params(self, params):
+        """params: [n_params] (shared) or [n_params, batch] (per member)."""
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        if p.ndim == 1:
+            self.param_stride = 0
+        elif p.ndim == 2 and p.shape[1] == self.batch:
+            self.param_stride = self.batch
+        else:
+            raise SFXM("params must be [n_params] or [n_params, batch]")
+        self.n_params = int(p.shape[0])
+        self.params = torch.from_numpy(p).to(self.device)
+
+    def set_bcs(self, filler):
+        """filler(prob) writes the BC part of a descriptor (bc.describe_bcs)."""
+        self._bc_filler = filler
+        self._probs = {}
+
+    def problem(self, split=False, split_locs=None):
+        key = (bool(split), tuple(sorted(set(split_locs))) if (split and split_locs is not None) else None)
+        hit = self._probs.get(key)
+        if hit is not None:
+            return hit
+        segs = split_segments(self.nv, split, split_locs)
+        P = _lib.Problem()
+        P.model, P.scheme = self.model_id, self.scheme_id
+        P.nv, P.nbl, P.nbr = self.nv, self.nbl, self.nbr
+        P.n_params = self.n_params
+        P.nx, P.batch = self.nx, self.batch
+        P.xmin, P.xmax = self.xmin, self.xmax
+        for k, (o, s) in enumerate(segs):
+            for j in range(o, o + s):
+                P.var_base[j] = o * self.nx
+                P.var_stride[j] = s
+                P.var_off[j] = j - o
+                P.var_seg[j] = k
+        if self._bc_filler is None:
+            raise SFXM("boundary conditions not set")
+        self._bc_filler(P)
+        self._probs[key] = (P, segs)
+        return P, segs
+
+    # -- memory ----------------------------------------------------------------------------------------
+    def empty_state(self):
+        return torch.empty((self.n, self.batch), dtype=torch.float64, device=self.device)
+
+    def to_device(self, l):
+        """Host flat vector [n] (batch 1) or [n, batch] -> device [n, batch]."""
+        a = np.ascontiguousarray(l, dtype=np.float64)
+        if a.ndim == 1:
+            if self.batch != 1:
+                raise SFXM("state must be [n, batch]")
+            a = a.reshape(-1, 1)
+        if a.shape != (self.n, self.batch):
+            raise SFXM("List length not aligned with interior size")
+        return torch.from_numpy(a).to(self.device)
+
+    def jacobian_buffer(self):
+        buf = self._work.get("J")
+        if buf is None:
+            buf = torch.zeros((self.nx, self.W, self.nv, self.nv, self.batch), dtype=torch.float64, device=self.device)
+            self._work["J"] = buf
+        return buf
+
+    def _scratch(self, name, numel, dtype=torch.float64):
+        buf = self._work.get(name)
+        if buf is None or buf.numel() < numel:
+            buf = torch.empty(max(int(numel), 1), dtype=dtype, device=self.device)
+            self._work[name] = buf
+        return buf
+
+    # -- C-ABI calls -----------------------------------------------------------------------------------
+    def residual(self, y, out=None, split=False, split_locs=None, y_out=None, dt=0.0):
+        P, _ = self.problem(split, split_locs)
+        if out is None and y_out is None:
+            out = torch.empty_like(y)
+        _lib.check(self.lib.sfxm_residual(ctypes.byref(P), _lib.ptr(self.x_int), _lib.ptr(self.params), self.param_stride,
+                                          _lib.ptr(y), _lib.ptr(out), _lib.ptr(y_out), float(dt), _lib.stream_ptr()))
+        _lib.count()
+        return out
+
+    def euler_step(self, y, y_out, dt, split=False, split_locs=None):
+        """y_out = y + dt * f(y) in one launch (simulation.py:455-463)."""
+        self.residual(y, None, split, split_locs, y_out=y_out, dt=dt)
+        return y_out
+
+    def fill_domain(self, y, split=False, split_locs=None):
+        """-> (x_all [ntot], U_all [ntot, nv, batch]) with ghosts, on the device."""
+        P, _ = self.problem(split, split_locs)
+        ntot = self.nx + self.nbl + self.nbr
+        x_all = torch.empty(ntot, dtype=torch.float64, device=self.device)
+        U_all = torch.empty((ntot, self.nv, self.batch), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.sfxm_fill_domain(ctypes.byref(P), _lib.ptr(self.x_int), _lib.ptr(y), _lib.ptr(x_all),
+                                             _lib.ptr(U_all), _lib.stream_ptr()))
+        _lib.count()
+        return x_all, U_all
+
+    def jacobian(self, y, split=False, split_locs=None, eps=1e-8, J=None, r0=None):
+        P, _ = self.problem(split, split_locs)
+        if J is None:
+            J = self.jacobian_buffer()
+        _lib.check(self.lib.sfxm_jacobian(ctypes.byref(P), _lib.ptr(self.x_int), _lib.ptr(self.params), self.param_stride,
+                                          _lib.ptr(y), float(eps), _lib.ptr(J), _lib.ptr(r0), _lib.stream_ptr()))
+        _lib.count()
+        return J
+
+    def solve(self, J, f, s, split=False, split_locs=None, seg_lo=0, seg_hi=None, shift=None, active=None, status=None):
+        """(J_seg + shift I) s = -f for segments [seg_lo, seg_hi)."""
+        P, segs = self.problem(split, split_locs)
+        if seg_hi is None:
+            seg_hi = len(segs)
+        nbytes = self.lib.sfxm_solve_workspace_bytes(ctypes.byref(P))
+        work = self._scratch("solve", nbytes // 8)
+        _lib.check(self.lib.sfxm_block_tridiag_solve(ctypes.byref(P), _lib.ptr(J), _lib.ptr(f), _lib.ptr(shift),
+                                                     _lib.ptr(active), int(seg_lo), int(seg_hi), _lib.ptr(s),
+                                                     _lib.ptr(work), _lib.ptr(status), _lib.stream_ptr()))
+        _lib.count(seg_hi - seg_lo)
+        return s
+
+    def sumsq(self, v, lo=0, hi=None, out=None):
+        if hi is None:
+            hi = self.n
+        if out is None:
+            out = torch.empty(self.batch, dtype=torch.float64, device=self.device)
+        nbytes = self.lib.sfxm_sumsq_workspace_bytes(hi - lo, self.batch)
+        work = self._scratch("sumsq", nbytes // 8)
+        _lib.check(self.lib.sfxm_sumsq(_lib.ptr(v), int(lo), int(hi), self.batch, _lib.ptr(out), _lib.ptr(work),
+                                       _lib.stream_ptr()))
+        _lib.count(2)
+        return out
+
+    def axpy(self, y, s, alpha=None, active=None, lo=0, hi=None):
+        if hi is None:
+            hi = self.n
+        _lib.check(self.lib.sfxm_axpy_masked(_lib.ptr(y), _lib.ptr(s), _lib.ptr(alpha), _lib.ptr(active), int(lo), int(hi),
+                                             self.batch, _lib.stream_ptr()))
+        _lib.count()
+        return y
+
+    # -- export ---------------------------------------------------------------------------------------
+    def jacobian_coo(self, J_host, split=False, split_locs=None):
+        """Banded J (host array [nx, W, nv, nv], one member) -> (rows, cols, vals) in the reference's index
+        convention (simulation.py:357-392): exact zeros dropped (lil_matrix never stores them), split mode keeps
+        same-segment entries only."""
+        _, segs = self.problem(split, split_locs)
+        nx, nv, W, nbl = self.nx, self.nv, self.W, self.nbl
+        idx = flat_index_table(nx, nv, segs)
+        seg_of = np.empty(nv, dtype=np.int64)
+        for k, (o, s) in enumerate(segs):
+            seg_of[o:o + s] = k
+        i = np.arange(nx)[:, None, None, None]
+        d = np.arange(W)[None, :, None, None]
+        r = np.arange(nv)[None, None, :, None]
+        c = np.arange(nv)[None, None, None, :]
+        pcol = (i + d - nbl) % nx
+        rows = np.broadcast_to(idx[i, r], J_host.shape)
+        cols = idx[pcol, c]
+        cols = np.broadcast_to(cols, J_host.shape)
+        keep = (J_host != 0.0) & np.broadcast_to(seg_of[r] == seg_of[c], J_host.shape)
+        return rows[keep], cols[keep], J_host[keep]

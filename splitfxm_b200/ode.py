@@ -1,0 +1,174 @@
+"""Time stepping on the device for Simulation.evolve (reference: simulation.py:396-472).
+
+* ``euler``   - the reference's hand-rolled loop (simulation.py:455-463), one fused residual+update launch
+                per step; reproduces the float-accumulated ``t`` (a trailing tiny step can occur).
+* ``rk45``    - scipy.integrate.solve_ivp(method='RK45', t_eval=[t_diff]) restated step for step
+                (scipy/integrate/_ivp/rk.py, common.py: select_initial_step, rk_step, error control with
+                SAFETY 0.9 / MIN_FACTOR 0.2 / MAX_FACTOR 10, dense output at the end point).  rtol/atol are
+                scipy's defaults 1e-3/1e-6 because the reference never forwards its own (simulation.py:468-469).
+
+The state and the 7 stage vectors stay in HBM; per attempted step the host reads back one scalar (the error
+norm).  Single-mesh control (batch members advance in lock-step only for Euler).
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .error import SFXM
+
+SAFETY, MIN_FACTOR, MAX_FACTOR = 0.9, 0.2, 10.0
+
+
+def _tableau():
+    from scipy.integrate._ivp.rk import RK45
+    return (np.ascontiguousarray(RK45.A, dtype=np.float64), np.ascontiguousarray(RK45.B, dtype=np.float64),
+            np.ascontiguousarray(RK45.C, dtype=np.float64), np.ascontiguousarray(RK45.E, dtype=np.float64),
+            np.ascontiguousarray(RK45.P, dtype=np.float64))
+
+
+def _dptr(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def euler(eng, y, t_diff, max_step, split=False, split_locs=None, on_step=None):
+    """y <- y after t_diff; returns (y, nfev).  simulation.py:455-463."""
+    t_current = 0.0
+    nfev = 0
+    other = torch.empty_like(y)
+    while t_current < t_diff:
+        delta_t = min(t_diff - t_current, max_step)
+        eng.euler_step(y, other, delta_t, split, split_locs)
+        y, other = other, y
+        nfev += 1
+        if on_step is not None:
+            on_step(y, t_current)
+        t_current += delta_t
+    return y, nfev
+
+
+class RK45Stepper:
+    def __init__(self, eng, split=False, split_locs=None, rtol=1e-3, atol=1e-6, max_step=np.inf):
+        if eng.batch != 1:
+            raise SFXM("adaptive RK45 drives one mesh; ensembles use Euler stepping or per-member Simulations")
+        if max_step <= 0:
+            raise ValueError("`max_step` must be positive.")
+        self.eng, self.split, self.split_locs = eng, split, split_locs
+        self.rtol, self.atol, self.max_step = float(rtol), float(atol), float(max_step)
+        self.A, self.Bc, self.C, self.E, self.P = _tableau()
+        self.n = eng.n
+        self.total = eng.n * eng.batch
+        dev = eng.device
+        self.K = torch.empty((7, eng.n, eng.batch), dtype=torch.float64, device=dev)
+        self.ytmp = torch.empty((eng.n, eng.batch), dtype=torch.float64, device=dev)
+        self.out1 = torch.empty(eng.batch, dtype=torch.float64, device=dev)
+        nbytes = eng.lib.sfxm_scaled_sumsq_workspace_bytes(eng.n, eng.batch)
+        self.work = torch.empty(max(nbytes // 8, 1), dtype=torch.float64, device=dev)
+        self.nfev = 0
+
+    def f(self, y, out):
+        self.eng.residual(y, out, self.split, self.split_locs)
+        self.nfev += 1
+
+    def _rms(self, a, a2, b):
+        """scipy common.norm((a - a2) / (atol + |b| rtol))."""
+        eng = self.eng
+        _lib.check(eng.lib.sfxm_scaled_diff_sumsq(_lib.ptr(a), _lib.ptr(a2), _lib.ptr(b), self.atol, self.rtol, eng.n,
+                                                  eng.batch, _lib.ptr(self.out1), _lib.ptr(self.work), _lib.stream_ptr()))
+        _lib.count(2)
+        return math.sqrt(float(self.out1[0])) / eng.n ** 0.5
+
+    def _lincomb(self, y, coef, nstage, h, out):
+        eng = self.eng
+        _lib.check(eng.lib.sfxm_rk_lincomb(_lib.ptr(y), _lib.ptr(self.K), self.total, _dptr(coef), nstage, float(h),
+                                           _lib.ptr(out), self.total, _lib.stream_ptr()))
+        _lib.count()
+
+    def select_initial_step(self, y0, t_bound):
+        """common.py select_initial_step (order = 4); uses K[0] = f0 and one more RHS evaluation."""
+        interval_length = abs(t_bound)
+        if interval_length == 0.0:
+            return 0.0
+        f0 = self.K[0]
+        d0 = self._rms(y0, None, y0)
+        d1 = self._rms(f0, None, y0)
+        if d0 < 1e-5 or d1 < 1e-5:
+            h0 = 1e-6
+        else:
+            h0 = 0.01 * d0 / d1
+        h0 = min(h0, interval_length)
+        one = np.array([1.0])
+        self._lincomb(y0, one, 1, h0, self.ytmp)            # y1 = y0 + h0 * f0
+        self.f(self.ytmp, self.K[1])
+        d2 = self._rms(self.K[1], f0, y0) / h0
+        if d1 <= 1e-15 and d2 <= 1e-15:
+            h1 = max(1e-6, h0 * 1e-3)
+        else:
+            h1 = (0.01 / max(d1, d2)) ** (1 / 5)
+        return min(100 * h0, h1, interval_length, self.max_step)
+
+    def integrate(self, y, t_bound):
+        """Advance y (device [n, 1]) from t = 0 to t_bound; returns the dense-output end value like
+        solve_ivp(..., t_eval=[t_bound]).y[:, 0]."""
+        eng = self.eng
+        if t_bound <= 0:
+            raise ValueError("t_diff must be positive")
+        y = y.clone()
+        y_new = torch.empty_like(y)
+        self.f(y, self.K[0])
+        h_abs = self.select_initial_step(y, t_bound)
+        t = 0.0
+        error_exponent = -1 / 5
+        result = None
+        while t != t_bound:
+            min_step = 10 * abs(np.nextafter(t, np.inf) - t)
+            if h_abs > self.max_step:
+                h_abs = self.max_step
+            elif h_abs < min_step:
+                h_abs = min_step
+            step_accepted = False
+            step_rejected = False
+            while not step_accepted:
+                if h_abs < min_step:
+                    raise SFXM("Required step size is less than spacing between numbers.")
+                h = h_abs
+                t_new = t + h
+                if t_new - t_bound > 0:
+                    t_new = t_bound
+                h = t_new - t
+                h_abs = abs(h)
+                # rk_step: K[0] holds f(t, y)
+                for s in range(1, 6):
+                    self._lincomb(y, self.A[s], s, h, self.ytmp)
+                    self.f(self.ytmp, self.K[s])
+                self._lincomb(y, self.Bc, 6, h, y_new)
+                self.f(y_new, self.K[6])
+                _lib.check(eng.lib.sfxm_rk_error_sumsq(_lib.ptr(self.K), self.total, _dptr(self.E), 7, float(h), _lib.ptr(y),
+                                                       _lib.ptr(y_new), self.atol, self.rtol, eng.n, eng.batch,
+                                                       _lib.ptr(self.out1), _lib.ptr(self.work), _lib.stream_ptr()))
+                _lib.count(2)
+                error_norm = math.sqrt(float(self.out1[0])) / eng.n ** 0.5
+                if error_norm < 1:
+                    if error_norm == 0:
+                        factor = MAX_FACTOR
+                    else:
+                        factor = min(MAX_FACTOR, SAFETY * error_norm ** error_exponent)
+                    if step_rejected:
+                        factor = min(1, factor)
+                    h_abs *= factor
+                    step_accepted = True
+                else:
+                    h_abs *= max(MIN_FACTOR, SAFETY * error_norm ** error_exponent)
+                    step_rejected = True
+            if t_new == t_bound:
+                # t_eval = [t_bound] is served by the dense output of the last step, not by y_new
+                result = torch.empty_like(y)
+                _lib.check(eng.lib.sfxm_rk_dense_end(_lib.ptr(y), _lib.ptr(self.K), self.total, _dptr(self.P), 7, float(h),
+                                                     _lib.ptr(result), self.total, _lib.stream_ptr()))
+                _lib.count()
+            t = t_new
+            y, y_new = y_new, y
+            self.K[0].copy_(self.K[6])      # FSAL: f_new becomes f of the next step
+        return result

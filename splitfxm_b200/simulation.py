@@ -1,0 +1,196 @@
+"""Simulation: the reference's solver front end (splitfxm/simulation.py:30-526) over the CUDA engine.
+
+Same constructor, methods, argument meaning and error behaviour as the reference.  Each public call uploads
+the Domain's interior once, runs entirely on the device (ghost fill, residual, Jacobian, linear solves, time
+stepping - csrc/*.cu) and writes the final state, ghosts included, back into the Domain.
+"""
+import math
+
+import numpy as np
+import torch
+from scipy.sparse import coo_matrix
+
+from . import _lib
+from .bc import apply_BC, describe_bcs
+from .constants import btype
+from .domain import Domain
+from .engine import Engine
+from .error import SFXM
+from .initialize import set_initial_condition
+from .model import Model
+from .newton import NewtonDriver
+from .ode import RK45Stepper, euler
+from .refine import Refiner
+from .schemes import FDSchemes, FVSchemes, _scheme_ids, stencil_sizes
+from .simhelper import array_list_reshape, report_bounds
+from .system import System
+
+JAC_REQUIRED = ["Radau", "BDF"]
+
+
+class Simulation:
+    def __init__(self, d: Domain, m: Model, ics: dict, bcs: dict, scheme, scheme_opts: dict = {}, ss: dict = {}):
+        self._d = d
+        self._s = System(m, scheme, scheme_opts)
+        self._r = Refiner()
+        self._bcs = bcs
+        self._ss = ss          # stored and never read by the reference (simulation.py:62); "maxiter" is honoured here
+
+        for c, ictype in ics.items():
+            set_initial_condition(self._d, c, ictype)
+        for c, bctype in self._bcs.items():
+            apply_BC(self._d, c, bctype)
+
+        boundary_cells = self._d.nb(btype.LEFT) + self._d.nb(btype.RIGHT)
+        if stencil_sizes.get(self._s._scheme) != boundary_cells + 1:
+            raise SFXM("Stencil size does not match boundary conditions")
+        self._eng = None
+        self._eng_key = None
+
+    # -- device engine -----------------------------------------------------------------------------------
+    def _engine(self):
+        """Engine for the Domain's current mesh (rebuilt when the mesh size changed, e.g. after AMR)."""
+        d, m = self._d, self._s._model
+        dev = getattr(m, "_device", None)
+        if dev is None:
+            raise SFXM("Model has no device functor: the hot path runs on the GPU only (no CPU fallback). "
+                       "Use splitfxm_b200.models.* or attach a DeviceModel to the model.")
+        scheme = self._s._scheme
+        if (dev.method == "FVM") != isinstance(scheme, FVSchemes):
+            raise SFXM("Scheme family does not match the model's numerical method")
+        if scheme not in _scheme_ids:
+            raise SFXM("Unsupported scheme")
+        x_int = d.interior_x()
+        key = (x_int.shape[0], d.num_components(), d.nb(btype.LEFT), d.nb(btype.RIGHT), _scheme_ids[scheme], dev.model_id)
+        if self._eng is None or self._eng_key != key:
+            self._eng = Engine(dev.model_id, _scheme_ids[scheme], d.num_components(), d.nb(btype.LEFT), d.nb(btype.RIGHT),
+                               x_int, d.xmin(), d.xmax(), dev.params, batch=1)
+            self._eng_key = key
+        else:
+            self._eng.set_mesh(x_int)
+            self._eng.set_params(dev.params)
+        self._eng.set_bcs(lambda P: describe_bcs(P, self._bcs, d))
+        return self._eng
+
+    def _store(self, eng, y, split, split_locs):
+        """Device state -> Domain (interior and ghosts): initialize_from_list + apply_BC (simulation.py:171-175)."""
+        x_all, U_all = eng.fill_domain(y, split, split_locs)
+        self._d._x[:] = x_all.cpu().numpy()
+        self._d._U[:, :] = U_all.cpu().numpy().reshape(self._d._U.shape)
+
+    # -- list related methods (simulation.py:81-264) -----------------------------------------------------
+    def get_shape_from_list(self, l):
+        nv = self._d.num_components()
+        if len(l) % nv != 0:
+            raise SFXM("List length not aligned with interior size")
+        return len(l) // nv, nv
+
+    def _check_split(self, nv, split, split_locs, msg_none, msg_range):
+        if split:
+            if split_locs is None:
+                raise SFXM(msg_none)
+            locs = sorted(set(split_locs))
+            if locs[-1] > nv or locs[0] < 0:
+                raise SFXM(msg_range)
+
+    def initialize_from_list(self, l, split=False, split_locs=None):
+        num_points, nv = self.get_shape_from_list(l)
+        if split:
+            self._check_split(nv, split, split_locs, "Split location must be specified in this case",
+                              "Split locations must be between 0 and nv-1")
+            split_locs = sorted(set(split_locs))
+            l_split = np.split(np.asarray(l), [i * num_points for i in split_locs])
+            block = np.hstack([array_list_reshape(segment, (num_points, -1)) for segment in l_split])
+        else:
+            block = array_list_reshape(l, (num_points, nv))
+        if num_points != self._d._nx:
+            raise SFXM("List length not aligned with interior size")
+        self._d.interior_U()[:, :] = block
+
+    def get_residuals_from_list(self, l, split=False, split_locs=None):
+        num_points, nv = self.get_shape_from_list(l)
+        self._check_split(nv, split, split_locs, "Split location must be specified in this case",
+                          "Split locations must be between 0 and nv-1")
+        eng = self._engine()
+        y = eng.to_device(np.asarray(l, dtype=np.float64))
+        r = eng.residual(y, None, split, split_locs)
+        self._store(eng, y, split, split_locs)
+        return r.cpu().numpy().reshape(-1)
+
+    def extend_bounds(self, bounds, num_points, nv, split=False, split_locs=None):
+        if bounds is None:
+            return None
+        if len(bounds) != 2:
+            raise SFXM("Bounds must be a list of 2 lists")
+        if len(bounds[0]) != nv or len(bounds[1]) != nv:
+            raise SFXM("Each list in bounds must be of length - number of variables")
+        if not split:
+            return [bounds[0] * num_points, bounds[1] * num_points]
+        if split_locs is None:
+            raise SFXM("split_locs must be provided if split is True")
+        split_locs = sorted(set(split_locs))
+        if split_locs[-1] > nv or split_locs[0] < 0:
+            raise SFXM("Split locations must be between 0 and nv-1")
+        lower = np.concatenate([np.tile(seg, num_points) for seg in np.split(bounds[0], split_locs)]).tolist()
+        upper = np.concatenate([np.tile(seg, num_points) for seg in np.split(bounds[1], split_locs)]).tolist()
+        return [lower, upper]
+
+    # -- solution related methods ------------------------------------------------------------------------
+    def jacobian(self, l, split=False, split_locs=None, epsilon=1e-8):
+        """Finite-difference Jacobian as scipy.sparse.lil_matrix (simulation.py:270-394)."""
+        num_points, nv = self.get_shape_from_list(l)
+        if split and split_locs is None:
+            raise SFXM("split_locs must be provided if split is True")
+        self._check_split(nv, split, split_locs, "Split location must be specified in this case",
+                          "Split locations must be between 0 and nv-1")
+        eng = self._engine()
+        y = eng.to_device(np.asarray(l, dtype=np.float64))
+        J = eng.jacobian(y, split, split_locs, epsilon)
+        self._store(eng, y, split, split_locs)
+        Jh = J.cpu().numpy().reshape(eng.nx, eng.W, nv, nv)
+        rows, cols, vals = eng.jacobian_coo(Jh, split, split_locs)
+        n = num_points * nv
+        return coo_matrix((vals, (rows, cols)), shape=(n, n)).tolil()
+
+    def evolve(self, t_diff: float, split=False, split_locs=None, method='RK45', rtol=1e-3, atol=1e-6,
+               max_step=np.inf, bounds=None):
+        """Advance the Domain by t_diff (simulation.py:396-472).  'Euler' and 'RK45' run on the device; like the
+        reference, rtol/atol are accepted but scipy's defaults are what is used (they are never forwarded,
+        simulation.py:468-469)."""
+        y0 = self._d.listify_interior(split, split_locs)
+        num_points, nv = self.get_shape_from_list(y0)
+        ext_bounds = self.extend_bounds(bounds, num_points, nv, split, split_locs)
+        eng = self._engine()
+        y = eng.to_device(y0)
+        if method == "Euler":
+            on_step = None
+            if bounds is not None:
+                def on_step(yd, t):
+                    report_bounds(yd.cpu().numpy().reshape(-1), ext_bounds, t)
+            y, _ = euler(eng, y, t_diff, max_step, split, split_locs, on_step)
+        elif method == "RK45":
+            stepper = RK45Stepper(eng, split, split_locs, 1e-3, 1e-6, max_step)
+            y = stepper.integrate(y, t_diff)
+            if bounds is not None:
+                report_bounds(y.cpu().numpy().reshape(-1), ext_bounds, t_diff)
+        else:
+            raise SFXM(f"evolve method '{method}' is not available on the device path (Euler, RK45)")
+        self._store(eng, y, split, split_locs)
+
+    def steady_state(self, split=False, split_locs=None, sparse=True, dt0=0.0, dtmax=1.0, armijo=False, bounds=None):
+        """Newton / Split-Newton to steady state (simulation.py:474-526); returns the iteration count."""
+        x0 = self._d.listify_interior(split, split_locs)
+        num_points, nv = self.get_shape_from_list(x0)
+        ext_bounds = self.extend_bounds(bounds, num_points, nv, split, split_locs)
+        if split:
+            self._check_split(nv, split, split_locs, "Split location must be specified in this case",
+                              "Split locations must be between 0 and nv-1")
+        eng = self._engine()
+        if eng.W != 3:
+            raise SFXM("steady_state needs a 3-cell stencil (block-tridiagonal Jacobian)")
+        y = eng.to_device(x0)
+        drv = NewtonDriver(eng, split, split_locs, dt0, dtmax, armijo, ext_bounds)
+        maxiter = self._ss.get("maxiter", math.inf) if isinstance(self._ss, dict) else math.inf
+        it = drv.run(y, maxiter)
+        self._store(eng, y, split, split_locs)
+        return int(it[0])

@@ -1,0 +1,107 @@
+"""Linear solves and Newton / Split-Newton on the device against the oracle specification (oracle/newton.py;
+parity unpinned against upstream splitnewton - see that file's header)."""
+import numpy as np
+import pytest
+
+from helpers import load, oracle_problem, product_simulation, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _dense_from_banded(eng, Jh, split, locs):
+    rows, cols, vals = eng.jacobian_coo(Jh, split, locs)
+    n = eng.n
+    A = np.zeros((n, n))
+    A[rows, cols] = vals
+    return A
+
+
+@pytest.mark.parametrize("name,split,locs", [
+    ("ad_fvm_lf_nx40_mixedbc", False, None),          # w periodic on the left only -> cyclic 3x3 blocks
+    ("ad_fvm_lf_nx40_mixedbc", True, [1, 2]),         # three scalar systems, one cyclic
+    ("ad_fdm_central_nonuniform_mixed", True, [2]),   # 2x2 + 1x1 segments on an AMR mesh
+    ("sod_cons_nx60_unsplit_t0p02", False, None),     # dense 3x3 blocks (Euler)
+    ("sod_cons_nx100_t0p05", True, [1]),
+])
+def test_block_tridiag_solve(name, split, locs):
+    import torch
+    z = load(name)
+    s, d, m = product_simulation(z)
+    eng = s._engine()
+    from oracle import core
+    y_host = core.to_flat(core.to_block(z["x0"], m["nx"], len(m["comps"]), m["split"], m["locs"]), split, locs)
+    y = eng.to_device(y_host)
+    r = torch.empty_like(y)
+    J = eng.jacobian(y, split, locs, r0=r)
+    shift = torch.full((1,), -7.5, dtype=torch.float64, device=y.device)
+    sol = torch.zeros_like(y)
+    status = torch.zeros(1, dtype=torch.int32, device=y.device)
+    eng.solve(J, r, sol, split, locs, shift=shift, status=status)
+    A = _dense_from_banded(eng, J.cpu().numpy()[..., 0], split, locs) - 7.5 * np.eye(eng.n)
+    ref = np.linalg.solve(A, -r.cpu().numpy()[:, 0])
+    assert int(status[0]) == 0
+    assert rel_err(sol.cpu().numpy()[:, 0], ref) < 1e-9 * max(1.0, np.linalg.cond(A) * 1e-6)
+
+
+def _well_posed_case():
+    """Advection-diffusion FVM, dirichlet/neumann data (non-singular blocks)."""
+    import splitfxm_b200 as sf
+    from splitfxm_b200.models.advection_diffusion import AdvectionDiffusion
+    comps = ["u", "v", "w"]
+    bcs = {"u": {"left": {"dirichlet": 1.0}, "right": {"dirichlet": 0.0}},
+           "v": {"left": {"dirichlet": 3}, "right": {"dirichlet": 4}},
+           "w": {"left": {"dirichlet": 2}, "right": {"neumann": 0.0}}}
+    ics = {"u": "gaussian", "v": "rarefaction", "w": "tophat"}
+    d = sf.Domain.from_size(40, 1, 1, comps)
+    s = sf.Simulation(d, AdvectionDiffusion(0.2, 0.05, "FVM"), ics, bcs, sf.FVSchemes.LAX_FRIEDRICHS)
+    return s, d, comps, bcs
+
+
+@pytest.mark.parametrize("split,locs,kw", [
+    (False, None, {}),
+    (True, [1, 2], {}),
+    (True, [1], {"dt0": 0.05, "dtmax": 10.0}),
+    (False, None, {"armijo": True}),
+    (True, [2], {"bounds": [[-1.0, -1.0, -1.0], [5.0, 5.0, 5.0]]}),
+])
+def test_steady_state_matches_oracle_spec(split, locs, kw):
+    from oracle import core, newton as onewton
+    s, d, comps, bcs = _well_posed_case()
+    x_all = np.array(d.positions())
+    P = core.Problem(core.AdvectionDiffusion(0.2, 0.05), "FVM", "LAX_FRIEDRICHS", x_all[1:-1], 1, 1, bcs, comps)
+    x0 = d.listify_interior(split, locs)
+    f = lambda u: P.residual(u, split, locs)
+    jac = lambda u: P.jacobian_matrix(u, split, locs)
+    okw = dict(kw)
+    if "bounds" in okw:
+        okw["bounds"] = s.extend_bounds(okw["bounds"], 40, 3, split, locs)
+    if split:
+        xf, _, it_ref = onewton.split_newton(f, jac, x0, [40 * i for i in locs], sparse=True, **okw)
+    else:
+        xf, _, it_ref = onewton.newton(f, jac, x0, sparse=True, **okw)
+    it = s.steady_state(split=split, split_locs=locs, **kw)
+    assert it == it_ref
+    got = d.listify_interior(split, locs)
+    assert rel_err(got, xf) < 1e-10
+    # and it is a steady state
+    assert np.max(np.abs(s.get_residuals_from_list(got, split, locs))) < 1e-6
+
+
+def test_ensemble_newton_members_match_single():
+    import splitfxm_b200 as sf
+    from splitfxm_b200.ensemble import EnsembleSimulation
+    from splitfxm_b200.models.advection_diffusion import AdvectionDiffusion
+    s, d, comps, bcs = _well_posed_case()
+    B = 40
+    cs = np.linspace(0.05, 0.5, B)
+    nus = np.logspace(-2, -1, B)
+    ens = EnsembleSimulation(d, "ad", {"c": cs, "nu": nus}, bcs, sf.FVSchemes.LAX_FRIEDRICHS, method="FVM")
+    x0 = d.listify_interior(True, [1, 2])
+    Y, its = ens.steady_state(np.repeat(x0[:, None], B, axis=1), split=True, split_locs=[1, 2])
+    Y = Y.cpu().numpy()
+    for k in (0, 17, 39):
+        d1 = sf.Domain.from_arrays(d._x, d._U, 1, 1, comps)
+        s1 = sf.Simulation(d1, AdvectionDiffusion(cs[k], nus[k], "FVM"), {}, bcs, sf.FVSchemes.LAX_FRIEDRICHS)
+        it1 = s1.steady_state(split=True, split_locs=[1, 2])
+        assert it1 == int(its[k])
+        assert np.array_equal(d1.listify_interior(True, [1, 2]), Y[:, k])

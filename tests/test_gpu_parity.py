@@ -1,0 +1,122 @@
+"""Parity of the CUDA path (through the Simulation API -> C ABI) with the reference fixtures and the oracle.
+
+Tolerances: advection-diffusion arithmetic is a fixed sequence of IEEE mul/add/div with no fused multiply-adds
+on either side -> BIT-EXACT.  Euler models: 1e-10 relative (north_star); the spectral radius is a closed form
+on the device and LAPACK in the reference.  Jacobian sparsity (row/col indices) is bit-exact everywhere.
+"""
+import numpy as np
+import pytest
+
+from helpers import EVOLVE_CASES, RESIDUAL_CASES, load, oracle_problem, product_simulation, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP = 1e-10
+
+
+@pytest.mark.parametrize("name", RESIDUAL_CASES)
+def test_residual_matches_reference(name):
+    z = load(name)
+    s, d, m = product_simulation(z)
+    r = s.get_residuals_from_list(z["x0"], m["split"], m["locs"])
+    if m["model"] == "ad":
+        assert np.array_equal(r, z["residual"])
+    else:
+        assert rel_err(r, z["residual"]) < TOL_FP
+    # side effect of the call: Domain holds the state with ghosts filled (simulation.py:171-175)
+    x_after = z["x_after"] if "x_after" in z.files else z["x_all"]
+    U_after = z["U_after"] if "U_after" in z.files else z["U_all"]
+    assert np.array_equal(np.array(d.positions()), x_after)
+    assert np.array_equal(d.values(), U_after)
+
+
+@pytest.mark.parametrize("name", RESIDUAL_CASES)
+def test_jacobian_matches_reference(name):
+    z = load(name)
+    s, d, m = product_simulation(z)
+    J = s.jacobian(z["x0"], m["split"], m["locs"]).tocoo()
+    order = np.lexsort((J.col, J.row))
+    rows, cols, vals = J.row[order], J.col[order], J.data[order]
+    if m["model"] == "ad":
+        assert np.array_equal(rows, z["jac_row"]) and np.array_equal(cols, z["jac_col"])
+        assert np.array_equal(vals, z["jac_val"])
+    else:
+        # finite-difference noise: entries are differences of O(1) numbers divided by 1e-8, so a 1e-16
+        # relative change in the residual moves an entry by ~1e-8 absolute; compare on that scale and
+        # compare the pattern on entries that are not pure noise
+        dense_ref = np.zeros(J.shape)
+        dense_ref[z["jac_row"], z["jac_col"]] = z["jac_val"]
+        dense = np.zeros(J.shape)
+        dense[rows, cols] = vals
+        assert np.max(np.abs(dense - dense_ref)) <= 1e-6 * np.max(np.abs(z["jac_val"]))
+        big = np.abs(dense_ref) > 1e-5 * np.max(np.abs(z["jac_val"]))
+        assert np.array_equal(dense[big] != 0, dense_ref[big] != 0)
+
+
+@pytest.mark.parametrize("name", EVOLVE_CASES)
+def test_evolve_matches_reference(name):
+    z = load(name)
+    s, d, m = product_simulation(z, z["x_init"], z["U_init"])
+    s.evolve(float(z["t"]), m["split"], m["locs"], method=str(z["ode_method"]), max_step=float(z["max_step"]))
+    assert np.array_equal(np.array(d.positions()), z["x_all"])
+    tol = 0.0 if str(z["ode_method"]) == "Euler" else 1e-13   # RK stage sums: BLAS dgemv order in scipy
+    assert rel_err(d.values(), z["U_all"]) <= tol
+
+
+@pytest.mark.parametrize("name", ["sod_cons_nx100_t0p05", "sod_cons_nx60_unsplit_t0p02", "sod_prim_nx60_t0p02"])
+def test_sod_evolve_matches_reference(name):
+    z = load(name)
+    s, d, m = product_simulation(z, z["x_init"], z["U_init"])
+    s.evolve(float(z["evolve_t"]), m["split"], m["locs"])
+    assert rel_err(d.values(), z["U_all"]) < TOL_FP
+
+
+def test_ensemble_members_equal_single_runs():
+    """65 members with different (c, nu): every member's residual and Jacobian is bit-identical to a batch-1
+    run with that member's parameters (member-fastest layout, coalesced path)."""
+    import torch
+    from splitfxm_b200.ensemble import EnsembleSimulation
+    from splitfxm_b200.models.advection_diffusion import AdvectionDiffusion
+    import splitfxm_b200 as sf
+    z = load("ad_fvm_lf_nx40_mixedbc")
+    _, _, m = product_simulation(z)
+    B = 65
+    rng = np.random.default_rng(5)
+    cs = rng.uniform(-0.5, 0.5, B)
+    nus = 10.0 ** rng.uniform(-4, -2, B)
+    d = sf.Domain.from_arrays(z["x_all"], z["U_all"], 1, 1, m["comps"])
+    ens = EnsembleSimulation(d, "ad", {"c": cs, "nu": nus}, m["bcs"], sf.FVSchemes.LAX_FRIEDRICHS, method="FVM")
+    Y = np.repeat(z["x0"][:, None], B, axis=1) + 0.01 * rng.standard_normal((z["x0"].shape[0], B))
+    R = ens.residual(Y).cpu().numpy()
+    Jb = ens.jacobian(Y).cpu().numpy()
+    for k in (0, 1, 31, 32, 64):
+        s1 = sf.Simulation(sf.Domain.from_arrays(z["x_all"], z["U_all"], 1, 1, m["comps"]),
+                           AdvectionDiffusion(cs[k], nus[k], "FVM"), {}, m["bcs"], sf.FVSchemes.LAX_FRIEDRICHS)
+        r1 = s1.get_residuals_from_list(Y[:, k])
+        assert np.array_equal(R[:, k], r1)
+        eng = s1._engine()
+        J1 = eng.jacobian(eng.to_device(Y[:, k])).cpu().numpy()[..., 0]
+        assert np.array_equal(Jb[..., k], J1)
+
+
+def test_large_mesh_linearity_and_oracle_sample():
+    """nx = 1e6 (BASELINE shape): advection-diffusion residual is linear in U for fixed dirichlet data = 0, and
+    a window of it equals the oracle on the same inputs."""
+    import splitfxm_b200 as sf
+    from splitfxm_b200.models.advection_diffusion import AdvectionDiffusion
+    from oracle import core
+    nx = 1_000_000
+    comps = ["u", "v", "w"]
+    bcs = {c: {"left": {"dirichlet": 0.0}, "right": {"dirichlet": 0.0}} for c in comps}
+    d = sf.Domain.from_size(nx, 1, 1, comps)
+    s = sf.Simulation(d, AdvectionDiffusion(0.2, 0.001, "FDM"), {}, bcs, sf.FDSchemes.CENTRAL)
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal(nx * 3)
+    b = rng.standard_normal(nx * 3)
+    ra = s.get_residuals_from_list(a)
+    rb = s.get_residuals_from_list(b)
+    rab = s.get_residuals_from_list(a + 2.0 * b)
+    scale = np.max(np.abs(rab))
+    assert np.max(np.abs(rab - (ra + 2.0 * rb))) < 1e-9 * scale
+    P = core.Problem(core.AdvectionDiffusion(0.2, 0.001), "FDM", "CENTRAL", np.linspace(0, 1, nx), 1, 1, bcs, comps)
+    assert np.array_equal(ra, P.residual(a))
