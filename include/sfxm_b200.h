@@ -75,7 +75,13 @@ const char *sfxm_last_error(void);
  * + the split-major re-ordering (:192-200), fused into one launch.
  * If y_out != NULL also writes y_out = y + dt * f(y) (the explicit Euler update, simulation.py:455-463). */
 int sfxm_residual(const sfxm_problem_t *prob, const double *x_int, const double *params, int64_t param_stride,
-                  const double *y, double *r, double *y_out, double dt, void *stream);
+                  const double *geom, const double *y, double *r, double *y_out, double dt, void *stream);
+
+/* Per-cell geometry table geom[SFXM_GEOM_ROWS * nx] (the divisors of the scheme, their reciprocals, 1/dx): it
+ * depends on the mesh and the ghost-position rule only, so an ensemble computes it once per mesh instead of once
+ * per member.  Optional everywhere: pass geom = NULL and each thread derives it from x_int. */
+#define SFXM_GEOM_ROWS 10
+int sfxm_geometry(const sfxm_problem_t *prob, const double *x_int, double *geom, void *stream);
 
 /* Materialise the Domain view: x_all[nbl+nx+nbr], U_all[(nbl+nx+nbr) * nv * batch] (cell-major, unsplit,
  * member-fastest) with ghosts filled.  Replaces initialize_from_list + apply_BC (simulation.py:171-175). */
@@ -87,7 +93,7 @@ int sfxm_fill_domain(const sfxm_problem_t *prob, const double *x_int, const doub
  * same-segment entries only (simulation.py:373-392); the others are left untouched (keep J zero-filled).
  * r0 (optional) receives the unperturbed residual in flat order. */
 int sfxm_jacobian(const sfxm_problem_t *prob, const double *x_int, const double *params, int64_t param_stride,
-                  const double *y, double eps, double *J, double *r0, void *stream);
+                  const double *geom, const double *y, double eps, double *J, double *r0, void *stream);
 
 /* Solve, for every member and every variable segment, (J_seg + shift_m I) s = -f  with the block-tridiagonal
  * (cyclic if wrap slots are non-zero) J from sfxm_jacobian; W must be 3.  `shift` is per member (NULL = 0):
@@ -127,6 +133,26 @@ int sfxm_scaled_diff_sumsq(const double *a, const double *a2, const double *b, d
 int sfxm_rk_error_sumsq(const double *K, int64_t stage_stride, const double *E_host, int32_t nstage, double h,
                         const double *y, const double *y_new, double atol, double rtol, int64_t n, int64_t batch,
                         double *out, double *work, void *stream);
+
+/* ---- adaptive mesh refinement (one mesh, batch = 1): Refiner.refine + perform_changes (refine.py:90-282).
+ * x[n], U[n * nv] cell-major interior.  mark: reductions (min/max of values and slopes per variable,
+ * refine.py:136-153), slope / curvature / grid-ratio / prune flags (:159-227), the adjacent-deletion rule (:231-233)
+ * and the exclusive scans that give every surviving or new cell its output slot; counts_dev[3] = {new size,
+ * inserted, deleted}.  apply: writes the refined mesh (kept cells + midpoints, refine.py:260-282).
+ * flags: copies the decision flags out (loc[n], keep[n], gridpt[n] bytes; comp[SFXM_MAX_NV] ints) for the
+ * reference's stdout report (refine.py:284-312).  `work` is shared by the three calls. ---- */
+int64_t sfxm_refine_workspace_bytes(int64_t n);
+int sfxm_refine_mark(const double *x, const double *U, int64_t n, int32_t nv, double ratio, double slope, double curve,
+                     double prune, double min_range, double min_grid, void *work, int64_t *counts_dev, void *stream);
+int sfxm_refine_flags(const void *work, int64_t n, uint8_t *loc_out, uint8_t *keep_out, uint8_t *gridpt_out,
+                      int32_t *comp_out, void *stream);
+int sfxm_refine_apply(const double *x, const double *U, int64_t n, int32_t nv, const void *work, double *x_out,
+                      double *U_out, void *stream);
+
+/* Device self-test: counts (into *mismatch_dev, a device uint64 the caller zeroes) operands for which the
+ * five-FMA division by a known reciprocal used in the stencil kernels differs from the IEEE quotient.
+ * mode 0 = random operands, mode 1 = adversarial (divisor mantissa all ones/zeros, half-way numerators). */
+int sfxm_selftest_div(int64_t n, uint64_t seed, int32_t mode, uint64_t *mismatch_dev, void *stream);
 
 #ifdef __cplusplus
 }

@@ -43,9 +43,10 @@ _PP = ctypes.POINTER(Problem)
 SIGNATURES = {
     "sfxm_abi_version": (ctypes.c_int, []),
     "sfxm_last_error": (ctypes.c_char_p, []),
-    "sfxm_residual": (ctypes.c_int, [_PP, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_f64, c_vp]),
+    "sfxm_residual": (ctypes.c_int, [_PP, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_f64, c_vp]),
+    "sfxm_geometry": (ctypes.c_int, [_PP, c_vp, c_vp, c_vp]),
     "sfxm_fill_domain": (ctypes.c_int, [_PP, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "sfxm_jacobian": (ctypes.c_int, [_PP, c_vp, c_vp, c_i64, c_vp, c_f64, c_vp, c_vp, c_vp]),
+    "sfxm_jacobian": (ctypes.c_int, [_PP, c_vp, c_vp, c_i64, c_vp, c_vp, c_f64, c_vp, c_vp, c_vp]),
     "sfxm_solve_workspace_bytes": (c_i64, [_PP]),
     "sfxm_block_tridiag_solve": (ctypes.c_int, [_PP, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_sumsq_workspace_bytes": (c_i64, [c_i64, c_i64]),
@@ -57,6 +58,11 @@ SIGNATURES = {
     "sfxm_scaled_diff_sumsq": (ctypes.c_int, [c_vp, c_vp, c_vp, c_f64, c_f64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "sfxm_rk_error_sumsq": (ctypes.c_int, [c_vp, c_i64, ctypes.POINTER(c_f64), c_i32, c_f64, c_vp, c_vp, c_f64, c_f64,
                                            c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "sfxm_refine_workspace_bytes": (c_i64, [c_i64]),
+    "sfxm_refine_mark": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_f64, c_f64, c_f64, c_f64, c_f64, c_f64, c_vp, c_vp, c_vp]),
+    "sfxm_refine_flags": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_refine_apply": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_selftest_div": (ctypes.c_int, [c_i64, ctypes.c_uint64, c_i32, c_vp, c_vp]),
 }
 
 _lib = None

@@ -121,6 +121,42 @@ __device__ __forceinline__ void load_slot(const sfxm_problem_t &P, const View &v
   }
 }
 
+// Whole stencil of cell i for member m.  off[j] = element offset of unknown (i, j) in the flat vectors (the same
+// for y, r and y_out).  Interior cells (no ghost in the stencil) take straight strided loads: one 64-bit multiply
+// per variable, then pointer steps - the general per-slot path costs ~40 integer instructions per slot.
+template <int NV, int W>
+__device__ __forceinline__ bool gather_stencil(const sfxm_problem_t &P, const View &v, int64_t i, bool need_x,
+                                               double (&u)[W][NV], double (&xs)[W], int64_t (&off)[NV]) {
+  const int64_t B = P.batch;
+  const int nbl = (W == 3) ? 1 : P.nbl;   // a 3-cell stencil is always 1 + 1 + 1 (validate())
+  const bool interior = (i >= nbl) && (i + (W - 1 - nbl) < P.nx);
+  int64_t rs[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    rs[j] = (int64_t)P.var_stride[j] * B;
+    off[j] = (P.var_base[j] + P.var_off[j]) * B + v.m + i * rs[j];
+  }
+  if (interior) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const double *p = v.y + (off[j] - nbl * rs[j]);
+#pragma unroll
+      for (int s = 0; s < W; ++s) {
+        u[s][j] = __ldg(p);
+        p += rs[j];
+      }
+    }
+    if (need_x) {
+#pragma unroll
+      for (int s = 0; s < W; ++s) xs[s] = __ldg(v.x + (i - nbl + s));
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < W; ++s) load_slot<NV>(P, v, i - nbl + s, xs[s], u[s]);
+  }
+  return interior;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Models: F (advective flux), D (diffusive quantity), spectral radius of dFdU.  S = 0 for all three.
 // ------------------------------------------------------------------------------------------------
@@ -129,6 +165,10 @@ struct ModelAD {   // models/advection_diffusion.py:28-31 ; params = (c, nu)
   static constexpr int kParams = 2;
   static constexpr bool kDiagonalDFDU = true;
   static constexpr bool kHasDiffusion = true;
+  // every variable obeys the same scalar equation: row r of the Jacobian depends on variable r only, and
+  // perturbing variable c leaves the other rows bit-identical (exact zeros in the reference as well)
+  static constexpr bool kDecoupled = true;
+  using Scalar = ModelAD<1>;
   __device__ __forceinline__ static void F(const double *p, const double (&u)[NV], double (&f)[NV]) {
 #pragma unroll
     for (int j = 0; j < NV; ++j) f[j] = p[0] * u[j];
@@ -184,6 +224,8 @@ struct ModelEulerPrim {   // tutorials/sod_shock/euler1d.py:27-50 ; params = (ga
   static constexpr int kParams = 1;
   static constexpr bool kDiagonalDFDU = false;
   static constexpr bool kHasDiffusion = false;
+  static constexpr bool kDecoupled = false;
+  using Scalar = ModelEulerPrim;
   __device__ __forceinline__ static void F(const double *pr, const double (&w)[3], double (&f)[3]) {
     const double g = pr[0], rho = w[0], u = w[1], p = w[2];
     const double u2 = u * u;
@@ -214,6 +256,8 @@ struct ModelEulerCons {   // tutorials/conservative_sod_shock/euler1d.py:28-63 ;
   static constexpr int kParams = 1;
   static constexpr bool kDiagonalDFDU = false;
   static constexpr bool kHasDiffusion = false;
+  static constexpr bool kDecoupled = false;
+  using Scalar = ModelEulerCons;
   __device__ __forceinline__ static void F(const double *pr, const double (&U)[3], double (&f)[3]) {
     const double g = pr[0], U1 = U[0], U2 = U[1], U3 = U[2];
     f[0] = U2;
@@ -235,18 +279,114 @@ struct ModelEulerCons {   // tutorials/conservative_sod_shock/euler1d.py:28-63 ;
 };
 
 // ------------------------------------------------------------------------------------------------
-// Per-cell residual (fv_transport.py:49-58, fd_transport.py:46-50, flux.pyx, derivatives.pyx)
-// u[s][j], xs[s] : stencil slots s = 0..W-1 (slot nbl is the centre for the FV schemes, fv_transport.py:49)
+// Exact division by a divisor whose reciprocal is already known.
+//
+// The reference divides (flux.pyx:288,297; derivatives.pyx:81,90,102,109,112,121; simulation.py:354), so the
+// parity target is the correctly rounded IEEE quotient.  nvcc expands a/b into ~35 FP64-pipe instructions
+// (reciprocal seed + Newton iterations + fix-up); the divisors here are mesh spacings and the FD epsilon,
+// shared by every perturbation of a cell, so their correctly rounded reciprocals rb = RN(1/b) are computed
+// once and each quotient costs five FMAs: two Markstein correction steps
+//      q1 = RN(q0 + RN(a - q0 b) rb),   q2 = RN(q1 + RN(a - q1 b) rb)
+// The first makes the quotient faithful, the second makes it correctly rounded (Markstein 1990; the residuals
+// a - q b are exact in an FMA).  This holds while nothing under- or overflows, so each thread checks ONCE that
+// its inputs are "sane" - stencil values and parameters zero or within 2^+-120, divisors within 2^+-120: then
+// every numerator (a difference of such values: zero or >= 2^-173) and every quotient stays far inside the
+// normal range - and otherwise (FAST = false instantiation) all its quotients use the IEEE division.
+// sfxm_selftest_div compares the two on random and adversarial operands (tests/test_gpu_div.py).
 // ------------------------------------------------------------------------------------------------
-template <class Model, int SCHEME, int NV, int W>
-__device__ __forceinline__ void cell_residual(const double *prm, const double (&u)[W][NV], const double (&xs)[W],
+// out of line on purpose: inlined, the compiler if-converts the rare path and executes the full IEEE division
+// (MUFU.RCP64H + ~10 DFMA + fix-up) for every quotient, which is what div_known exists to avoid
+static __device__ __noinline__ double div_ieee(double a, double b) { return a / b; }
+
+template <bool FAST>
+__device__ __forceinline__ double div_known(double a, double b, double rb) {
+  if constexpr (!FAST) return div_ieee(a, b);
+  const double q0 = a * rb;
+  const double q1 = __fma_rn(__fma_rn(-q0, b, a), rb, q0);
+  return __fma_rn(__fma_rn(-q1, b, a), rb, q1);
+}
+
+// exponent of v within 2^+-span, or v == 0
+__device__ __forceinline__ bool sane(double v, unsigned span) {
+  const unsigned e = ((unsigned)__double2hiint(v) >> 20) & 0x7ffu;
+  // bitwise, not short-circuit: keeps the check branch-free (integer pipe only)
+  return ((e - (1023u - span)) < 2u * span) | ((((unsigned)__double2hiint(v) << 1) | (unsigned)__double2loint(v)) == 0u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-cell residual (fv_transport.py:49-58, fd_transport.py:46-50, flux.pyx, derivatives.pyx)
+// u[s][j] : stencil slots s = 0..W-1 (slot 1 is the centre for the FV schemes, fv_transport.py:49)
+// Geom    : everything that depends on the positions only (shared by all perturbations of a cell)
+// ------------------------------------------------------------------------------------------------
+template <int SCHEME, int W>
+struct Geom {
+  double d[4];    // divisors, in the order the reference forms them
+  double rd[4];   // RN(1 / d[k])
+  double inv;     // FV: 1 / dx (the reference multiplies by it, fv_transport.py:58)
+  bool fast;      // divisors sane (and, once and_inputs() was called, the stencil values too): use div_known's FMAs
+  __device__ __forceinline__ explicit Geom(const double (&xs)[W]) {
+    d[0] = d[1] = d[2] = d[3] = 1.0;
+    inv = 0.0;
+    if constexpr (SCHEME == SFXM_FV_LAX_FRIEDRICHS || SCHEME == SFXM_FV_CENTRAL || SCHEME == SFXM_FV_UPWIND) {
+      const double dxw = xs[1] - xs[0];
+      const double dxe = xs[2] - xs[1];
+      const double dx = 0.5 * (dxw + dxe);                 // fv_transport.py:50-52
+      inv = 1.0 / dx;
+      d[0] = 0.5 * (xs[1] - xs[0]);                        // flux.pyx:285 (note the 0.5)
+      d[1] = 0.5 * (xs[2] - xs[1]);                        // flux.pyx:294
+    } else if constexpr (SCHEME == SFXM_FD_CENTRAL) {
+      d[0] = xs[2] - xs[0];                                // derivatives.pyx:78
+      d[1] = xs[1] - xs[0];                                // derivatives.pyx:99
+      d[2] = xs[2] - xs[1];                                // derivatives.pyx:106
+      d[3] = (d[1] + d[2]) / 2.0;                          // derivatives.pyx:111
+    } else {
+      const double h = xs[1] - xs[0];                      // only the first spacing, derivatives.pyx:89,120
+      d[0] = 4.0 * h;
+      d[1] = 2.0 * (h * h);
+    }
+    fast = true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      rd[k] = 1.0 / d[k];
+      fast = fast & sane(d[k], 120) & (d[k] != 0.0);
+    }
+  }
+  // from the per-cell table written by geometry_kernel: tab[k * nx + i], k = d0..d3, rd0..rd3, inv, fast
+  __device__ __forceinline__ Geom(const double *__restrict__ tab, int64_t nx, int64_t i) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      d[k] = __ldg(tab + k * nx + i);
+      rd[k] = __ldg(tab + (4 + k) * nx + i);
+    }
+    inv = __ldg(tab + 8 * nx + i);
+    fast = __ldg(tab + 9 * nx + i) != 0.0;
+  }
+  __device__ __forceinline__ void store(double *__restrict__ tab, int64_t nx, int64_t i) const {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      tab[k * nx + i] = d[k];
+      tab[(4 + k) * nx + i] = rd[k];
+    }
+    tab[8 * nx + i] = inv;
+    tab[9 * nx + i] = fast ? 1.0 : 0.0;
+  }
+  template <int NV, int NP>
+  __device__ __forceinline__ void and_inputs(const double (&u)[W][NV], const double (&prm)[NP]) {
+#pragma unroll
+    for (int s = 0; s < W; ++s)
+#pragma unroll
+      for (int j = 0; j < NV; ++j) fast = fast & sane(u[s][j], 120);
+#pragma unroll
+    for (int k = 0; k < NP; ++k) fast = fast & sane(prm[k], 120);
+  }
+};
+
+// FAST: this thread's inputs passed the sanity check, quotients use div_known's FMAs (else the IEEE division)
+template <class Model, int SCHEME, int NV, int W, bool FAST>
+__device__ __forceinline__ void cell_residual(const double *prm, const double (&u)[W][NV], const Geom<SCHEME, W> &g,
                                               double (&r)[NV]) {
   if constexpr (SCHEME == SFXM_FV_LAX_FRIEDRICHS || SCHEME == SFXM_FV_CENTRAL || SCHEME == SFXM_FV_UPWIND) {
     static_assert(W == 3 || SCHEME > SFXM_FV_UPWIND, "FV schemes use a 3-cell stencil");
-    const double dxw = xs[1] - xs[0];
-    const double dxe = xs[2] - xs[1];
-    const double dx = 0.5 * (dxw + dxe);                    // fv_transport.py:50-52
-    const double inv = 1.0 / dx;                            // fv_transport.py:58 "(1 / dx)"
     double Fl[NV], Fc[NV], Fr[NV], Fw[NV], Fe[NV];
     Model::F(prm, u[0], Fl);
     Model::F(prm, u[1], Fc);
@@ -277,39 +417,33 @@ __device__ __forceinline__ void cell_residual(const double *prm, const double (&
       Model::D(prm, u[0], Dl);
       Model::D(prm, u[1], Dc);
       Model::D(prm, u[2], Dr);
-      const double hw = 0.5 * (xs[1] - xs[0]);              // flux.pyx:285 (note the 0.5)
-      const double he = 0.5 * (xs[2] - xs[1]);              // flux.pyx:294
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        const double DFw = (Dc[j] - Dl[j]) / hw;
-        const double DFe = (Dr[j] - Dc[j]) / he;
-        r[j] = (0.0 - inv * (Fe[j] - Fw[j])) + inv * (DFe - DFw);   // fv_transport.py:58
+        const double DFw = div_known<FAST>(Dc[j] - Dl[j], g.d[0], g.rd[0]);      // flux.pyx:288
+        const double DFe = div_known<FAST>(Dr[j] - Dc[j], g.d[1], g.rd[1]);      // flux.pyx:297
+        r[j] = (0.0 - g.inv * (Fe[j] - Fw[j])) + g.inv * (DFe - DFw);      // fv_transport.py:58
       }
     } else {
       // D == 0: (Dc-Dl)/hw = +0, DFe-DFw = +0, inv*0 = 0, and a + 0 = a
 #pragma unroll
-      for (int j = 0; j < NV; ++j) r[j] = (0.0 - inv * (Fe[j] - Fw[j])) + 0.0;
+      for (int j = 0; j < NV; ++j) r[j] = (0.0 - g.inv * (Fe[j] - Fw[j])) + 0.0;
     }
   } else if constexpr (SCHEME == SFXM_FD_CENTRAL) {
     double Fl[NV], Fr[NV];
     Model::F(prm, u[0], Fl);
     Model::F(prm, u[2], Fr);
-    const double dx2 = xs[2] - xs[0];                       // derivatives.pyx:78
-    const double dxw = xs[1] - xs[0];                       // derivatives.pyx:99
-    const double dxe = xs[2] - xs[1];                       // derivatives.pyx:106
-    const double dxm = (dxw + dxe) / 2.0;                   // derivatives.pyx:111
     double Dl[NV], Dc[NV], Dr[NV];
     Model::D(prm, u[0], Dl);
     Model::D(prm, u[1], Dc);
     Model::D(prm, u[2], Dr);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      const double dF = (Fr[j] - Fl[j]) / dx2;
+      const double dF = div_known<FAST>(Fr[j] - Fl[j], g.d[0], g.rd[0]);        // derivatives.pyx:81
       double d2 = 0.0;
       if constexpr (Model::kHasDiffusion) {
-        const double Dw = (Dc[j] - Dl[j]) / dxw;
-        const double De = (Dr[j] - Dc[j]) / dxe;
-        d2 = (De - Dw) / dxm;
+        const double Dw = div_known<FAST>(Dc[j] - Dl[j], g.d[1], g.rd[1]);      // derivatives.pyx:102
+        const double De = div_known<FAST>(Dr[j] - Dc[j], g.d[2], g.rd[2]);      // derivatives.pyx:109
+        d2 = div_known<FAST>(De - Dw, g.d[3], g.rd[3]);                         // derivatives.pyx:112
       }
       r[j] = (0.0 - dF) + d2;                               // fd_transport.py:46-50
     }
@@ -320,9 +454,6 @@ __device__ __forceinline__ void cell_residual(const double *prm, const double (&
     Model::F(prm, u[1], F1);
     Model::F(prm, u[2], F2);
     Model::F(prm, u[W - 1], F3);
-    const double h = xs[1] - xs[0];                         // only the first spacing, derivatives.pyx:89,120
-    const double den1 = 4.0 * h;
-    const double den2 = 2.0 * (h * h);
     double D0[NV], D1[NV], D2[NV], D3[NV];
     Model::D(prm, u[0], D0);
     Model::D(prm, u[1], D1);
@@ -330,9 +461,10 @@ __device__ __forceinline__ void cell_residual(const double *prm, const double (&
     Model::D(prm, u[W - 1], D3);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      const double dF = (((-F0[j] - F1[j]) + F2[j]) + F3[j]) / den1;      // derivatives.pyx:88-90
+      const double dF = div_known<FAST>(((-F0[j] - F1[j]) + F2[j]) + F3[j], g.d[0], g.rd[0]);      // derivatives.pyx:88-90
       double d2 = 0.0;
-      if constexpr (Model::kHasDiffusion) d2 = (((D0[j] - D1[j]) - D2[j]) + D3[j]) / den2;   // :119-121
+      if constexpr (Model::kHasDiffusion)
+        d2 = div_known<FAST>(((D0[j] - D1[j]) - D2[j]) + D3[j], g.d[1], g.rd[1]);                  // :119-121
       r[j] = (0.0 - dF) + d2;
     }
   }

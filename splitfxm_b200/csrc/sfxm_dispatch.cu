@@ -1,0 +1,109 @@
+// sfxm_dispatch.cu - C ABI of the residual / Jacobian / domain-fill kernels and the model dispatch.
+#include <cuda_runtime.h>
+#include "sfxm_kernels.cuh"
+
+namespace sfxm {
+
+// one translation unit per model (sfxm_inst_*.cu)
+int launch_ad1(const Launch &L);
+int launch_ad2(const Launch &L);
+int launch_ad3(const Launch &L);
+int launch_ad4(const Launch &L);
+int launch_euler_prim(const Launch &L);
+int launch_euler_cons(const Launch &L);
+
+static int validate(const sfxm_problem_t &P) {
+  if (P.nv < 1 || P.nv > SFXM_MAX_NV) return set_error("nv must be 1..4");
+  if (P.nbl < 1 || P.nbr < 1 || P.nbl > SFXM_MAX_NB || P.nbr > SFXM_MAX_NB) return set_error("nb_left/nb_right must be 1..2");
+  if (P.nx < 2 * (P.nbl + P.nbr + 1)) return set_error("mesh smaller than twice the stencil");
+  if (P.batch < 1) return set_error("batch must be >= 1");
+  return 0;
+}
+
+static int dispatch(const Launch &L) {
+  const sfxm_problem_t &P = *L.P;
+  if (int e = validate(P)) return e;
+  switch (P.model) {
+    case SFXM_MODEL_AD:
+      switch (P.nv) {
+        case 1: return launch_ad1(L);
+        case 2: return launch_ad2(L);
+        case 3: return launch_ad3(L);
+        case 4: return launch_ad4(L);
+      }
+      break;
+    case SFXM_MODEL_EULER_PRIM:
+      if (P.nv != 3) return set_error("Euler1D has 3 variables");
+      return launch_euler_prim(L);
+    case SFXM_MODEL_EULER_CONS:
+      if (P.nv != 3) return set_error("Euler1DConservative has 3 variables");
+      return launch_euler_cons(L);
+  }
+  return set_error("unknown model");
+}
+
+}  // namespace sfxm
+
+using namespace sfxm;
+
+extern "C" int sfxm_residual(const sfxm_problem_t *prob, const double *x_int, const double *params,
+                             int64_t param_stride, const double *geom, const double *y, double *r, double *y_out,
+                             double dt, void *stream) {
+  if (!prob || !x_int || !params || !y || (!r && !y_out)) return set_error("sfxm_residual: null argument");
+  Launch L{OP_RESIDUAL, prob, x_int, params, param_stride, y, r, y_out, dt, (cudaStream_t)stream, geom};
+  return dispatch(L);
+}
+
+extern "C" int sfxm_jacobian(const sfxm_problem_t *prob, const double *x_int, const double *params,
+                             int64_t param_stride, const double *geom, const double *y, double eps, double *J,
+                             double *r0, void *stream) {
+  if (!prob || !x_int || !params || !y || !J) return set_error("sfxm_jacobian: null argument");
+  if (!(eps > 0.0)) return set_error("sfxm_jacobian: epsilon must be positive");
+  Launch L{OP_JACOBIAN, prob, x_int, params, param_stride, y, J, r0, eps, (cudaStream_t)stream, geom};
+  return dispatch(L);
+}
+
+extern "C" int sfxm_fill_domain(const sfxm_problem_t *prob, const double *x_int, const double *y, double *x_all,
+                                double *U_all, void *stream) {
+  if (!prob || !x_int || !y || !U_all) return set_error("sfxm_fill_domain: null argument");
+  const sfxm_problem_t &P = *prob;
+  if (int e = validate(P)) return e;
+  dim3 b = block_for(P.batch), g = grid_for(P.batch, P.nx + P.nbl + P.nbr, b);
+  if (g.z > 65535) return set_error("mesh too large for one launch");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (P.nv) {
+    case 1: fill_domain_kernel<1><<<g, b, 0, st>>>(P, x_int, y, x_all, U_all); break;
+    case 2: fill_domain_kernel<2><<<g, b, 0, st>>>(P, x_int, y, x_all, U_all); break;
+    case 3: fill_domain_kernel<3><<<g, b, 0, st>>>(P, x_int, y, x_all, U_all); break;
+    case 4: fill_domain_kernel<4><<<g, b, 0, st>>>(P, x_int, y, x_all, U_all); break;
+  }
+  return check_launch("sfxm_fill_domain");
+}
+
+extern "C" int sfxm_geometry(const sfxm_problem_t *prob, const double *x_int, double *geom, void *stream) {
+  if (!prob || !x_int || !geom) return set_error("sfxm_geometry: null argument");
+  const sfxm_problem_t &P = *prob;
+  if (int e = validate(P)) return e;
+  const int W = P.nbl + P.nbr + 1;
+  const unsigned blocks = (unsigned)((P.nx + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (P.scheme) {
+    case SFXM_FV_LAX_FRIEDRICHS:
+    case SFXM_FV_CENTRAL:
+    case SFXM_FV_UPWIND:
+      if (W != 3) return set_error("Stencil size does not match boundary conditions");
+      geometry_kernel<SFXM_FV_LAX_FRIEDRICHS, 3><<<blocks, 256, 0, st>>>(P, x_int, geom);   // same geometry for the 3 FV schemes
+      break;
+    case SFXM_FD_CENTRAL:
+      if (W != 3) return set_error("Stencil size does not match boundary conditions");
+      geometry_kernel<SFXM_FD_CENTRAL, 3><<<blocks, 256, 0, st>>>(P, x_int, geom);
+      break;
+    case SFXM_FD_RIGHT_BIAS:
+      if (W != 4) return set_error("Stencil size does not match boundary conditions");
+      geometry_kernel<SFXM_FD_RIGHT_BIAS, 4><<<blocks, 256, 0, st>>>(P, x_int, geom);
+      break;
+    default:
+      return set_error("unknown scheme");
+  }
+  return check_launch("sfxm_geometry");
+}

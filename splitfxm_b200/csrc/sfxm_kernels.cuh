@@ -1,0 +1,309 @@
+// sfxm_kernels.cuh - residual / ghost fill / finite-difference Jacobian kernel templates (sm_100a).
+// Instantiated per model in sfxm_inst_*.cu (separate translation units so they compile in parallel);
+// the C ABI and the model dispatch are in sfxm_dispatch.cu.
+//
+// Thread mapping (all kernels): threadIdx.x walks ensemble members (fastest-varying in memory, so a
+// warp's accesses are one contiguous line per (cell, variable) row), threadIdx.y walks cells.  With
+// batch == 1 the block is (1, 256): consecutive threads own consecutive cells of the cell-major vector.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include "sfxm_device.cuh"
+#include "sfxm_host.h"
+
+namespace sfxm {
+
+// (member, cell) of this thread.  Ensembles (blockDim.x == 32): blockIdx.x walks member tiles, so the CTAs that are
+// resident together write long contiguous pieces of the same (cell, variable) rows; blockIdx.y/z walk cell tiles.
+// Small batches (blockDim.x == 1): blockIdx.x walks cell tiles, blockIdx.y members.
+__device__ __forceinline__ void thread_coords(int64_t &m, int64_t &i) {
+  if (blockDim.x == 32) {
+    m = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    i = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * blockDim.y + threadIdx.y;
+  } else {
+    m = blockIdx.y;
+    i = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// residual (+ optional fused explicit-Euler update)
+// ------------------------------------------------------------------------------------------------
+template <class Model, int SCHEME, int NV, int W>
+__global__ void __launch_bounds__(256)
+residual_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restrict__ x_int,
+                const double *__restrict__ params, int64_t param_stride, const double *__restrict__ y,
+                double *__restrict__ r_out, double *__restrict__ y_out, double dt,
+                const double *__restrict__ geom_tab) {
+  int64_t m, i;
+  thread_coords(m, i);
+  if (m >= P.batch || i >= P.nx) return;
+  double prm[Model::kParams];
+#pragma unroll
+  for (int k = 0; k < Model::kParams; ++k) prm[k] = __ldg(params + (param_stride ? k * param_stride + m : k));
+  View v{y, x_int, m, -1, 0, 0.0};
+  double u[W][NV], xs[W], r[NV];
+  int64_t off[NV];
+  gather_stencil<NV, W>(P, v, i, geom_tab == nullptr, u, xs, off);
+  // geometry depends on the mesh only: with many members per cell it comes from a table (sfxm_geometry)
+  Geom<SCHEME, W> geom = geom_tab ? Geom<SCHEME, W>(geom_tab, P.nx, i) : Geom<SCHEME, W>(xs);
+  geom.and_inputs(u, prm);
+  if (geom.fast) cell_residual<Model, SCHEME, NV, W, true>(prm, u, geom, r);
+  else cell_residual<Model, SCHEME, NV, W, false>(prm, u, geom, r);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    if (r_out) r_out[off[j]] = r[j];
+    // the cell's own value is slot nbl (selected, not indexed: a dynamic index would push u[][] to local memory)
+    const double uc = (W == 3 || P.nbl == 1) ? u[1][j] : u[W == 3 ? 1 : 2][j];
+    if (y_out) y_out[off[j]] = uc + dt * r[j];              // sol.y += delta_t * f, simulation.py:459
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-cell geometry table (divisors, their reciprocals, 1/dx): mesh-only data shared by all ensemble members
+// ------------------------------------------------------------------------------------------------
+template <int SCHEME, int W>
+__global__ void geometry_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restrict__ x_int,
+                                double *__restrict__ tab) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.nx) return;
+  double xs[W];
+#pragma unroll
+  for (int s = 0; s < W; ++s) {
+    const int64_t pos = i - P.nbl + s;
+    xs[s] = pos < 0 ? ghost_x_left(P, x_int, (int)(-pos - 1))
+                    : (pos >= P.nx ? ghost_x_right(P, x_int, (int)(pos - P.nx)) : __ldg(x_int + pos));
+  }
+  const Geom<SCHEME, W> g(xs);
+  g.store(tab, P.nx, i);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Domain view: interior + ghosts, cell-major unsplit (initialize_from_list + apply_BC)
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void fill_domain_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restrict__ x_int,
+                                   const double *__restrict__ y, double *__restrict__ x_all,
+                                   double *__restrict__ U_all) {
+  int64_t m, c;   // c: index into the padded mesh
+  thread_coords(m, c);
+  const int64_t ntot = P.nx + P.nbl + P.nbr;
+  if (m >= P.batch || c >= ntot) return;
+  View v{y, x_int, m, -1, 0, 0.0};
+  double xs, u[NV];
+  load_slot<NV>(P, v, c - P.nbl, xs, u);
+  if (m == 0 && x_all) x_all[c] = xs;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) U_all[(c * NV + j) * P.batch + m] = u[j];
+}
+
+// ------------------------------------------------------------------------------------------------
+// finite-difference Jacobian, all perturbations in one pass (simulation.py:270-394)
+// ------------------------------------------------------------------------------------------------
+// One perturbed evaluation: column c of the stencil is `upc`, everything else is the base state.
+// Returns (r(u + eps e) - r0) / eps for every row (decoupled models: only row c can be non-zero).
+template <class Model, int SCHEME, int NV, int W, bool FAST>
+__device__ __forceinline__ void jac_column(const double *prm, const double (&u)[W][NV], const double (&upc)[W], int c,
+                                           const Geom<SCHEME, W> &geom, const double (&r0)[NV], double eps, double reps,
+                                           double (&col)[NV]) {
+  if constexpr (Model::kDecoupled) {
+    // scalar equation per variable: only row c can change (the other rows are exact zeros in the reference too)
+    double us[W][1], r1[1];
+#pragma unroll
+    for (int s = 0; s < W; ++s) us[s][0] = upc[s];
+    cell_residual<typename Model::Scalar, SCHEME, 1, W, FAST>(prm, us, geom, r1);    // simulation.py:345
+#pragma unroll
+    for (int r = 0; r < NV; ++r) col[r] = 0.0;
+    col[c] = div_known<FAST>(r1[0] - r0[c], eps, reps);                              // simulation.py:354
+  } else {
+    double up[W][NV], r1[NV];
+#pragma unroll
+    for (int s = 0; s < W; ++s)
+#pragma unroll
+      for (int j = 0; j < NV; ++j) up[s][j] = (j == c) ? upc[s] : u[s][j];
+    cell_residual<Model, SCHEME, NV, W, FAST>(prm, up, geom, r1);                    // simulation.py:345
+#pragma unroll
+    for (int r = 0; r < NV; ++r) col[r] = div_known<FAST>(r1[r] - r0[r], eps, reps); // simulation.py:354
+  }
+}
+
+// Block row of one cell.  entry_mask bit (r * NV + c): rows r and columns c of the same split segment
+// (simulation.py:373-392).  J entry (d, r, c) of this cell/member is at p + ((d*NV + r)*NV + c) * B.
+template <class Model, int SCHEME, int NV, int W, bool FAST>
+__device__ __forceinline__ void jacobian_cell(const sfxm_problem_t &P, const double *__restrict__ x_int,
+                                              const double *__restrict__ y, const double *prm, int64_t i, int64_t m,
+                                              bool interior, const int64_t (&off)[NV], const double (&u)[W][NV],
+                                              const Geom<SCHEME, W> &geom, double eps,
+                                              double *__restrict__ p, double *__restrict__ r0_out, uint32_t entry_mask) {
+  const int64_t B = P.batch;
+  const double reps = 1.0 / eps;
+  double r0[NV];
+  cell_residual<Model, SCHEME, NV, W, FAST>(prm, u, geom, r0);   // unperturbed rhs, simulation.py:320
+  if (r0_out) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) r0_out[off[j]] = r0[j];
+  }
+  // interior == false: the stencil contains ghost cells (then BCs are re-applied after every perturbation,
+  // simulation.py:340-342, and wrap columns exist for periodic variables, bc.py:195-240)
+  if (interior) {
+#pragma unroll
+    for (int d = 0; d < W; ++d) {
+      double cols[NV][NV];   // cols[c][r]
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+        double upc[W];
+#pragma unroll
+        for (int s = 0; s < W; ++s) upc[s] = u[s][c];
+        upc[d] = u[d][c] + eps;                             // simulation.py:337
+        jac_column<Model, SCHEME, NV, W, FAST>(prm, u, upc, c, geom, r0, eps, reps, cols[c]);
+      }
+#pragma unroll
+      for (int r = 0; r < NV; ++r)
+#pragma unroll
+        for (int c = 0; c < NV; ++c) {
+          if (entry_mask & (1u << (r * NV + c))) *p = cols[c][r];
+          p += B;
+        }
+    }
+    return;
+  }
+#pragma unroll 1
+  for (int d = 0; d < W; ++d) {
+    const int64_t pos = i - P.nbl + d;
+    double cols[NV][NV];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      // column cell: in-band interior cell, or the periodic image (extend_band, bc.py:195-240)
+      int64_t pc = pos;
+      bool live = true;
+      if (pos < 0) {
+        live = (P.bc_ltype[c] == SFXM_BC_PERIODIC);
+        pc = pos + P.nx;
+      } else if (pos >= P.nx) {
+        live = (P.bc_rtype[c] == SFXM_BC_PERIODIC);
+        pc = pos - P.nx;
+      }
+#pragma unroll
+      for (int r = 0; r < NV; ++r) cols[c][r] = 0.0;
+      if (live) {
+        View vp{y, x_int, m, pc, c, eps};
+        double upc[W];
+#pragma unroll
+        for (int s = 0; s < W; ++s) {
+          const int64_t ps = i - P.nbl + s;
+          if (ps < 0) upc[s] = ghost_u_left(P, vp, (int)(-ps - 1), c);
+          else if (ps >= P.nx) upc[s] = ghost_u_right(P, vp, (int)(ps - P.nx), c);
+          else upc[s] = (ps == pc) ? u[s][c] + eps : u[s][c];
+        }
+        jac_column<Model, SCHEME, NV, W, FAST>(prm, u, upc, c, geom, r0, eps, reps, cols[c]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NV; ++r)
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+        if (entry_mask & (1u << (r * NV + c))) *p = cols[c][r];
+        p += B;
+      }
+  }
+}
+
+template <class Model, int SCHEME, int NV, int W>
+__global__ void __launch_bounds__(256)
+jacobian_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restrict__ x_int,
+                const double *__restrict__ params, int64_t param_stride, const double *__restrict__ y,
+                double eps, double *__restrict__ J, double *__restrict__ r0_out, uint32_t entry_mask,
+                const double *__restrict__ geom_tab) {
+  int64_t m, i;
+  thread_coords(m, i);
+  if (m >= P.batch || i >= P.nx) return;
+  double prm[Model::kParams];
+#pragma unroll
+  for (int k = 0; k < Model::kParams; ++k) prm[k] = __ldg(params + (param_stride ? k * param_stride + m : k));
+  View v{y, x_int, m, -1, 0, 0.0};
+  double u[W][NV], xs[W];
+  int64_t off[NV];
+  const bool interior = gather_stencil<NV, W>(P, v, i, geom_tab == nullptr, u, xs, off);
+  Geom<SCHEME, W> geom = geom_tab ? Geom<SCHEME, W>(geom_tab, P.nx, i) : Geom<SCHEME, W>(xs);
+  geom.and_inputs(u, prm);
+  geom.fast = geom.fast && sane(eps, 120);
+  double *p = J + (i * W) * (int64_t)(NV * NV) * P.batch + m;
+  if (geom.fast)
+    jacobian_cell<Model, SCHEME, NV, W, true>(P, x_int, y, prm, i, m, interior, off, u, geom, eps, p, r0_out, entry_mask);
+  else
+    jacobian_cell<Model, SCHEME, NV, W, false>(P, x_int, y, prm, i, m, interior, off, u, geom, eps, p, r0_out, entry_mask);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------------
+static dim3 block_for(int64_t batch) { return batch >= 32 ? dim3(32, 8) : dim3(1, 256); }
+static dim3 grid_for(int64_t batch, int64_t ncells, dim3 b) {
+  const int64_t ctiles = (ncells + b.y - 1) / b.y;
+  if (b.x == 32) {   // x: member tiles, y/z: cell tiles
+    const int64_t gy = ctiles < 65535 ? ctiles : 65535;
+    return dim3((unsigned)((batch + 31) / 32), (unsigned)gy, (unsigned)((ctiles + gy - 1) / gy));
+  }
+  return dim3((unsigned)ctiles, (unsigned)batch);   // x: cell tiles, y: members (< 32)
+}
+
+enum Op { OP_RESIDUAL, OP_JACOBIAN };
+
+struct Launch {
+  Op op;
+  const sfxm_problem_t *P;
+  const double *x, *params;
+  int64_t pstride;
+  const double *y;
+  double *out0, *out1;
+  double scalar;
+  cudaStream_t st;
+  const double *geom;
+};
+
+template <class Model, int SCHEME, int NV, int W>
+static int launch_t(const Launch &L) {
+  const sfxm_problem_t &P = *L.P;
+  dim3 b = block_for(P.batch), g = grid_for(P.batch, P.nx, b);
+  if (g.z > 65535) return set_error("mesh too large for one launch");
+  if (L.op == OP_RESIDUAL)
+    residual_kernel<Model, SCHEME, NV, W><<<g, b, 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.out0, L.out1, L.scalar, L.geom);
+  else {
+    uint32_t mask = 0;
+    for (int r = 0; r < NV; ++r)
+      for (int c = 0; c < NV; ++c)
+        if (P.var_seg[r] == P.var_seg[c]) mask |= 1u << (r * NV + c);
+    jacobian_kernel<Model, SCHEME, NV, W><<<g, b, 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.scalar, L.out0, L.out1, mask, L.geom);
+  }
+  return check_launch("sfxm kernel launch");
+}
+
+template <class Model, int NV>
+static int launch_scheme(const Launch &L) {
+  const sfxm_problem_t &P = *L.P;
+  const int W = P.nbl + P.nbr + 1;
+  switch (P.scheme) {
+    case SFXM_FV_LAX_FRIEDRICHS:
+      if (W != 3) break;
+      return launch_t<Model, SFXM_FV_LAX_FRIEDRICHS, NV, 3>(L);
+    case SFXM_FV_CENTRAL:
+      if (W != 3) break;
+      return launch_t<Model, SFXM_FV_CENTRAL, NV, 3>(L);
+    case SFXM_FV_UPWIND:
+      if (W != 3) break;
+      if constexpr (Model::kDiagonalDFDU) return launch_t<Model, SFXM_FV_UPWIND, NV, 3>(L);
+      else return set_error("UPWIND needs a diagonal dFdU (the reference's eigenvector order is LAPACK-defined)");
+    case SFXM_FD_CENTRAL:
+      if (W != 3) break;
+      return launch_t<Model, SFXM_FD_CENTRAL, NV, 3>(L);
+    case SFXM_FD_RIGHT_BIAS:
+      if (W != 4) break;
+      return launch_t<Model, SFXM_FD_RIGHT_BIAS, NV, 4>(L);
+    default:
+      return set_error("unknown scheme");
+  }
+  return set_error("Stencil size does not match boundary conditions");
+}
+
+}  // namespace sfxm

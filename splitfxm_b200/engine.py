@@ -62,6 +62,7 @@ class Engine:
         self.x_int = torch.from_numpy(x_int).to(self.device)
         self._probs = {}
         self._work = {}
+        self._geom = None
 
     def set_params(self, params):
         """params: [n_params] (shared) or [n_params, batch] (per member)."""
@@ -79,6 +80,7 @@ class Engine:
         """filler(prob) writes the BC part of a descriptor (bc.describe_bcs)."""
         self._bc_filler = filler
         self._probs = {}
+        self._geom = None
 
     def problem(self, split=False, split_locs=None):
         key = (bool(split), tuple(sorted(set(split_locs))) if (split and split_locs is not None) else None)
@@ -102,6 +104,11 @@ class Engine:
             raise SFXM("boundary conditions not set")
         self._bc_filler(P)
         self._probs[key] = (P, segs)
+        if self.batch >= 32 and self._geom is None:
+            # mesh-only data shared by all members: computed once per mesh (the split layout does not enter)
+            self._geom = torch.empty(10 * self.nx, dtype=torch.float64, device=self.device)
+            _lib.check(self.lib.sfxm_geometry(ctypes.byref(P), _lib.ptr(self.x_int), _lib.ptr(self._geom), _lib.stream_ptr()))
+            _lib.count()
         return P, segs
 
     # -- memory ----------------------------------------------------------------------------------------
@@ -139,7 +146,8 @@ class Engine:
         if out is None and y_out is None:
             out = torch.empty_like(y)
         _lib.check(self.lib.sfxm_residual(ctypes.byref(P), _lib.ptr(self.x_int), _lib.ptr(self.params), self.param_stride,
-                                          _lib.ptr(y), _lib.ptr(out), _lib.ptr(y_out), float(dt), _lib.stream_ptr()))
+                                          _lib.ptr(self._geom), _lib.ptr(y), _lib.ptr(out), _lib.ptr(y_out), float(dt),
+                                          _lib.stream_ptr()))
         _lib.count()
         return out
 
@@ -164,7 +172,8 @@ class Engine:
         if J is None:
             J = self.jacobian_buffer()
         _lib.check(self.lib.sfxm_jacobian(ctypes.byref(P), _lib.ptr(self.x_int), _lib.ptr(self.params), self.param_stride,
-                                          _lib.ptr(y), float(eps), _lib.ptr(J), _lib.ptr(r0), _lib.stream_ptr()))
+                                          _lib.ptr(self._geom), _lib.ptr(y), float(eps), _lib.ptr(J), _lib.ptr(r0),
+                                          _lib.stream_ptr()))
         _lib.count()
         return J
 

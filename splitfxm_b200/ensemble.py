@@ -67,5 +67,5 @@ class EnsembleSimulation:
         return y, its
 
     def evolve_euler(self, Y, t_diff, max_step, split=False, split_locs=None):
-        y, _ = euler(self.eng, self._state(Y).clone(), t_diff, max_step, split, split_locs)
+        y, _, _ = euler(self.eng, self._state(Y).clone(), t_diff, max_step, split, split_locs)
         return y

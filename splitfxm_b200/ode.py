@@ -34,7 +34,7 @@ def _dptr(a):
 
 
 def euler(eng, y, t_diff, max_step, split=False, split_locs=None, on_step=None):
-    """y <- y after t_diff; returns (y, nfev).  simulation.py:455-463."""
+    """Returns (y after t_diff, state of the last RHS evaluation or None, nfev).  simulation.py:455-463."""
     t_current = 0.0
     nfev = 0
     other = torch.empty_like(y)
@@ -46,7 +46,7 @@ def euler(eng, y, t_diff, max_step, split=False, split_locs=None, on_step=None):
         if on_step is not None:
             on_step(y, t_current)
         t_current += delta_t
-    return y, nfev
+    return y, (other if nfev > 0 else None), nfev
 
 
 class RK45Stepper:
@@ -67,6 +67,7 @@ class RK45Stepper:
         nbytes = eng.lib.sfxm_scaled_sumsq_workspace_bytes(eng.n, eng.batch)
         self.work = torch.empty(max(nbytes // 8, 1), dtype=torch.float64, device=dev)
         self.nfev = 0
+        self.last_rhs_state = None     # state of the last RHS evaluation (the reference's ghosts belong to it)
 
     def f(self, y, out):
         self.eng.residual(y, out, self.split, self.split_locs)
@@ -170,5 +171,6 @@ class RK45Stepper:
                 _lib.count()
             t = t_new
             y, y_new = y_new, y
+            self.last_rhs_state = y
             self.K[0].copy_(self.K[6])      # FSAL: f_new becomes f of the next step
         return result

@@ -72,11 +72,20 @@ class Simulation:
         self._eng.set_bcs(lambda P: describe_bcs(P, self._bcs, d))
         return self._eng
 
-    def _store(self, eng, y, split, split_locs):
-        """Device state -> Domain (interior and ghosts): initialize_from_list + apply_BC (simulation.py:171-175)."""
-        x_all, U_all = eng.fill_domain(y, split, split_locs)
+    def _store(self, eng, y, split, split_locs, ghost_state=None):
+        """Device state -> Domain: initialize_from_list + apply_BC (simulation.py:171-175).
+
+        ``ghost_state``: the state of the last right-hand-side evaluation.  The reference's evolve() ends with
+        initialize_from_list (simulation.py:472), which rewrites the interior only, so the ghost cells it leaves
+        behind are those of the last RHS call - reproduced here."""
+        x_all, U_all = eng.fill_domain(y if ghost_state is None else ghost_state, split, split_locs)
         self._d._x[:] = x_all.cpu().numpy()
         self._d._U[:, :] = U_all.cpu().numpy().reshape(self._d._U.shape)
+        if ghost_state is not None:
+            from .engine import flat_index_table
+            _, segs = eng.problem(split, split_locs)
+            idx = flat_index_table(eng.nx, eng.nv, segs)
+            self._d.interior_U()[:, :] = y.cpu().numpy().reshape(-1)[idx]
 
     # -- list related methods (simulation.py:81-264) -----------------------------------------------------
     def get_shape_from_list(self, l):
@@ -162,20 +171,22 @@ class Simulation:
         ext_bounds = self.extend_bounds(bounds, num_points, nv, split, split_locs)
         eng = self._engine()
         y = eng.to_device(y0)
+        ghost_state = None
         if method == "Euler":
             on_step = None
             if bounds is not None:
                 def on_step(yd, t):
                     report_bounds(yd.cpu().numpy().reshape(-1), ext_bounds, t)
-            y, _ = euler(eng, y, t_diff, max_step, split, split_locs, on_step)
+            y, ghost_state, _ = euler(eng, y, t_diff, max_step, split, split_locs, on_step)
         elif method == "RK45":
             stepper = RK45Stepper(eng, split, split_locs, 1e-3, 1e-6, max_step)
             y = stepper.integrate(y, t_diff)
+            ghost_state = stepper.last_rhs_state
             if bounds is not None:
                 report_bounds(y.cpu().numpy().reshape(-1), ext_bounds, t_diff)
         else:
             raise SFXM(f"evolve method '{method}' is not available on the device path (Euler, RK45)")
-        self._store(eng, y, split, split_locs)
+        self._store(eng, y, split, split_locs, ghost_state)
 
     def steady_state(self, split=False, split_locs=None, sparse=True, dt0=0.0, dtmax=1.0, armijo=False, bounds=None):
         """Newton / Split-Newton to steady state (simulation.py:474-526); returns the iteration count."""
