@@ -45,7 +45,9 @@ enum { SFXM_MODEL_AD = 0, SFXM_MODEL_EULER_PRIM = 1, SFXM_MODEL_EULER_CONS = 2 }
 enum { SFXM_FV_LAX_FRIEDRICHS = 0, SFXM_FV_CENTRAL = 1, SFXM_FV_UPWIND = 2, SFXM_FD_CENTRAL = 3,
        SFXM_FD_RIGHT_BIAS = 4 };
 /* boundary types (bc.py:47-153); KEEP = variable/side has no entry in `bcs`, ghost keeps its value */
-enum { SFXM_BC_PERIODIC = 0, SFXM_BC_OUTFLOW = 1, SFXM_BC_NEUMANN = 2, SFXM_BC_DIRICHLET = 3, SFXM_BC_KEEP = 4 };
+enum { SFXM_BC_PERIODIC = 0, SFXM_BC_OUTFLOW = 1, SFXM_BC_NEUMANN = 2, SFXM_BC_DIRICHLET = 3, SFXM_BC_KEEP = 4,
+       /* slab decomposition: the ghost values come from the neighbouring rank (halo_left / halo_right below) */
+       SFXM_BC_HALO = 5 };
 /* which rule wrote the shared ghost positions last (bc.py:56,64 periodic; :73,87,114,127,141,151 mirror) */
 enum { SFXM_GX_PERIODIC = 0, SFXM_GX_MIRROR = 1, SFXM_GX_KEEP = 2 };
 
@@ -64,6 +66,9 @@ typedef struct sfxm_problem {
   /* flat-vector layout (split permutation) */
   int64_t var_base[SFXM_MAX_NV];
   int32_t var_stride[SFXM_MAX_NV], var_off[SFXM_MAX_NV], var_seg[SFXM_MAX_NV];
+  /* device buffers [(g * nv + j) * batch + m] with the neighbouring slab's boundary cells, ghost g = 0 nearest
+   * (used by variables whose BC type is SFXM_BC_HALO; NULL otherwise) */
+  const double *halo_left, *halo_right;
 } sfxm_problem_t;
 
 int sfxm_abi_version(void);

@@ -15,7 +15,7 @@ MAX_NV, MAX_NB, MAX_PARAMS = 4, 2, 4
 
 MODEL_AD, MODEL_EULER_PRIM, MODEL_EULER_CONS = 0, 1, 2
 FV_LAX_FRIEDRICHS, FV_CENTRAL, FV_UPWIND, FD_CENTRAL, FD_RIGHT_BIAS = 0, 1, 2, 3, 4
-BC_PERIODIC, BC_OUTFLOW, BC_NEUMANN, BC_DIRICHLET, BC_KEEP = 0, 1, 2, 3, 4
+BC_PERIODIC, BC_OUTFLOW, BC_NEUMANN, BC_DIRICHLET, BC_KEEP, BC_HALO = 0, 1, 2, 3, 4, 5
 GX_PERIODIC, GX_MIRROR, GX_KEEP = 0, 1, 2
 
 c_i32, c_i64, c_f64, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
@@ -35,6 +35,7 @@ class Problem(ctypes.Structure):
         ("gx_keep_left", c_f64 * MAX_NB), ("gx_keep_right", c_f64 * MAX_NB),
         ("var_base", c_i64 * MAX_NV),
         ("var_stride", c_i32 * MAX_NV), ("var_off", c_i32 * MAX_NV), ("var_seg", c_i32 * MAX_NV),
+        ("halo_left", c_vp), ("halo_right", c_vp),
     ]
 
 

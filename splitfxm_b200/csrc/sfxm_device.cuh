@@ -55,6 +55,7 @@ __device__ __forceinline__ double ghost_x_right(const sfxm_problem_t &P, const d
 
 __device__ inline double ghost_u_left(const sfxm_problem_t &P, const View &v, int g, int j) {
   const int t = P.bc_ltype[j];
+  if (t == SFXM_BC_HALO) return __ldg(P.halo_left + (int64_t)(g * P.nv + j) * P.batch + v.m);   // neighbouring slab
   if (t == SFXM_BC_PERIODIC) return ld_u(P, v, P.nx - 1 - g, j);            // bc.py:57
   if (t == SFXM_BC_DIRICHLET || t == SFXM_BC_KEEP) return P.bc_lval[j][g];  // bc.py:143
   const double u0 = ld_u(P, v, 0, j);
@@ -78,6 +79,7 @@ __device__ inline double ghost_u_left(const sfxm_problem_t &P, const View &v, in
 
 __device__ inline double ghost_u_right(const sfxm_problem_t &P, const View &v, int g, int j) {
   const int t = P.bc_rtype[j];
+  if (t == SFXM_BC_HALO) return __ldg(P.halo_right + (int64_t)(g * P.nv + j) * P.batch + v.m);  // neighbouring slab
   if (t == SFXM_BC_PERIODIC) return ld_u(P, v, g, j);                       // bc.py:65
   if (t == SFXM_BC_DIRICHLET || t == SFXM_BC_KEEP) return P.bc_rval[j][g];  // bc.py:153
   const int64_t ihi = P.nx - 1;

@@ -175,14 +175,18 @@ __device__ __forceinline__ void jacobian_cell(const sfxm_problem_t &P, const dou
 #pragma unroll
     for (int c = 0; c < NV; ++c) {
       // column cell: in-band interior cell, or the periodic image (extend_band, bc.py:195-240)
+      // (a HALO ghost belongs to the neighbouring slab: its own value is the unknown that is perturbed, and the
+      // slot holds the coupling block to that slab)
       int64_t pc = pos;
-      bool live = true;
+      bool live = true, halo = false;
       if (pos < 0) {
-        live = (P.bc_ltype[c] == SFXM_BC_PERIODIC);
-        pc = pos + P.nx;
+        halo = (P.bc_ltype[c] == SFXM_BC_HALO);
+        live = halo || (P.bc_ltype[c] == SFXM_BC_PERIODIC);
+        pc = halo ? -1 : pos + P.nx;
       } else if (pos >= P.nx) {
-        live = (P.bc_rtype[c] == SFXM_BC_PERIODIC);
-        pc = pos - P.nx;
+        halo = (P.bc_rtype[c] == SFXM_BC_HALO);
+        live = halo || (P.bc_rtype[c] == SFXM_BC_PERIODIC);
+        pc = halo ? -1 : pos - P.nx;
       }
 #pragma unroll
       for (int r = 0; r < NV; ++r) cols[c][r] = 0.0;
@@ -195,6 +199,7 @@ __device__ __forceinline__ void jacobian_cell(const sfxm_problem_t &P, const dou
           if (ps < 0) upc[s] = ghost_u_left(P, vp, (int)(-ps - 1), c);
           else if (ps >= P.nx) upc[s] = ghost_u_right(P, vp, (int)(ps - P.nx), c);
           else upc[s] = (ps == pc) ? u[s][c] + eps : u[s][c];
+          if (halo && ps == pos) upc[s] = upc[s] + eps;
         }
         jac_column<Model, SCHEME, NV, W, FAST>(prm, u, upc, c, geom, r0, eps, reps, cols[c]);
       }

@@ -1,0 +1,220 @@
+"""Slab decomposition of ONE large mesh over the GPUs of a box, with halo exchange (BASELINE config 5).
+
+The reference has no domain decomposition (the whole mesh is one Python list, domain.py:40-41).  Here each rank
+owns a contiguous slab of interior cells; the ghost cells a slab needs from its neighbours are ordinary ghost
+cells of boundary type SFXM_BC_HALO whose values sit in two small device buffers.  Before every right-hand-side
+evaluation each rank sends its first ``nbr`` / last ``nbl`` cells to the left / right neighbour (periodic
+variables wrap rank 0 <-> G-1): ``nb * nv`` doubles per side, i.e. latency-bound traffic, sent with
+``torch.distributed`` point-to-point operations (NCCL over NVLink on the box, gloo in the CPU tests).  Physical
+boundary conditions are applied by the kernels on the ranks that own a domain end, exactly as on one GPU, so
+the slab residuals concatenated are bit-identical to the single-mesh residual.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .bc import _check_dirs, _parse_side
+from .engine import Engine, flat_index_table
+from .error import SFXM
+from .schemes import FVSchemes, _scheme_ids, stencil_sizes
+
+
+def slab_bounds(nx, world, rank):
+    """Balanced contiguous partition: cells [lo, hi) of rank."""
+    base, rem = divmod(nx, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class HaloTransport:
+    """Moves the packed boundary cells between neighbouring ranks.  send_left goes to the left neighbour and
+    lands in ITS recv_right; send_right goes to the right neighbour's recv_left.  `left`/`right` are neighbour
+    ranks or None (no neighbour: a non-periodic physical boundary)."""
+
+    def __init__(self, rank, world, left, right, group=None):
+        self.rank, self.world, self.left, self.right, self.group = rank, world, left, right, group
+
+    def exchange(self, send_left, send_right, recv_left, recv_right):
+        import torch.distributed as dist
+        if self.world == 1:
+            # periodic wrap onto itself
+            if self.left is not None:
+                recv_left.copy_(send_right)
+            if self.right is not None:
+                recv_right.copy_(send_left)
+            return
+        # Messages between one pair of ranks match in posting order, and with 2 ranks and periodic data the
+        # left and the right neighbour are the same rank: post sends as [to-left, to-right] and receives as
+        # [from-right, from-left], so a peer's "to-left" message lands in my recv_right.
+        ops = []
+        if self.left is not None:
+            ops.append(dist.P2POp(dist.isend, send_left, self.left, self.group))
+        if self.right is not None:
+            ops.append(dist.P2POp(dist.isend, send_right, self.right, self.group))
+        if self.right is not None:
+            ops.append(dist.P2POp(dist.irecv, recv_right, self.right, self.group))
+        if self.left is not None:
+            ops.append(dist.P2POp(dist.irecv, recv_left, self.left, self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+
+class LocalTransport:
+    """All slabs live in one process (tests, or several slabs per GPU): direct copies between their buffers."""
+
+    def __init__(self):
+        self.slabs = []
+
+    def exchange_all(self, packed):
+        """packed[k] = (send_left, send_right) of slab k; fills every slab's halo buffers."""
+        for k, slab in enumerate(self.slabs):
+            if slab.left is not None:
+                slab.halo_left.copy_(packed[slab.left][1])      # left neighbour's LAST cells
+            if slab.right is not None:
+                slab.halo_right.copy_(packed[slab.right][0])    # right neighbour's FIRST cells
+
+
+class SlabSimulation:
+    """One rank's slab of a single mesh.  model: 'ad' | 'euler_prim' | 'euler_cons' (device functors)."""
+
+    def __init__(self, x_global, comps, model, params, bcs, scheme, method, rank, world, xmin=0.0, xmax=1.0,
+                 nbl=1, nbr=1, device=None, transport=None, batch=1):
+        from .ensemble import _MODELS
+        if (method == "FVM") != isinstance(scheme, FVSchemes):
+            raise SFXM("Scheme family does not match the numerical method")
+        if stencil_sizes.get(scheme) != nbl + nbr + 1:
+            raise SFXM("Stencil size does not match boundary conditions")
+        x_global = np.ascontiguousarray(x_global, dtype=np.float64)
+        nxg = x_global.shape[0]
+        self.rank, self.world = rank, world
+        self.lo, self.hi = slab_bounds(nxg, world, rank)
+        self.nv, self.nbl, self.nbr = len(comps), nbl, nbr
+        self.comps = list(comps)
+        model_id, names = _MODELS[model]
+        table = np.array([float(params[k]) for k in names])
+        self.eng = Engine(model_id, _scheme_ids[scheme], self.nv, nbl, nbr, x_global[self.lo:self.hi], xmin, xmax, table,
+                          batch=batch, device=device)
+        dev = self.eng.device
+        B = batch
+        self.halo_left = torch.zeros((nbl, self.nv, B), dtype=torch.float64, device=dev)
+        self.halo_right = torch.zeros((nbr, self.nv, B), dtype=torch.float64, device=dev)
+        self.send_left = torch.empty((nbr, self.nv, B), dtype=torch.float64, device=dev)    # my FIRST nbr cells
+        self.send_right = torch.empty((nbl, self.nv, B), dtype=torch.float64, device=dev)   # my LAST nbl cells
+        first, last = rank == 0, rank == world - 1
+        # parse the physical BCs once
+        parsed = {}
+        for name, bc in bcs.items():
+            _check_dirs(bc)
+            parsed[self.comps.index(name)] = (_parse_side(bc["left"]), _parse_side(bc["right"]))
+        any_per_left = any(p[0][0] == _lib.BC_PERIODIC for p in parsed.values())
+        any_per_right = any(p[1][0] == _lib.BC_PERIODIC for p in parsed.values())
+        # neighbours: interior faces always; domain ends only when some variable is periodic there
+        self.left = (rank - 1) if not first else ((world - 1) if any_per_left else None)
+        self.right = (rank + 1) if not last else (0 if any_per_right else None)
+        order = [self.comps.index(n) for n in bcs.keys()]      # application order decides the ghost positions
+        nx_loc = self.hi - self.lo
+
+        def fill(P):
+            for j in range(self.nv):
+                P.bc_ltype[j] = P.bc_rtype[j] = _lib.BC_KEEP
+                for g in range(_lib.MAX_NB):
+                    P.bc_lval[j][g] = P.bc_rval[j][g] = 0.0
+            P.gx_left = P.gx_right = _lib.GX_KEEP
+            dx0 = (xmax - xmin) / nxg                             # Domain.from_size initial ghosts, domain.py:87-97
+            for g in range(_lib.MAX_NB):
+                P.gx_keep_left[g] = xmin - (g + 1) * dx0
+                P.gx_keep_right[g] = xmax + (g + 1) * dx0
+            for j, ((lt, lv), (rt, rv)) in parsed.items():
+                P.bc_ltype[j], P.bc_rtype[j] = lt, rt
+                for g in range(_lib.MAX_NB):
+                    P.bc_lval[j][g], P.bc_rval[j][g] = lv, rv
+            # ---- left face
+            if not first:
+                for j in range(self.nv):
+                    P.bc_ltype[j] = _lib.BC_HALO
+                for g in range(nbl):
+                    P.gx_keep_left[g] = float(x_global[self.lo - 1 - g])
+            else:
+                for j, ((lt, _), _r) in parsed.items():
+                    if lt == _lib.BC_PERIODIC:
+                        P.bc_ltype[j] = _lib.BC_HALO              # values come from rank G-1 (bc.py:57)
+                if order:
+                    last_lt = parsed[order[-1]][0][0]
+                    if last_lt == _lib.BC_PERIODIC:               # bc.py:55-56 on the GLOBAL mesh
+                        for g in range(nbl):
+                            P.gx_keep_left[g] = xmin - (xmax - float(x_global[nxg - 2 - g]))
+                    else:
+                        P.gx_left = _lib.GX_MIRROR
+            # ---- right face
+            if not last:
+                for j in range(self.nv):
+                    P.bc_rtype[j] = _lib.BC_HALO
+                for g in range(nbr):
+                    P.gx_keep_right[g] = float(x_global[self.hi + g])
+            else:
+                for j, (_l, (rt, _)) in parsed.items():
+                    if rt == _lib.BC_PERIODIC:
+                        P.bc_rtype[j] = _lib.BC_HALO              # values come from rank 0 (bc.py:65)
+                if order:
+                    last_rt = parsed[order[-1]][1][0]
+                    if last_rt == _lib.BC_PERIODIC:               # bc.py:63-64 on the GLOBAL mesh
+                        for g in range(nbr):
+                            P.gx_keep_right[g] = xmax + (float(x_global[g + 1]) - xmin)
+                    else:
+                        P.gx_right = _lib.GX_MIRROR
+            P.halo_left = self.halo_left.data_ptr()
+            P.halo_right = self.halo_right.data_ptr()
+
+        self.eng.set_bcs(fill)
+        self.transport = transport if transport is not None else HaloTransport(rank, world, self.left, self.right)
+        self._pack_idx = {}
+        if nx_loc < 2 * (nbl + nbr + 1):
+            raise SFXM("slab smaller than twice the stencil")
+
+    # -- halo -------------------------------------------------------------------------------------------
+    def _indices(self, split, split_locs):
+        key = (bool(split), tuple(split_locs) if split_locs else None)
+        hit = self._pack_idx.get(key)
+        if hit is None:
+            _, segs = self.eng.problem(split, split_locs)
+            idx = flat_index_table(self.eng.nx, self.nv, segs)
+            first = torch.from_numpy(idx[:self.nbr].reshape(-1)).to(self.eng.device)                  # cells 0..nbr-1
+            last = torch.from_numpy(idx[::-1][:self.nbl].reshape(-1).copy()).to(self.eng.device)       # cells nx-1, nx-2, ..
+            hit = (first, last)
+            self._pack_idx[key] = hit
+        return hit
+
+    def pack(self, y, split=False, split_locs=None):
+        """Boundary cells of y -> (send_left, send_right), in the receiver's ghost order (g = 0 nearest)."""
+        first, last = self._indices(split, split_locs)
+        torch.index_select(y, 0, first, out=self.send_left.view(-1, self.eng.batch))
+        torch.index_select(y, 0, last, out=self.send_right.view(-1, self.eng.batch))
+        return self.send_left, self.send_right
+
+    def exchange(self, y, split=False, split_locs=None):
+        sl, sr = self.pack(y, split, split_locs)
+        self.transport.exchange(sl, sr, self.halo_left, self.halo_right)
+
+    # -- hot path ---------------------------------------------------------------------------------------
+    def residual(self, y, out=None, split=False, split_locs=None, exchange=True):
+        if exchange:
+            self.exchange(y, split, split_locs)
+        return self.eng.residual(y, out, split, split_locs)
+
+    def evolve_euler(self, y, t_diff, max_step, split=False, split_locs=None):
+        """The reference's explicit Euler loop (simulation.py:455-463) on the slab; every rank runs the same
+        step sequence (dt depends on t only), one halo exchange + one fused launch per step."""
+        t_current = 0.0
+        other = torch.empty_like(y)
+        nsteps = 0
+        while t_current < t_diff:
+            delta_t = min(t_diff - t_current, max_step)
+            self.exchange(y, split, split_locs)
+            self.eng.euler_step(y, other, delta_t, split, split_locs)
+            y, other = other, y
+            t_current += delta_t
+            nsteps += 1
+        return y, nsteps
