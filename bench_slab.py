@@ -1,0 +1,120 @@
+#!/usr/bin/env python
+"""bench_slab.py - BASELINE config 5: one conservative Sod mesh, slab-decomposed over N GPUs with halo exchange.
+
+Launch:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+             bench_slab.py --nx 10000000 --steps 200
+Every rank owns nx/N cells of the Euler1DConservative FVM Lax-Friedrichs problem (neumann-0 ends,
+tutorials/conservative_sod_shock/conservative_sod_shock.py:17-34) and runs explicit Euler steps with
+max_step = 0.4 dx / 2.2: per step one NCCL halo exchange (nb*nv doubles per side) and one fused
+residual+update launch.  Strong scaling: the mesh is fixed, N varies.  `--check` first verifies, on a small
+mesh, that the gathered slabs equal a single-GPU run bit for bit.
+Prints one JSON line (rank 0): cell-updates/s, ms per step, achieved HBM GB/s (56 B per cell-step) per GPU.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+COMPS = ["rho", "rhou", "E"]
+BCS = {n: {"left": {"neumann": 0.0}, "right": {"neumann": 0.0}} for n in COMPS}
+
+
+def sod_state(x):
+    left = x < 0.5
+    return np.stack([np.where(left, 1.0, 0.125), np.zeros_like(x), np.where(left, 2.5, 0.25)], axis=1)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nx", type=int, default=10_000_000)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--check", action="store_true")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    import splitfxm_b200 as sf
+    from splitfxm_b200.distributed import SlabSimulation
+    from splitfxm_b200.models.euler1d import Euler1DConservative
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def make(nx):
+        x = np.linspace(0.0, 1.0, nx)
+        slab = SlabSimulation(x, COMPS, "euler_cons", {"gamma": 1.4}, BCS, sf.FVSchemes.LAX_FRIEDRICHS, "FVM", rank, world,
+                              device=dev)
+        y = slab.eng.to_device(sod_state(x[slab.lo:slab.hi]).reshape(-1))
+        return x, slab, y
+
+    check = None
+    if args.check:
+        nx = 4096
+        x, slab, y = make(nx)
+        dt = 0.4 * (x[1] - x[0]) / 2.2
+        y, nsteps = slab.evolve_euler(y, 40 * dt, dt)
+        mine = y.cpu().numpy().reshape(-1, 3)
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, mine)
+        else:
+            parts = [mine]
+        if rank == 0:
+            d = sf.Domain.from_size(nx, 1, 1, COMPS)
+            d.interior_U()[:, :] = sod_state(np.array(d.positions(interior=True)))
+            sim = sf.Simulation(d, Euler1DConservative(1.4, "FVM"), {}, BCS, sf.FVSchemes.LAX_FRIEDRICHS)
+            sim.evolve(40 * dt, method="Euler", max_step=dt)
+            check = bool(np.array_equal(np.concatenate(parts), d.values(interior=True)))
+            assert check, "slab-decomposed evolution differs from the single-GPU run"
+
+    x, slab, y = make(args.nx)
+    dt = 0.4 * (x[1] - x[0]) / 2.2
+    other = torch.empty_like(y)
+
+    def step(y, other):
+        slab.exchange(y)
+        slab.eng.euler_step(y, other, dt)
+        return other, y
+
+    for _ in range(args.warmup):
+        y, other = step(y, other)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        y, other = step(y, other)
+    t1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms[0])
+    finite = bool(torch.isfinite(y).all())
+    if rank == 0:
+        per_step = ms / args.steps
+        cells_s = args.nx * args.steps / (ms * 1e-3)
+        print(json.dumps({"workload": f"conservative Sod, Euler1DConservative FVM LF, nx={args.nx}, explicit Euler, "
+                                      f"slab-decomposed x{world} with NCCL halo exchange",
+                          "n_gpus": world, "steps": args.steps, "ms_per_step": per_step, "cell_updates_per_s": cells_s,
+                          "GBps_per_gpu": (args.nx / world) * 56 / (per_step * 1e-3) / 1e9, "scaling": "strong",
+                          "parity_vs_single_gpu": check, "finite": finite}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
