@@ -40,7 +40,11 @@ extern "C" {
 
 /* models (models/advection_diffusion.py:28-31, tutorials/sod_shock/euler1d.py:27-50,
  * tutorials/conservative_sod_shock/euler1d.py:28-63) */
-enum { SFXM_MODEL_AD = 0, SFXM_MODEL_EULER_PRIM = 1, SFXM_MODEL_EULER_CONS = 2 };
+enum { SFXM_MODEL_AD = 0, SFXM_MODEL_EULER_PRIM = 1, SFXM_MODEL_EULER_CONS = 2,
+       /* custom Model._equation: device functors compiled from user CUDA source into a plugin library that
+        * registers itself in slot (model - SFXM_MODEL_USER0), see sfxm_register_user_model */
+       SFXM_MODEL_USER0 = 16 };
+#define SFXM_MAX_USER_MODELS 16
 /* schemes (schemes.py:4-14) */
 enum { SFXM_FV_LAX_FRIEDRICHS = 0, SFXM_FV_CENTRAL = 1, SFXM_FV_UPWIND = 2, SFXM_FD_CENTRAL = 3,
        SFXM_FD_RIGHT_BIAS = 4 };
@@ -153,6 +157,13 @@ int sfxm_refine_flags(const void *work, int64_t n, uint8_t *loc_out, uint8_t *ke
                       int32_t *comp_out, void *stream);
 int sfxm_refine_apply(const double *x, const double *U, int64_t n, int32_t nv, const void *work, double *x_out,
                       double *U_out, void *stream);
+
+/* Register the launcher of a user-model plugin (built by splitfxm_b200/custom.py from the user's device functor:
+ * the same residual/Jacobian kernel templates instantiated for that functor).  launch_fn has the signature
+ * int (*)(const void *launch) and is called by sfxm_residual / sfxm_jacobian when prob->model is
+ * SFXM_MODEL_USER0 + slot.  The reference's equivalent is a Model whose _equation holds Python callables
+ * F, D, S, dFdU (model.py:8, fv_transport.py:18, fd_transport.py:18). */
+int sfxm_register_user_model(int32_t slot, void *launch_fn);
 
 /* Device self-test: counts (into *mismatch_dev, a device uint64 the caller zeroes) operands for which the
  * five-FMA division by a known reciprocal used in the stencil kernels differs from the IEEE quotient.

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libsfxm_b200.so")
 MAX_NV, MAX_NB, MAX_PARAMS = 4, 2, 4
 
 MODEL_AD, MODEL_EULER_PRIM, MODEL_EULER_CONS = 0, 1, 2
+MODEL_USER0, MAX_USER_MODELS = 16, 16
 FV_LAX_FRIEDRICHS, FV_CENTRAL, FV_UPWIND, FD_CENTRAL, FD_RIGHT_BIAS = 0, 1, 2, 3, 4
 BC_PERIODIC, BC_OUTFLOW, BC_NEUMANN, BC_DIRICHLET, BC_KEEP, BC_HALO = 0, 1, 2, 3, 4, 5
 GX_PERIODIC, GX_MIRROR, GX_KEEP = 0, 1, 2
@@ -63,6 +64,7 @@ SIGNATURES = {
     "sfxm_refine_mark": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_f64, c_f64, c_f64, c_f64, c_f64, c_f64, c_vp, c_vp, c_vp]),
     "sfxm_refine_flags": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_refine_apply": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_register_user_model": (ctypes.c_int, [c_i32, c_vp]),
     "sfxm_selftest_div": (ctypes.c_int, [c_i64, ctypes.c_uint64, c_i32, c_vp, c_vp]),
 }
 
@@ -77,7 +79,7 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise SFXM(f"{LIB_PATH} is missing: build it with splitfxm_b200/csrc/build.sh "
                    "(there is no CPU fallback for the hot path)")
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)    # user-model plugins resolve sfxm:: symbols against it
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args

@@ -103,23 +103,25 @@ __device__ inline double ghost_u_right(const sfxm_problem_t &P, const View &v, i
 }
 
 // stencil slot s of cell i -> position and values (system.py:58-61: cells[i - nbl .. i + nbr])
+// (j0: first variable of the group this thread handles - 0 for the coupled kernels, the thread's own variable for
+// the one-variable-per-thread kernels of decoupled models)
 template <int NV>
 __device__ __forceinline__ void load_slot(const sfxm_problem_t &P, const View &v, int64_t pos, double &xs,
-                                          double (&u)[NV]) {
+                                          double (&u)[NV], int j0 = 0) {
   if (pos < 0) {
     const int g = (int)(-pos - 1);
     xs = ghost_x_left(P, v.x, g);
 #pragma unroll
-    for (int j = 0; j < NV; ++j) u[j] = ghost_u_left(P, v, g, j);
+    for (int j = 0; j < NV; ++j) u[j] = ghost_u_left(P, v, g, j0 + j);
   } else if (pos >= P.nx) {
     const int g = (int)(pos - P.nx);
     xs = ghost_x_right(P, v.x, g);
 #pragma unroll
-    for (int j = 0; j < NV; ++j) u[j] = ghost_u_right(P, v, g, j);
+    for (int j = 0; j < NV; ++j) u[j] = ghost_u_right(P, v, g, j0 + j);
   } else {
     xs = __ldg(v.x + pos);
 #pragma unroll
-    for (int j = 0; j < NV; ++j) u[j] = ld_u(P, v, pos, j);
+    for (int j = 0; j < NV; ++j) u[j] = ld_u(P, v, pos, j0 + j);
   }
 }
 
@@ -128,15 +130,15 @@ __device__ __forceinline__ void load_slot(const sfxm_problem_t &P, const View &v
 // per variable, then pointer steps - the general per-slot path costs ~40 integer instructions per slot.
 template <int NV, int W>
 __device__ __forceinline__ bool gather_stencil(const sfxm_problem_t &P, const View &v, int64_t i, bool need_x,
-                                               double (&u)[W][NV], double (&xs)[W], int64_t (&off)[NV]) {
+                                               double (&u)[W][NV], double (&xs)[W], int64_t (&off)[NV], int j0 = 0) {
   const int64_t B = P.batch;
   const int nbl = (W == 3) ? 1 : P.nbl;   // a 3-cell stencil is always 1 + 1 + 1 (validate())
   const bool interior = (i >= nbl) && (i + (W - 1 - nbl) < P.nx);
   int64_t rs[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
-    rs[j] = (int64_t)P.var_stride[j] * B;
-    off[j] = (P.var_base[j] + P.var_off[j]) * B + v.m + i * rs[j];
+    rs[j] = (int64_t)P.var_stride[j0 + j] * B;
+    off[j] = (P.var_base[j0 + j] + P.var_off[j0 + j]) * B + v.m + i * rs[j];
   }
   if (interior) {
 #pragma unroll
@@ -154,7 +156,7 @@ __device__ __forceinline__ bool gather_stencil(const sfxm_problem_t &P, const Vi
     }
   } else {
 #pragma unroll
-    for (int s = 0; s < W; ++s) load_slot<NV>(P, v, i - nbl + s, xs[s], u[s]);
+    for (int s = 0; s < W; ++s) load_slot<NV>(P, v, i - nbl + s, xs[s], u[s], j0);
   }
   return interior;
 }

@@ -12,6 +12,10 @@ int launch_ad4(const Launch &L);
 int launch_euler_prim(const Launch &L);
 int launch_euler_cons(const Launch &L);
 
+// user models: plugins built from user CUDA source (splitfxm_b200/custom.py) register a launcher per slot
+typedef int (*user_launch_fn)(const void *launch);
+static user_launch_fn g_user[SFXM_MAX_USER_MODELS] = {nullptr};
+
 static int validate(const sfxm_problem_t &P) {
   if (P.nv < 1 || P.nv > SFXM_MAX_NV) return set_error("nv must be 1..4");
   if (P.nbl < 1 || P.nbr < 1 || P.nbl > SFXM_MAX_NB || P.nbr > SFXM_MAX_NB) return set_error("nb_left/nb_right must be 1..2");
@@ -38,6 +42,11 @@ static int dispatch(const Launch &L) {
     case SFXM_MODEL_EULER_CONS:
       if (P.nv != 3) return set_error("Euler1DConservative has 3 variables");
       return launch_euler_cons(L);
+  }
+  if (P.model >= SFXM_MODEL_USER0 && P.model < SFXM_MODEL_USER0 + SFXM_MAX_USER_MODELS) {
+    user_launch_fn fn = g_user[P.model - SFXM_MODEL_USER0];
+    if (!fn) return set_error("user model slot is not registered");
+    return fn(&L);
   }
   return set_error("unknown model");
 }
@@ -106,4 +115,10 @@ extern "C" int sfxm_geometry(const sfxm_problem_t *prob, const double *x_int, do
       return set_error("unknown scheme");
   }
   return check_launch("sfxm_geometry");
+}
+
+extern "C" int sfxm_register_user_model(int32_t slot, void *launch_fn) {
+  if (slot < 0 || slot >= SFXM_MAX_USER_MODELS || !launch_fn) return set_error("sfxm_register_user_model: bad argument");
+  g_user[slot] = (user_launch_fn)launch_fn;
+  return 0;
 }

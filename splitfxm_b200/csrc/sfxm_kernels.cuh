@@ -8,6 +8,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "sfxm_device.cuh"
 #include "sfxm_host.h"
@@ -20,7 +21,8 @@ namespace sfxm {
 __device__ __forceinline__ void thread_coords(int64_t &m, int64_t &i) {
   if (blockDim.x == 32) {
     m = (int64_t)blockIdx.x * 32 + threadIdx.x;
-    i = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * blockDim.y + threadIdx.y;
+    if (blockDim.y == 1) i = (int64_t)blockIdx.z * gridDim.y + blockIdx.y;   // one warp per CTA: the cell index is warp-uniform
+    else i = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * blockDim.y + threadIdx.y;
   } else {
     m = blockIdx.y;
     i = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
@@ -35,14 +37,18 @@ __global__ void __launch_bounds__(256)
 residual_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restrict__ x_int,
                 const double *__restrict__ params, int64_t param_stride, const double *__restrict__ y,
                 double *__restrict__ r_out, double *__restrict__ y_out, double dt,
-                const double *__restrict__ geom_tab) {
-  int64_t m, i;
-  thread_coords(m, i);
-  if (m >= P.batch || i >= P.nx) return;
+                const double *__restrict__ geom_tab, int strip) {
+  int64_t m, i0;
+  thread_coords(m, i0);
+  i0 *= strip;
+  if (m >= P.batch) return;
   double prm[Model::kParams];
 #pragma unroll
   for (int k = 0; k < Model::kParams; ++k) prm[k] = __ldg(params + (param_stride ? k * param_stride + m : k));
   View v{y, x_int, m, -1, 0, 0.0};
+  // strip > 1 only for one-warp CTAs (ensembles): the warp walks `strip` consecutive cells, so parameters and
+  // address bases are set up once and the neighbours' rows are still in L1 when the next cell needs them
+  for (int64_t i = i0; i < i0 + strip && i < P.nx; ++i) {
   double u[W][NV], xs[W], r[NV];
   int64_t off[NV];
   gather_stencil<NV, W>(P, v, i, geom_tab == nullptr, u, xs, off);
@@ -57,6 +63,7 @@ residual_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restri
     // the cell's own value is slot nbl (selected, not indexed: a dynamic index would push u[][] to local memory)
     const double uc = (W == 3 || P.nbl == 1) ? u[1][j] : u[W == 3 ? 1 : 2][j];
     if (y_out) y_out[off[j]] = uc + dt * r[j];              // sol.y += delta_t * f, simulation.py:459
+  }
   }
 }
 
@@ -220,6 +227,7 @@ jacobian_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restri
                 const double *__restrict__ params, int64_t param_stride, const double *__restrict__ y,
                 double eps, double *__restrict__ J, double *__restrict__ r0_out, uint32_t entry_mask,
                 const double *__restrict__ geom_tab) {
+  // (no strip loop here: wrapping this body in a loop costs registers - 128 + spills - and measured slower)
   int64_t m, i;
   thread_coords(m, i);
   if (m >= P.batch || i >= P.nx) return;
@@ -241,11 +249,160 @@ jacobian_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// Decoupled models (every variable obeys the same scalar equation): ONE THREAD PER (cell, variable, member).
+// Three times the warps of the cell-per-thread kernels at a third of the registers (latency hiding instead of
+// 21 % occupancy, profiles/README.md r1f), and with batch = 1 consecutive threads touch consecutive unknowns of
+// the cell-major vector.  threadIdx.y / blockIdx walk t = cell * NV + variable.
+// ------------------------------------------------------------------------------------------------
+template <class Model, int SCHEME, int NV, int W>
+__global__ void __launch_bounds__(256)
+residual_scalar_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restrict__ x_int,
+                       const double *__restrict__ params, int64_t param_stride, const double *__restrict__ y,
+                       double *__restrict__ r_out, double *__restrict__ y_out, double dt,
+                       const double *__restrict__ geom_tab) {
+  using M1 = typename Model::Scalar;
+  int64_t m, t;
+  thread_coords(m, t);
+  if (m >= P.batch || t >= P.nx * NV) return;
+  const int64_t i = t / NV;
+  const int j = (int)(t - i * NV);
+  double prm[M1::kParams];
+#pragma unroll
+  for (int k = 0; k < M1::kParams; ++k) prm[k] = __ldg(params + (param_stride ? k * param_stride + m : k));
+  View v{y, x_int, m, -1, 0, 0.0};
+  double u[W][1], xs[W], r[1];
+  int64_t off[1];
+  gather_stencil<1, W>(P, v, i, geom_tab == nullptr, u, xs, off, j);
+  Geom<SCHEME, W> geom = geom_tab ? Geom<SCHEME, W>(geom_tab, P.nx, i) : Geom<SCHEME, W>(xs);
+  geom.and_inputs(u, prm);
+  if (geom.fast) cell_residual<M1, SCHEME, 1, W, true>(prm, u, geom, r);
+  else cell_residual<M1, SCHEME, 1, W, false>(prm, u, geom, r);
+  if (r_out) r_out[off[0]] = r[0];
+  const double uc = (W == 3 || P.nbl == 1) ? u[1][0] : u[W == 3 ? 1 : 2][0];
+  if (y_out) y_out[off[0]] = uc + dt * r[0];                // sol.y += delta_t * f, simulation.py:459
+}
+
+template <class M1, int SCHEME, int W, bool FAST>
+__device__ __forceinline__ void jacobian_scalar_cell(const sfxm_problem_t &P, const double *__restrict__ x_int,
+                                                     const double *__restrict__ y, const double *prm, int64_t i,
+                                                     int j, int64_t m, bool interior, const double (&u)[W][1],
+                                                     const Geom<SCHEME, W> &geom, double eps, double r0,
+                                                     double *__restrict__ p, int nv, uint32_t row_mask) {
+  // p: entry (d = 0, r = j, c = 0) of this cell/member; row j of block d is at p + (d*nv*nv + c) * B.
+  // Writes the diagonal entry and the exact zeros of the other same-segment columns (row_mask bit c).
+  const int64_t B = P.batch;
+  const double reps = 1.0 / eps;
+  auto emit = [&](int d, double val) {
+    double *q = p + (int64_t)d * (nv * nv) * B;
+    for (int c = 0; c < nv; ++c)
+      if (row_mask & (1u << c)) q[(int64_t)c * B] = (c == j) ? val : 0.0;
+  };
+  if (interior) {
+#pragma unroll
+    for (int d = 0; d < W; ++d) {
+      double up[W][1], r1[1];
+#pragma unroll
+      for (int s = 0; s < W; ++s) up[s][0] = u[s][0];
+      up[d][0] = u[d][0] + eps;                             // simulation.py:337
+      cell_residual<M1, SCHEME, 1, W, FAST>(prm, up, geom, r1);                  // simulation.py:345
+      emit(d, div_known<FAST>(r1[0] - r0, eps, reps));                           // simulation.py:354
+    }
+    return;
+  }
+#pragma unroll 1
+  for (int d = 0; d < W; ++d) {
+    const int64_t pos = i - P.nbl + d;
+    int64_t pc = pos;
+    bool live = true, halo = false;
+    if (pos < 0) {
+      halo = (P.bc_ltype[j] == SFXM_BC_HALO);
+      live = halo || (P.bc_ltype[j] == SFXM_BC_PERIODIC);
+      pc = halo ? -1 : pos + P.nx;
+    } else if (pos >= P.nx) {
+      halo = (P.bc_rtype[j] == SFXM_BC_HALO);
+      live = halo || (P.bc_rtype[j] == SFXM_BC_PERIODIC);
+      pc = halo ? -1 : pos - P.nx;
+    }
+    double val = 0.0;
+    if (live) {
+      View vp{y, x_int, m, pc, j, eps};
+      double up[W][1], r1[1];
+#pragma unroll
+      for (int s = 0; s < W; ++s) {
+        const int64_t ps = i - P.nbl + s;
+        if (ps < 0) up[s][0] = ghost_u_left(P, vp, (int)(-ps - 1), j);
+        else if (ps >= P.nx) up[s][0] = ghost_u_right(P, vp, (int)(ps - P.nx), j);
+        else up[s][0] = (ps == pc) ? u[s][0] + eps : u[s][0];
+        if (halo && ps == pos) up[s][0] = up[s][0] + eps;
+      }
+      cell_residual<M1, SCHEME, 1, W, FAST>(prm, up, geom, r1);
+      val = div_known<FAST>(r1[0] - r0, eps, reps);
+    }
+    emit(d, val);
+  }
+}
+
+template <class Model, int SCHEME, int NV, int W>
+__global__ void __launch_bounds__(256)
+jacobian_scalar_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restrict__ x_int,
+                       const double *__restrict__ params, int64_t param_stride, const double *__restrict__ y,
+                       double eps, double *__restrict__ J, double *__restrict__ r0_out, uint32_t entry_mask,
+                       const double *__restrict__ geom_tab) {
+  using M1 = typename Model::Scalar;
+  int64_t m, t;
+  thread_coords(m, t);
+  if (m >= P.batch || t >= P.nx * NV) return;
+  const int64_t i = t / NV;
+  const int j = (int)(t - i * NV);
+  double prm[M1::kParams];
+#pragma unroll
+  for (int k = 0; k < M1::kParams; ++k) prm[k] = __ldg(params + (param_stride ? k * param_stride + m : k));
+  View v{y, x_int, m, -1, 0, 0.0};
+  double u[W][1], xs[W], r0[1];
+  int64_t off[1];
+  const bool interior = gather_stencil<1, W>(P, v, i, geom_tab == nullptr, u, xs, off, j);
+  Geom<SCHEME, W> geom = geom_tab ? Geom<SCHEME, W>(geom_tab, P.nx, i) : Geom<SCHEME, W>(xs);
+  geom.and_inputs(u, prm);
+  geom.fast = geom.fast && sane(eps, 120);
+  const int64_t B = P.batch;
+  double *p = J + ((i * W) * (int64_t)(NV * NV) + (int64_t)j * NV) * B + m;
+  const uint32_t row_mask = (entry_mask >> (j * NV)) & ((1u << NV) - 1u);
+  if (geom.fast) {
+    cell_residual<M1, SCHEME, 1, W, true>(prm, u, geom, r0);                     // simulation.py:320
+    jacobian_scalar_cell<M1, SCHEME, W, true>(P, x_int, y, prm, i, j, m, interior, u, geom, eps, r0[0], p, NV, row_mask);
+  } else {
+    cell_residual<M1, SCHEME, 1, W, false>(prm, u, geom, r0);
+    jacobian_scalar_cell<M1, SCHEME, W, false>(P, x_int, y, prm, i, j, m, interior, u, geom, eps, r0[0], p, NV, row_mask);
+  }
+  if (r0_out) r0_out[off[0]] = r0[0];
+}
+
+// ------------------------------------------------------------------------------------------------
 // dispatch
 // ------------------------------------------------------------------------------------------------
-static dim3 block_for(int64_t batch) { return batch >= 32 ? dim3(32, 8) : dim3(1, 256); }
-static dim3 grid_for(int64_t batch, int64_t ncells, dim3 b) {
-  const int64_t ctiles = (ncells + b.y - 1) / b.y;
+static int ensemble_block_y() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SFXM_BLOCK_Y");
+    v = e ? atoi(e) : 1;
+    if (v < 1 || v > 8) v = 1;
+  }
+  return v;
+}
+static int ensemble_strip() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SFXM_STRIP");
+    v = e ? atoi(e) : 8;
+    if (v < 1 || v > 4096) v = 8;
+  }
+  return v;
+}
+static dim3 block_for(int64_t batch) { return batch >= 32 ? dim3(32, ensemble_block_y()) : dim3(1, 256); }
+// cells per CTA row: one-warp CTAs walk a strip of cells
+static int strip_for(dim3 b) { return (b.x == 32 && b.y == 1) ? ensemble_strip() : 1; }
+static dim3 grid_for(int64_t batch, int64_t ncells, dim3 b, int strip = 1) {
+  const int64_t ctiles = (ncells + (int64_t)b.y * strip - 1) / ((int64_t)b.y * strip);
   if (b.x == 32) {   // x: member tiles, y/z: cell tiles
     const int64_t gy = ctiles < 65535 ? ctiles : 65535;
     return dim3((unsigned)((batch + 31) / 32), (unsigned)gy, (unsigned)((ctiles + gy - 1) / gy));
@@ -270,15 +427,32 @@ struct Launch {
 template <class Model, int SCHEME, int NV, int W>
 static int launch_t(const Launch &L) {
   const sfxm_problem_t &P = *L.P;
-  dim3 b = block_for(P.batch), g = grid_for(P.batch, P.nx, b);
-  if (g.z > 65535) return set_error("mesh too large for one launch");
-  if (L.op == OP_RESIDUAL)
-    residual_kernel<Model, SCHEME, NV, W><<<g, b, 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.out0, L.out1, L.scalar, L.geom);
-  else {
-    uint32_t mask = 0;
-    for (int r = 0; r < NV; ++r)
-      for (int c = 0; c < NV; ++c)
-        if (P.var_seg[r] == P.var_seg[c]) mask |= 1u << (r * NV + c);
+  uint32_t mask = 0;
+  for (int r = 0; r < NV; ++r)
+    for (int c = 0; c < NV; ++c)
+      if (P.var_seg[r] == P.var_seg[c]) mask |= 1u << (r * NV + c);
+  if constexpr (Model::kDecoupled) {
+   if (P.batch < 32) {
+    // (ensembles keep one thread per cell: the per-thread overhead - addresses, parameters, geometry, sanity check -
+    // is then shared by the NV variables; measured 0.77 ms vs 1.04 ms on the bench shape)
+    dim3 b = block_for(P.batch), g = grid_for(P.batch, P.nx * NV, b);
+    if (g.z > 65535) return set_error("mesh too large for one launch");
+    if (L.op == OP_RESIDUAL)
+      residual_scalar_kernel<Model, SCHEME, NV, W><<<g, b, 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.out0, L.out1, L.scalar, L.geom);
+    else
+      jacobian_scalar_kernel<Model, SCHEME, NV, W><<<g, b, 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.scalar, L.out0, L.out1, mask, L.geom);
+    return check_launch("sfxm kernel launch");
+  }
+  }
+  dim3 b = block_for(P.batch);
+  if (L.op == OP_RESIDUAL) {
+    const int strip = strip_for(b);
+    dim3 g = grid_for(P.batch, P.nx, b, strip);
+    if (g.z > 65535) return set_error("mesh too large for one launch");
+    residual_kernel<Model, SCHEME, NV, W><<<g, b, 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.out0, L.out1, L.scalar, L.geom, strip);
+  } else {
+    dim3 g = grid_for(P.batch, P.nx, b);
+    if (g.z > 65535) return set_error("mesh too large for one launch");
     jacobian_kernel<Model, SCHEME, NV, W><<<g, b, 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.scalar, L.out0, L.out1, mask, L.geom);
   }
   return check_launch("sfxm kernel launch");

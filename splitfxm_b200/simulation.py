@@ -8,7 +8,7 @@ import math
 
 import numpy as np
 import torch
-from scipy.sparse import coo_matrix
+from scipy.sparse import lil_matrix
 
 from . import _lib
 from .bc import apply_BC, describe_bcs
@@ -26,6 +26,24 @@ from .simhelper import array_list_reshape, report_bounds
 from .system import System
 
 JAC_REQUIRED = ["Radau", "BDF"]
+
+
+def _lil_from_coo(rows, cols, vals, n):
+    """lil_matrix with the given (unique) entries, filled row list by row list - several times cheaper than
+    coo_matrix(...).tolil() for the few thousand entries of a banded Jacobian."""
+    order = np.lexsort((cols, rows))
+    rows, cols, vals = rows[order], cols[order], vals[order]
+    counts = np.bincount(rows, minlength=n)
+    cl, vl = cols.tolist(), vals.tolist()
+    L = lil_matrix((n, n))
+    at = 0
+    lrows, ldata = L.rows, L.data
+    for i, c in enumerate(counts.tolist()):
+        if c:
+            lrows[i] = cl[at:at + c]
+            ldata[i] = vl[at:at + c]
+            at += c
+    return L
 
 
 class Simulation:
@@ -158,8 +176,7 @@ class Simulation:
         self._store(eng, y, split, split_locs)
         Jh = J.cpu().numpy().reshape(eng.nx, eng.W, nv, nv)
         rows, cols, vals = eng.jacobian_coo(Jh, split, split_locs)
-        n = num_points * nv
-        return coo_matrix((vals, (rows, cols)), shape=(n, n)).tolil()
+        return _lil_from_coo(rows, cols, vals, num_points * nv)
 
     def evolve(self, t_diff: float, split=False, split_locs=None, method='RK45', rtol=1e-3, atol=1e-6,
                max_step=np.inf, bounds=None):
