@@ -13,6 +13,10 @@
 #include "sfxm_device.cuh"
 #include "sfxm_host.h"
 
+#ifndef SFXM_PAIR_MIN_CTAS
+#define SFXM_PAIR_MIN_CTAS 16
+#endif
+
 namespace sfxm {
 
 // (member, cell) of this thread.  Ensembles (blockDim.x == 32): blockIdx.x walks member tiles, so the CTAs that are
@@ -64,6 +68,100 @@ residual_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restri
     const double uc = (W == 3 || P.nbl == 1) ? u[1][j] : u[W == 3 ? 1 : 2][j];
     if (y_out) y_out[off[j]] = uc + dt * r[j];              // sol.y += delta_t * f, simulation.py:459
   }
+  }
+}
+
+// Ensemble twin of residual_kernel: one warp per CTA walking `strip` cells, two adjacent members per lane
+// (16-byte loads/stores), warp-uniform cell index.  Boundary cells and insane inputs fall back per member.
+template <class Model, int SCHEME, int NV, int W>
+__device__ __noinline__ void residual_member_noinline(const sfxm_problem_t &P, const double *__restrict__ x_int,
+                                                      const double *__restrict__ params, int64_t param_stride,
+                                                      const double *__restrict__ y, double *__restrict__ r_out,
+                                                      double *__restrict__ y_out, double dt,
+                                                      const double *__restrict__ geom_tab, int64_t i, int64_t m) {
+  double prm[Model::kParams];
+#pragma unroll
+  for (int k = 0; k < Model::kParams; ++k) prm[k] = __ldg(params + (param_stride ? k * param_stride + m : k));
+  View v{y, x_int, m, -1, 0, 0.0};
+  double u[W][NV], xs[W], r[NV];
+  int64_t off[NV];
+  gather_stencil<NV, W>(P, v, i, geom_tab == nullptr, u, xs, off);
+  Geom<SCHEME, W> geom = geom_tab ? Geom<SCHEME, W>(geom_tab, P.nx, i) : Geom<SCHEME, W>(xs);
+  geom.and_inputs(u, prm);
+  if (geom.fast) cell_residual<Model, SCHEME, NV, W, true>(prm, u, geom, r);
+  else cell_residual<Model, SCHEME, NV, W, false>(prm, u, geom, r);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    if (r_out) r_out[off[j]] = r[j];
+    const double uc = (W == 3 || P.nbl == 1) ? u[1][j] : u[W == 3 ? 1 : 2][j];
+    if (y_out) y_out[off[j]] = uc + dt * r[j];
+  }
+}
+
+template <class Model, int SCHEME, int NV, int W>
+__global__ void __launch_bounds__(32)
+residual_pair_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restrict__ x_int,
+                     const double *__restrict__ params, int64_t param_stride, const double *__restrict__ y,
+                     double *__restrict__ r_out, double *__restrict__ y_out, double dt,
+                     const double *__restrict__ geom_tab, int strip) {
+  const int64_t i0 = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * strip;
+  const int64_t m0 = ((int64_t)blockIdx.x * 32 + threadIdx.x) * 2;
+  if (m0 >= P.batch) return;
+  const int64_t B = P.batch;
+  const int nbl = (W == 3) ? 1 : P.nbl;
+  double prm[2][Model::kParams];
+#pragma unroll
+  for (int k = 0; k < Model::kParams; ++k) {
+    if (param_stride) {
+      const double2 t = __ldg(reinterpret_cast<const double2 *>(params + k * param_stride + m0));
+      prm[0][k] = t.x;
+      prm[1][k] = t.y;
+    } else {
+      prm[0][k] = prm[1][k] = __ldg(params + k);
+    }
+  }
+  bool prm_ok = true;
+#pragma unroll
+  for (int k = 0; k < Model::kParams; ++k) prm_ok = prm_ok & sane(prm[0][k], 120) & sane(prm[1][k], 120);
+  for (int64_t i = i0; i < i0 + strip && i < P.nx; ++i) {
+    const bool interior = (i >= nbl) && (i + (W - 1 - nbl) < P.nx);
+    bool ok = interior && prm_ok;
+    double u[2][W][NV];
+    int64_t off[NV];
+    if (ok) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int64_t rs = (int64_t)P.var_stride[j] * B;
+        off[j] = (P.var_base[j] + P.var_off[j]) * B + m0 + i * rs;
+        const double *q = y + (off[j] - nbl * rs);
+#pragma unroll
+        for (int s = 0; s < W; ++s) {
+          const double2 t = __ldg(reinterpret_cast<const double2 *>(q));
+          u[0][s][j] = t.x;
+          u[1][s][j] = t.y;
+          ok = ok & sane(t.x, 120) & sane(t.y, 120);
+          q += rs;
+        }
+      }
+    }
+    const Geom<SCHEME, W> geom(geom_tab, P.nx, i);
+    if (!(ok && geom.fast)) {
+      residual_member_noinline<Model, SCHEME, NV, W>(P, x_int, params, param_stride, y, r_out, y_out, dt, geom_tab, i, m0);
+      residual_member_noinline<Model, SCHEME, NV, W>(P, x_int, params, param_stride, y, r_out, y_out, dt, geom_tab, i, m0 + 1);
+      continue;
+    }
+    double r[2][NV];
+#pragma unroll
+    for (int v = 0; v < 2; ++v) cell_residual<Model, SCHEME, NV, W, true>(prm[v], u[v], geom, r[v]);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      if (r_out) *reinterpret_cast<double2 *>(r_out + off[j]) = make_double2(r[0][j], r[1][j]);
+      if (y_out) {
+        const double c0 = (W == 3 || P.nbl == 1) ? u[0][1][j] : u[0][W == 3 ? 1 : 2][j];
+        const double c1 = (W == 3 || P.nbl == 1) ? u[1][1][j] : u[1][W == 3 ? 1 : 2][j];
+        *reinterpret_cast<double2 *>(y_out + off[j]) = make_double2(c0 + dt * r[0][j], c1 + dt * r[1][j]);   // simulation.py:459
+      }
+    }
   }
 }
 
@@ -221,16 +319,13 @@ __device__ __forceinline__ void jacobian_cell(const sfxm_problem_t &P, const dou
   }
 }
 
+// Everything one (cell, member) does for the Jacobian: gather, sanity check, block row (general path).
 template <class Model, int SCHEME, int NV, int W>
-__global__ void __launch_bounds__(256)
-jacobian_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restrict__ x_int,
-                const double *__restrict__ params, int64_t param_stride, const double *__restrict__ y,
-                double eps, double *__restrict__ J, double *__restrict__ r0_out, uint32_t entry_mask,
-                const double *__restrict__ geom_tab) {
-  // (no strip loop here: wrapping this body in a loop costs registers - 128 + spills - and measured slower)
-  int64_t m, i;
-  thread_coords(m, i);
-  if (m >= P.batch || i >= P.nx) return;
+__device__ __forceinline__ void jacobian_member(const sfxm_problem_t &P, const double *__restrict__ x_int,
+                                                const double *__restrict__ params, int64_t param_stride,
+                                                const double *__restrict__ y, double eps, double *__restrict__ J,
+                                                double *__restrict__ r0_out, uint32_t entry_mask,
+                                                const double *__restrict__ geom_tab, int64_t i, int64_t m) {
   double prm[Model::kParams];
 #pragma unroll
   for (int k = 0; k < Model::kParams; ++k) prm[k] = __ldg(params + (param_stride ? k * param_stride + m : k));
@@ -246,6 +341,124 @@ jacobian_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restri
     jacobian_cell<Model, SCHEME, NV, W, true>(P, x_int, y, prm, i, m, interior, off, u, geom, eps, p, r0_out, entry_mask);
   else
     jacobian_cell<Model, SCHEME, NV, W, false>(P, x_int, y, prm, i, m, interior, off, u, geom, eps, p, r0_out, entry_mask);
+}
+
+// out-of-line copy for the rare paths of the pair kernel (keeps its straight-line path free of their registers)
+template <class Model, int SCHEME, int NV, int W>
+__device__ __noinline__ void jacobian_member_noinline(const sfxm_problem_t &P, const double *__restrict__ x_int,
+                                                      const double *__restrict__ params, int64_t param_stride,
+                                                      const double *__restrict__ y, double eps, double *__restrict__ J,
+                                                      double *__restrict__ r0_out, uint32_t entry_mask,
+                                                      const double *__restrict__ geom_tab, int64_t i, int64_t m) {
+  jacobian_member<Model, SCHEME, NV, W>(P, x_int, params, param_stride, y, eps, J, r0_out, entry_mask, geom_tab, i, m);
+}
+
+template <class Model, int SCHEME, int NV, int W>
+__global__ void __launch_bounds__(256)
+jacobian_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restrict__ x_int,
+                const double *__restrict__ params, int64_t param_stride, const double *__restrict__ y,
+                double eps, double *__restrict__ J, double *__restrict__ r0_out, uint32_t entry_mask,
+                const double *__restrict__ geom_tab) {
+  // (no strip loop here: wrapping this body in a loop costs registers - 128 + spills - and measured slower)
+  int64_t m, i;
+  thread_coords(m, i);
+  if (m >= P.batch || i >= P.nx) return;
+  jacobian_member<Model, SCHEME, NV, W>(P, x_int, params, param_stride, y, eps, J, r0_out, entry_mask, geom_tab, i, m);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ensembles: one warp per CTA, the cell index comes from blockIdx (warp-uniform address arithmetic) and every
+// lane owns TWO adjacent members: 16-byte loads/stores halve the memory instructions and their 64-bit address
+// arithmetic per member, and the two members' division chains interleave (the r1f profile is latency-bound on
+// those chains at 21 % occupancy).  Needs an even batch; boundary cells and threads whose inputs fail the
+// sanity check take the general path member by member.
+// ------------------------------------------------------------------------------------------------
+template <class Model, int SCHEME, int NV, int W>
+__global__ void __launch_bounds__(32, SFXM_PAIR_MIN_CTAS)
+jacobian_pair_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restrict__ x_int,
+                     const double *__restrict__ params, int64_t param_stride, const double *__restrict__ y,
+                     double eps, double *__restrict__ J, double *__restrict__ r0_out, uint32_t entry_mask,
+                     const double *__restrict__ geom_tab) {
+  const int64_t i = (int64_t)blockIdx.z * gridDim.y + blockIdx.y;
+  const int64_t m0 = ((int64_t)blockIdx.x * 32 + threadIdx.x) * 2;
+  if (m0 >= P.batch || i >= P.nx) return;
+  const int64_t B = P.batch;
+  const int nbl = (W == 3) ? 1 : P.nbl;
+  const bool interior = (i >= nbl) && (i + (W - 1 - nbl) < P.nx);
+  if (!interior || geom_tab == nullptr) {   // warp-uniform: boundary cells take the general path
+    jacobian_member_noinline<Model, SCHEME, NV, W>(P, x_int, params, param_stride, y, eps, J, r0_out, entry_mask, geom_tab, i, m0);
+    jacobian_member_noinline<Model, SCHEME, NV, W>(P, x_int, params, param_stride, y, eps, J, r0_out, entry_mask, geom_tab, i, m0 + 1);
+    return;
+  }
+  bool vector_ok = true;
+  double prm[2][Model::kParams];
+  double u[2][W][NV];
+  int64_t off[NV];
+  const Geom<SCHEME, W> geom(geom_tab, P.nx, i);
+  {
+#pragma unroll
+    for (int k = 0; k < Model::kParams; ++k) {
+      if (param_stride) {
+        const double2 t = __ldg(reinterpret_cast<const double2 *>(params + k * param_stride + m0));
+        prm[0][k] = t.x;
+        prm[1][k] = t.y;
+      } else {
+        prm[0][k] = prm[1][k] = __ldg(params + k);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int64_t rs = (int64_t)P.var_stride[j] * B;
+      off[j] = (P.var_base[j] + P.var_off[j]) * B + m0 + i * rs;
+      const double *q = y + (off[j] - nbl * rs);
+#pragma unroll
+      for (int s = 0; s < W; ++s) {
+        const double2 t = __ldg(reinterpret_cast<const double2 *>(q));
+        u[0][s][j] = t.x;
+        u[1][s][j] = t.y;
+        q += rs;
+      }
+    }
+    Geom<SCHEME, W> g0 = geom, g1 = geom;
+    g0.and_inputs(u[0], prm[0]);
+    g1.and_inputs(u[1], prm[1]);
+    vector_ok = g0.fast & g1.fast & sane(eps, 120);
+  }
+  if (!vector_ok) {
+    jacobian_member_noinline<Model, SCHEME, NV, W>(P, x_int, params, param_stride, y, eps, J, r0_out, entry_mask, geom_tab, i, m0);
+    jacobian_member_noinline<Model, SCHEME, NV, W>(P, x_int, params, param_stride, y, eps, J, r0_out, entry_mask, geom_tab, i, m0 + 1);
+    return;
+  }
+  const double reps = 1.0 / eps;
+  double r0[2][NV];
+#pragma unroll
+  for (int v = 0; v < 2; ++v) cell_residual<Model, SCHEME, NV, W, true>(prm[v], u[v], geom, r0[v]);   // simulation.py:320
+  if (r0_out) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) *reinterpret_cast<double2 *>(r0_out + off[j]) = make_double2(r0[0][j], r0[1][j]);
+  }
+  double *p = J + (i * W) * (int64_t)(NV * NV) * B + m0;
+#pragma unroll
+  for (int d = 0; d < W; ++d) {
+    double cols[2][NV][NV];   // [member][c][r]
+#pragma unroll
+    for (int v = 0; v < 2; ++v)
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+        double upc[W];
+#pragma unroll
+        for (int s = 0; s < W; ++s) upc[s] = u[v][s][c];
+        upc[d] = u[v][d][c] + eps;                          // simulation.py:337
+        jac_column<Model, SCHEME, NV, W, true>(prm[v], u[v], upc, c, geom, r0[v], eps, reps, cols[v][c]);
+      }
+#pragma unroll
+    for (int r = 0; r < NV; ++r)
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+        if (entry_mask & (1u << (r * NV + c))) *reinterpret_cast<double2 *>(p) = make_double2(cols[0][c][r], cols[1][c][r]);
+        p += B;
+      }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -389,6 +602,14 @@ static int ensemble_block_y() {
   }
   return v;
 }
+static bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SFXM_PAIR");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
 static int ensemble_strip() {
   static int v = -1;
   if (v < 0) {
@@ -445,11 +666,23 @@ static int launch_t(const Launch &L) {
   }
   }
   dim3 b = block_for(P.batch);
-  if (L.op == OP_RESIDUAL) {
+  if (L.op == OP_RESIDUAL && P.batch >= 64 && P.batch % 2 == 0 && L.geom != nullptr && pair_enabled()) {
+    const int strip = ensemble_strip();
+    const int64_t tiles = (P.nx + strip - 1) / strip;
+    const int64_t gy = tiles < 65535 ? tiles : 65535;
+    dim3 g((unsigned)((P.batch / 2 + 31) / 32), (unsigned)gy, (unsigned)((tiles + gy - 1) / gy));
+    if (g.z > 65535) return set_error("mesh too large for one launch");
+    residual_pair_kernel<Model, SCHEME, NV, W><<<g, dim3(32, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.out0, L.out1, L.scalar, L.geom, strip);
+  } else if (L.op == OP_RESIDUAL) {
     const int strip = strip_for(b);
     dim3 g = grid_for(P.batch, P.nx, b, strip);
     if (g.z > 65535) return set_error("mesh too large for one launch");
     residual_kernel<Model, SCHEME, NV, W><<<g, b, 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.out0, L.out1, L.scalar, L.geom, strip);
+  } else if (P.batch >= 64 && P.batch % 2 == 0 && L.geom != nullptr && pair_enabled()) {
+    const int64_t gy = P.nx < 65535 ? P.nx : 65535;
+    dim3 g((unsigned)((P.batch / 2 + 31) / 32), (unsigned)gy, (unsigned)((P.nx + gy - 1) / gy));
+    if (g.z > 65535) return set_error("mesh too large for one launch");
+    jacobian_pair_kernel<Model, SCHEME, NV, W><<<g, dim3(32, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.scalar, L.out0, L.out1, mask, L.geom);
   } else {
     dim3 g = grid_for(P.batch, P.nx, b);
     if (g.z > 65535) return set_error("mesh too large for one launch");
