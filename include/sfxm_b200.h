@@ -114,6 +114,14 @@ int sfxm_block_tridiag_solve(const sfxm_problem_t *prob, const double *J, const 
                              const int32_t *active, int32_t seg_lo, int32_t seg_hi, double *s, double *work,
                              int32_t *status, void *stream);
 
+/* Same contract as sfxm_block_tridiag_solve, by block parallel cyclic reduction: one thread per (cell, member)
+ * and ceil(log2 nx) streaming passes instead of one thread per member - the solver for a single large mesh or
+ * a small batch.  work: sfxm_pcr_workspace_bytes(). */
+int64_t sfxm_pcr_workspace_bytes(const sfxm_problem_t *prob);
+int sfxm_block_tridiag_solve_pcr(const sfxm_problem_t *prob, const double *J, const double *f, const double *shift,
+                                 const int32_t *active, int32_t seg_lo, int32_t seg_hi, double *s, double *work,
+                                 int32_t *status, void *stream);
+
 /* Per-member sums of squares over a flat-index range [lo, hi): out[m] = sum v[q*batch+m]^2, accumulated in a
  * fixed order (deterministic).  work: sfxm_sumsq_workspace_bytes(hi - lo, batch).  The norms of
  * splitnewton's convergence criterion. */

@@ -51,6 +51,8 @@ SIGNATURES = {
     "sfxm_jacobian": (ctypes.c_int, [_PP, c_vp, c_vp, c_i64, c_vp, c_vp, c_f64, c_vp, c_vp, c_vp]),
     "sfxm_solve_workspace_bytes": (c_i64, [_PP]),
     "sfxm_block_tridiag_solve": (ctypes.c_int, [_PP, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_pcr_workspace_bytes": (c_i64, [_PP]),
+    "sfxm_block_tridiag_solve_pcr": (ctypes.c_int, [_PP, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_sumsq_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "sfxm_sumsq": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "sfxm_axpy_masked": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),

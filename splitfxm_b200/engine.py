@@ -177,17 +177,28 @@ class Engine:
         _lib.count()
         return J
 
-    def solve(self, J, f, s, split=False, split_locs=None, seg_lo=0, seg_hi=None, shift=None, active=None, status=None):
+    def solve(self, J, f, s, split=False, split_locs=None, seg_lo=0, seg_hi=None, shift=None, active=None, status=None,
+              method=None):
         """(J_seg + shift I) s = -f for segments [seg_lo, seg_hi)."""
         P, segs = self.problem(split, split_locs)
         if seg_hi is None:
             seg_hi = len(segs)
-        nbytes = self.lib.sfxm_solve_workspace_bytes(ctypes.byref(P))
-        work = self._scratch("solve", nbytes // 8)
-        _lib.check(self.lib.sfxm_block_tridiag_solve(ctypes.byref(P), _lib.ptr(J), _lib.ptr(f), _lib.ptr(shift),
-                                                     _lib.ptr(active), int(seg_lo), int(seg_hi), _lib.ptr(s),
-                                                     _lib.ptr(work), _lib.ptr(status), _lib.stream_ptr()))
-        _lib.count(seg_hi - seg_lo)
+        if method is None:
+            # one thread per member (Thomas) needs thousands of members to fill the GPU; below that, one thread per
+            # (cell, member) and log2(nx) passes (parallel cyclic reduction)
+            method = "thomas" if self.batch >= 2048 else "pcr"
+        if method == "thomas":
+            nbytes = self.lib.sfxm_solve_workspace_bytes(ctypes.byref(P))
+            work = self._scratch("solve", nbytes // 8)
+            fn = self.lib.sfxm_block_tridiag_solve
+            _lib.count(seg_hi - seg_lo)
+        else:
+            nbytes = self.lib.sfxm_pcr_workspace_bytes(ctypes.byref(P))
+            work = self._scratch("pcr", nbytes // 8)
+            fn = self.lib.sfxm_block_tridiag_solve_pcr
+            _lib.count((seg_hi - seg_lo) * (2 + max(self.nx - 1, 1).bit_length()))
+        _lib.check(fn(ctypes.byref(P), _lib.ptr(J), _lib.ptr(f), _lib.ptr(shift), _lib.ptr(active), int(seg_lo), int(seg_hi),
+                      _lib.ptr(s), _lib.ptr(work), _lib.ptr(status), _lib.stream_ptr()))
         return s
 
     def sumsq(self, v, lo=0, hi=None, out=None):
