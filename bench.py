@@ -330,7 +330,7 @@ def extras(torch, sf, ens, Y, dev, peak):
     out["ensemble_split_newton"] = {"members": B, "seconds": dt, "steady_states_per_s": B / dt,
                                     "iterations_min_max": [int(its.min()), int(its.max())], "max_abs_residual": res}
     sweep = []
-    for nx in (1000, 10000, 100000, 1000000):
+    for nx in (250, 1000, 10000, 100000, 1000000):
         d = sf.Domain.from_size(nx, 1, 1, COMPS)
         sim = sf.Simulation(d, AdvectionDiffusion(0.2, 0.001, "FDM"), ICS, BCS, sf.FDSchemes.CENTRAL)
         e1 = sim._engine()
@@ -339,9 +339,23 @@ def extras(torch, sf, ens, Y, dev, peak):
         rr = torch.empty_like(y)
         ms_j = timed(lambda: e1.jacobian(y, SPLIT, LOCS, J=Jb), 5)
         ms_r = timed(lambda: e1.residual(y, rr, SPLIT, LOCS), 5)
+        ss = torch.zeros_like(y)
+        st1 = torch.zeros(1, dtype=torch.int32, device=dev)
+
+        def newton_iteration():      # one Newton iteration of the device driver: J + f, solve (PCR), update, criterion norms
+            e1.jacobian(y, SPLIT, LOCS, J=Jb, r0=rr)
+            e1.solve(Jb, rr, ss, SPLIT, LOCS, status=st1)
+            e1.axpy(y, ss)
+            e1.sumsq(ss)
+            e1.sumsq(y)
+        ms_n = timed(newton_iteration, 3)
+        t0 = time.perf_counter()
+        iters = sim.steady_state(split=SPLIT, split_locs=LOCS)       # public API, host buffers in and out
+        t_ss = time.perf_counter() - t0
         sweep.append({"nx": nx, "jacobian_ms": ms_j, "jacobian_assemblies_per_s": 1e3 / ms_j,
                       "jacobian_GBps": nx * (24 + 8 + 15 * 8) / ms_j / 1e6, "residual_ms": ms_r,
-                      "residual_GBps": nx * 56 / ms_r / 1e6})
+                      "residual_GBps": nx * 56 / ms_r / 1e6, "newton_iteration_ms": ms_n,
+                      "newton_iterations_per_s": 1e3 / ms_n, "steady_state_api_s": t_ss, "steady_state_iterations": iters})
     out["single_mesh_sweep"] = sweep
     return out
 

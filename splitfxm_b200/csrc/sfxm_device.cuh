@@ -386,46 +386,44 @@ struct Geom {
 };
 
 // FAST: this thread's inputs passed the sanity check, quotients use div_known's FMAs (else the IEEE division)
+//
+// cell_combine: the stencil arithmetic on flux values Fv[s] = F(u[s]), Dv[s] = D(u[s]) already evaluated per slot
+// (sigma_c = spectral radius at the centre slot, Lax-Friedrichs only).  cell_residual evaluates them itself; the
+// warp-cooperative kernel evaluates each cell's fluxes once and passes them between lanes by shuffle.
 template <class Model, int SCHEME, int NV, int W, bool FAST>
-__device__ __forceinline__ void cell_residual(const double *prm, const double (&u)[W][NV], const Geom<SCHEME, W> &g,
-                                              double (&r)[NV]) {
+__device__ __forceinline__ void cell_combine(const double *prm, const double (&u)[W][NV], const double (&Fv)[W][NV],
+                                             const double (&Dv)[W][NV], double sigma_c, const Geom<SCHEME, W> &g,
+                                             double (&r)[NV]) {
   if constexpr (SCHEME == SFXM_FV_LAX_FRIEDRICHS || SCHEME == SFXM_FV_CENTRAL || SCHEME == SFXM_FV_UPWIND) {
     static_assert(W == 3 || SCHEME > SFXM_FV_UPWIND, "FV schemes use a 3-cell stencil");
-    double Fl[NV], Fc[NV], Fr[NV], Fw[NV], Fe[NV];
-    Model::F(prm, u[0], Fl);
-    Model::F(prm, u[1], Fc);
-    Model::F(prm, u[2], Fr);
+    double Fw[NV], Fe[NV];
     if constexpr (SCHEME == SFXM_FV_LAX_FRIEDRICHS) {
-      const double hs = 0.5 * Model::sigma(prm, u[1]);      // flux.pyx:98-99, "0.5 * sigma * u_diff"
+      const double hs = 0.5 * sigma_c;                      // flux.pyx:98-99, "0.5 * sigma * u_diff"
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        Fw[j] = 0.5 * (Fl[j] + Fc[j]) - hs * (u[1][j] - u[0][j]);   // flux.pyx:154-160
-        Fe[j] = 0.5 * (Fc[j] + Fr[j]) - hs * (u[2][j] - u[1][j]);   // flux.pyx:163-167
+        Fw[j] = 0.5 * (Fv[0][j] + Fv[1][j]) - hs * (u[1][j] - u[0][j]);   // flux.pyx:154-160
+        Fe[j] = 0.5 * (Fv[1][j] + Fv[2][j]) - hs * (u[2][j] - u[1][j]);   // flux.pyx:163-167
       }
     } else if constexpr (SCHEME == SFXM_FV_CENTRAL) {
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        Fw[j] = 0.5 * (Fl[j] + Fc[j]);                      // flux.pyx:253-255
-        Fe[j] = 0.5 * (Fc[j] + Fr[j]);
+        Fw[j] = 0.5 * (Fv[0][j] + Fv[1][j]);                // flux.pyx:253-255
+        Fe[j] = 0.5 * (Fv[1][j] + Fv[2][j]);
       }
     } else {                                                // UPWIND, diagonal dFdU only (R = I)
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         const bool pos = Model::eig(prm, u[1], j) > 0.0;    // flux.pyx:209-218
-        Fw[j] = pos ? Fl[j] : Fc[j];
-        Fe[j] = pos ? Fc[j] : Fr[j];
+        Fw[j] = pos ? Fv[0][j] : Fv[1][j];
+        Fe[j] = pos ? Fv[1][j] : Fv[2][j];
       }
     }
     if constexpr (Model::kHasDiffusion) {
-      double Dl[NV], Dc[NV], Dr[NV];
-      Model::D(prm, u[0], Dl);
-      Model::D(prm, u[1], Dc);
-      Model::D(prm, u[2], Dr);
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        const double DFw = div_known<FAST>(Dc[j] - Dl[j], g.d[0], g.rd[0]);      // flux.pyx:288
-        const double DFe = div_known<FAST>(Dr[j] - Dc[j], g.d[1], g.rd[1]);      // flux.pyx:297
-        r[j] = (0.0 - g.inv * (Fe[j] - Fw[j])) + g.inv * (DFe - DFw);      // fv_transport.py:58
+        const double DFw = div_known<FAST>(Dv[1][j] - Dv[0][j], g.d[0], g.rd[0]);      // flux.pyx:288
+        const double DFe = div_known<FAST>(Dv[2][j] - Dv[1][j], g.d[1], g.rd[1]);      // flux.pyx:297
+        r[j] = (0.0 - g.inv * (Fe[j] - Fw[j])) + g.inv * (DFe - DFw);                  // fv_transport.py:58
       }
     } else {
       // D == 0: (Dc-Dl)/hw = +0, DFe-DFw = +0, inv*0 = 0, and a + 0 = a
@@ -433,45 +431,48 @@ __device__ __forceinline__ void cell_residual(const double *prm, const double (&
       for (int j = 0; j < NV; ++j) r[j] = (0.0 - g.inv * (Fe[j] - Fw[j])) + 0.0;
     }
   } else if constexpr (SCHEME == SFXM_FD_CENTRAL) {
-    double Fl[NV], Fr[NV];
-    Model::F(prm, u[0], Fl);
-    Model::F(prm, u[2], Fr);
-    double Dl[NV], Dc[NV], Dr[NV];
-    Model::D(prm, u[0], Dl);
-    Model::D(prm, u[1], Dc);
-    Model::D(prm, u[2], Dr);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      const double dF = div_known<FAST>(Fr[j] - Fl[j], g.d[0], g.rd[0]);        // derivatives.pyx:81
+      const double dF = div_known<FAST>(Fv[2][j] - Fv[0][j], g.d[0], g.rd[0]);         // derivatives.pyx:81
       double d2 = 0.0;
       if constexpr (Model::kHasDiffusion) {
-        const double Dw = div_known<FAST>(Dc[j] - Dl[j], g.d[1], g.rd[1]);      // derivatives.pyx:102
-        const double De = div_known<FAST>(Dr[j] - Dc[j], g.d[2], g.rd[2]);      // derivatives.pyx:109
-        d2 = div_known<FAST>(De - Dw, g.d[3], g.rd[3]);                         // derivatives.pyx:112
+        const double Dw = div_known<FAST>(Dv[1][j] - Dv[0][j], g.d[1], g.rd[1]);       // derivatives.pyx:102
+        const double De = div_known<FAST>(Dv[2][j] - Dv[1][j], g.d[2], g.rd[2]);       // derivatives.pyx:109
+        d2 = div_known<FAST>(De - Dw, g.d[3], g.rd[3]);                                // derivatives.pyx:112
       }
       r[j] = (0.0 - dF) + d2;                               // fd_transport.py:46-50
     }
   } else {                                                  // FD RIGHT_BIAS, 4 slots
     static_assert(W == 4 || SCHEME != SFXM_FD_RIGHT_BIAS, "RIGHT_BIAS uses a 4-cell stencil");
-    double F0[NV], F1[NV], F2[NV], F3[NV];
-    Model::F(prm, u[0], F0);
-    Model::F(prm, u[1], F1);
-    Model::F(prm, u[2], F2);
-    Model::F(prm, u[W - 1], F3);
-    double D0[NV], D1[NV], D2[NV], D3[NV];
-    Model::D(prm, u[0], D0);
-    Model::D(prm, u[1], D1);
-    Model::D(prm, u[2], D2);
-    Model::D(prm, u[W - 1], D3);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      const double dF = div_known<FAST>(((-F0[j] - F1[j]) + F2[j]) + F3[j], g.d[0], g.rd[0]);      // derivatives.pyx:88-90
+      const double dF = div_known<FAST>(((-Fv[0][j] - Fv[1][j]) + Fv[2][j]) + Fv[W - 1][j], g.d[0], g.rd[0]);   // derivatives.pyx:88-90
       double d2 = 0.0;
       if constexpr (Model::kHasDiffusion)
-        d2 = div_known<FAST>(((D0[j] - D1[j]) - D2[j]) + D3[j], g.d[1], g.rd[1]);                  // :119-121
+        d2 = div_known<FAST>(((Dv[0][j] - Dv[1][j]) - Dv[2][j]) + Dv[W - 1][j], g.d[1], g.rd[1]);               // :119-121
       r[j] = (0.0 - dF) + d2;
     }
   }
+}
+
+template <class Model, int SCHEME, int NV, int W, bool FAST>
+__device__ __forceinline__ void cell_residual(const double *prm, const double (&u)[W][NV], const Geom<SCHEME, W> &g,
+                                              double (&r)[NV]) {
+  // fluxes per slot (slots a scheme does not use are dead code: FD CENTRAL never reads Fv[1])
+  double Fv[W][NV], Dv[W][NV];
+#pragma unroll
+  for (int s = 0; s < W; ++s) {
+    Model::F(prm, u[s], Fv[s]);
+    if constexpr (Model::kHasDiffusion) {
+      Model::D(prm, u[s], Dv[s]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) Dv[s][j] = 0.0;
+    }
+  }
+  double sigma_c = 0.0;
+  if constexpr (SCHEME == SFXM_FV_LAX_FRIEDRICHS) sigma_c = Model::sigma(prm, u[1]);
+  cell_combine<Model, SCHEME, NV, W, FAST>(prm, u, Fv, Dv, sigma_c, g, r);
 }
 
 }  // namespace sfxm

@@ -166,6 +166,81 @@ residual_pair_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
 }
 
 // ------------------------------------------------------------------------------------------------
+// Coupled models on one mesh (batch < 32): warp-cooperative residual.  Consecutive lanes own consecutive cells; each
+// lane loads ITS cell and evaluates F, D (and the spectral radius) ONCE, the stencil neighbours' values and fluxes
+// arrive by warp shuffle - a third of the loads and of the flux evaluations (the Euler fluxes are three IEEE
+// divisions each) of the one-thread-does-everything kernel.  Lanes [nbl, 32 - nbr) of a warp produce residuals, the
+// outer lanes only feed their neighbours.  Warps that touch a domain end use the general per-thread path.
+// ------------------------------------------------------------------------------------------------
+template <class Model, int SCHEME, int NV, int W>
+__global__ void __launch_bounds__(256)
+residual_warp_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restrict__ x_int,
+                     const double *__restrict__ params, int64_t param_stride, const double *__restrict__ y,
+                     double *__restrict__ r_out, double *__restrict__ y_out, double dt) {
+  const int64_t m = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int nbl = (W == 3) ? 1 : P.nbl;
+  const int nbr = W - 1 - nbl;
+  const int per_warp = 32 - (W - 1);
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t first = warp * per_warp;                  // first cell this warp produces
+  if (first >= P.nx) return;
+  const int64_t i = first - nbl + lane;                   // this lane's cell
+  double prm[Model::kParams];
+#pragma unroll
+  for (int k = 0; k < Model::kParams; ++k) prm[k] = __ldg(params + (param_stride ? k * param_stride + m : k));
+  const bool warp_interior = (first - nbl >= 0) && (first - nbl + 31 < P.nx);
+  if (!warp_interior) {
+    // general path: every producing lane gathers its own stencil (ghost cells, mesh ends)
+    if (lane < nbl || lane >= 32 - nbr || i >= P.nx) return;
+    residual_member_noinline<Model, SCHEME, NV, W>(P, x_int, params, param_stride, y, r_out, y_out, dt, nullptr, i, m);
+    return;
+  }
+  const int64_t B = P.batch;
+  int64_t off[NV];
+  double uc[NV], Fc[NV], Dc[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    off[j] = (P.var_base[j] + P.var_off[j] + i * (int64_t)P.var_stride[j]) * B + m;
+    uc[j] = __ldg(y + off[j]);
+  }
+  const double xc = __ldg(x_int + i);
+  Model::F(prm, uc, Fc);
+  if constexpr (Model::kHasDiffusion) {
+    Model::D(prm, uc, Dc);
+  } else {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) Dc[j] = 0.0;
+  }
+  double sigma_c = 0.0;
+  if constexpr (SCHEME == SFXM_FV_LAX_FRIEDRICHS) sigma_c = Model::sigma(prm, uc);
+  // stencil slot s of lane l is lane l - nbl + s
+  double u[W][NV], Fv[W][NV], Dv[W][NV], xs[W];
+#pragma unroll
+  for (int s = 0; s < W; ++s) {
+    const int src = lane - nbl + s;
+    xs[s] = __shfl_sync(0xffffffffu, xc, src);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      u[s][j] = __shfl_sync(0xffffffffu, uc[j], src);
+      Fv[s][j] = __shfl_sync(0xffffffffu, Fc[j], src);
+      Dv[s][j] = Model::kHasDiffusion ? __shfl_sync(0xffffffffu, Dc[j], src) : 0.0;
+    }
+  }
+  if (lane < nbl || lane >= 32 - nbr) return;             // feeder lanes are done
+  Geom<SCHEME, W> geom(xs);
+  geom.and_inputs(u, prm);
+  double r[NV];
+  if (geom.fast) cell_combine<Model, SCHEME, NV, W, true>(prm, u, Fv, Dv, sigma_c, geom, r);
+  else cell_combine<Model, SCHEME, NV, W, false>(prm, u, Fv, Dv, sigma_c, geom, r);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    if (r_out) r_out[off[j]] = r[j];
+    if (y_out) y_out[off[j]] = uc[j] + dt * r[j];           // sol.y += delta_t * f, simulation.py:459
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // per-cell geometry table (divisors, their reciprocals, 1/dx): mesh-only data shared by all ensemble members
 // ------------------------------------------------------------------------------------------------
 template <int SCHEME, int W>
@@ -602,6 +677,14 @@ static int ensemble_block_y() {
   }
   return v;
 }
+static bool warp_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SFXM_WARP");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
 static bool pair_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -673,6 +756,11 @@ static int launch_t(const Launch &L) {
     dim3 g((unsigned)((P.batch / 2 + 31) / 32), (unsigned)gy, (unsigned)((tiles + gy - 1) / gy));
     if (g.z > 65535) return set_error("mesh too large for one launch");
     residual_pair_kernel<Model, SCHEME, NV, W><<<g, dim3(32, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.out0, L.out1, L.scalar, L.geom, strip);
+  } else if (L.op == OP_RESIDUAL && P.batch < 32 && !Model::kDecoupled && warp_enabled()) {
+    const int per_warp = 32 - (W - 1);
+    const int64_t warps = (P.nx + per_warp - 1) / per_warp;
+    dim3 g((unsigned)((warps + 7) / 8), (unsigned)P.batch);
+    residual_warp_kernel<Model, SCHEME, NV, W><<<g, dim3(256, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.out0, L.out1, L.scalar);
   } else if (L.op == OP_RESIDUAL) {
     const int strip = strip_for(b);
     dim3 g = grid_for(P.batch, P.nx, b, strip);
