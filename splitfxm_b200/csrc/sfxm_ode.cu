@@ -8,6 +8,7 @@
 #include <cstdint>
 #include "../../include/sfxm_b200.h"
 #include "sfxm_host.h"
+#include "sfxm_reduce.cuh"
 
 namespace sfxm {
 
@@ -49,50 +50,35 @@ __global__ void dense_end_kernel(const double *__restrict__ y_old, const double 
   out[q] = h * dot + __ldg(y_old + q);
 }
 
-// Per-member sum over q in [0, n) of (num / scale)^2 in fixed order, two stages (see sumsq in sfxm_solve.cu).
-//   MODE 0: num = a[q] - (a2 ? a2[q] : 0)            scale = atol + |b[q]| * rtol            (select_initial_step)
-//   MODE 1: num = (sum_s K_s E_s) * h                 scale = atol + max(|b|, |b2|) * rtol    (_estimate_error_norm)
-template <int MODE>
-__global__ void scaled_sumsq_partial_kernel(const double *__restrict__ a, const double *__restrict__ a2,
-                                            const double *__restrict__ b, const double *__restrict__ b2,
-                                            int64_t stage_stride, const __grid_constant__ Coefs E, double h,
-                                            double atol, double rtol, int64_t n, int64_t B, int64_t chunk,
-                                            double *__restrict__ partial) {
-  const int64_t m = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
-  const int64_t k = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
-  const int64_t q0 = k * chunk;
-  if (m >= B || q0 >= n) return;
-  const int64_t q1 = q0 + chunk < n ? q0 + chunk : n;
-  double acc = 0.0;
-  for (int64_t q = q0; q < q1; ++q) {
+// Terms of the deterministic row reduction (sfxm_reduce.cuh):
+//   ScaledDiffTerm: ((a - a2) / (atol + |b| rtol))^2                           (select_initial_step's d0, d1, d2)
+//   RkErrorTerm:    (((sum_s K_s E_s) * h) / (atol + max(|y|, |y_new|) rtol))^2  (_estimate_error_norm)
+struct ScaledDiffTerm {
+  const double *a, *a2, *b;
+  double atol, rtol;
+  int64_t B;
+  __device__ __forceinline__ double operator()(int64_t q, int64_t m) const {
     const int64_t e = q * B + m;
-    double num, scale;
-    if (MODE == 0) {
-      num = __ldg(a + e);
-      if (a2) num = num - __ldg(a2 + e);
-      scale = atol + fabs(__ldg(b + e)) * rtol;
-    } else {
-      double d = __ldg(a + e) * E.c[0];
-      for (int s = 1; s < E.n; ++s) d = d + __ldg(a + s * stage_stride + e) * E.c[s];
-      num = d * h;
-      scale = atol + fmax(fabs(__ldg(b + e)), fabs(__ldg(b2 + e))) * rtol;
-    }
-    const double t = num / scale;
-    acc += t * t;
+    double num = __ldg(a + e);
+    if (a2) num = num - __ldg(a2 + e);
+    const double t = num / (atol + fabs(__ldg(b + e)) * rtol);
+    return t * t;
   }
-  partial[k * B + m] = acc;
-}
-
-__global__ void sum_partials_kernel(const double *__restrict__ partial, int64_t nchunk, int64_t B,
-                                    double *__restrict__ out) {
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= B) return;
-  double acc = 0.0;
-  for (int64_t k = 0; k < nchunk; ++k) acc += partial[k * B + m];
-  out[m] = acc;
-}
-
-static const int64_t kChunk = 256;
+};
+struct RkErrorTerm {
+  const double *K, *y, *y_new;
+  int64_t stage_stride;
+  Coefs E;
+  double h, atol, rtol;
+  int64_t B;
+  __device__ __forceinline__ double operator()(int64_t q, int64_t m) const {
+    const int64_t e = q * B + m;
+    double d = __ldg(K + e) * E.c[0];
+    for (int s = 1; s < E.n; ++s) d = d + __ldg(K + s * stage_stride + e) * E.c[s];
+    const double t = (d * h) / (atol + fmax(fabs(__ldg(y + e)), fabs(__ldg(y_new + e))) * rtol);
+    return t * t;
+  }
+};
 
 }  // namespace sfxm
 
@@ -124,30 +110,14 @@ extern "C" int sfxm_rk_dense_end(const double *y_old, const double *K, int64_t s
 }
 
 extern "C" int64_t sfxm_scaled_sumsq_workspace_bytes(int64_t n, int64_t batch) {
-  return ((n + kChunk - 1) / kChunk) * batch * (int64_t)sizeof(double);
-}
-
-static int scaled_launch(int mode, const double *a, const double *a2, const double *b, const double *b2,
-                         int64_t stage_stride, const Coefs &E, double h, double atol, double rtol, int64_t n,
-                         int64_t batch, double *out, double *work, cudaStream_t st) {
-  const int64_t nchunk = (n + kChunk - 1) / kChunk;
-  if (nchunk > 0) {
-    dim3 blk = batch >= 32 ? dim3(32, 8) : dim3(1, 256);
-    dim3 g((unsigned)((nchunk + blk.y - 1) / blk.y), (unsigned)((batch + blk.x - 1) / blk.x));
-    if (mode == 0)
-      scaled_sumsq_partial_kernel<0><<<g, blk, 0, st>>>(a, a2, b, b2, stage_stride, E, h, atol, rtol, n, batch, kChunk, work);
-    else
-      scaled_sumsq_partial_kernel<1><<<g, blk, 0, st>>>(a, a2, b, b2, stage_stride, E, h, atol, rtol, n, batch, kChunk, work);
-  }
-  sum_partials_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(work, nchunk, batch, out);
-  return check_launch("sfxm scaled sumsq");
+  return (reduce_tiles(n, batch) + 1) * batch * (int64_t)sizeof(double);
 }
 
 extern "C" int sfxm_scaled_diff_sumsq(const double *a, const double *a2, const double *b, double atol, double rtol,
                                       int64_t n, int64_t batch, double *out, double *work, void *stream) {
   if (!a || !b || !out || !work) return set_error("sfxm_scaled_diff_sumsq: bad argument");
-  Coefs E{};
-  return scaled_launch(0, a, a2, b, nullptr, 0, E, 0.0, atol, rtol, n, batch, out, work, (cudaStream_t)stream);
+  reduce_rows(ScaledDiffTerm{a, a2, b, atol, rtol, batch}, 0, n, batch, out, work, (cudaStream_t)stream);
+  return check_launch("sfxm_scaled_diff_sumsq");
 }
 
 extern "C" int sfxm_rk_error_sumsq(const double *K, int64_t stage_stride, const double *E_host, int32_t nstage,
@@ -158,5 +128,6 @@ extern "C" int sfxm_rk_error_sumsq(const double *K, int64_t stage_stride, const 
   Coefs E;
   E.n = nstage;
   for (int s = 0; s < SFXM_RK_MAX_STAGES; ++s) E.c[s] = s < nstage ? E_host[s] : 0.0;
-  return scaled_launch(1, K, nullptr, y, y_new, stage_stride, E, h, atol, rtol, n, batch, out, work, (cudaStream_t)stream);
+  reduce_rows(RkErrorTerm{K, y, y_new, stage_stride, E, h, atol, rtol, batch}, 0, n, batch, out, work, (cudaStream_t)stream);
+  return check_launch("sfxm_rk_error_sumsq");
 }

@@ -1,0 +1,73 @@
+// sfxm_reduce.cuh - deterministic per-member sums over the rows of a member-fastest array.
+//
+// out[m] = sum over rows q in [lo, hi) of term(q, m), where term() is a functor.  Two stages:
+//   1. a CTA owns a tile of TM members x ROWS_PER_CTA rows; thread (mx, ry) adds its rows ry, ry + TR, ... in
+//      increasing order, the TR partial sums of a member are then added in increasing ry by one thread
+//      -> partial[tile][m];
+//   2. the tile partials of a member are added in increasing tile order.
+// The summation order depends only on (lo, hi, batch), never on scheduling: results are bit-reproducible (the Newton
+// criterion and the RK45 step controller branch on these numbers).  Loads are coalesced for every batch size:
+// TM = 32 (members contiguous) when batch >= 32, TM = 1 (rows contiguous) otherwise.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace sfxm {
+
+static constexpr int kReduceThreads = 256;
+static constexpr int kReduceRowsPerThread = 8;
+
+__host__ __device__ inline int64_t reduce_rows_per_cta(int64_t batch) {
+  return (int64_t)(batch >= 32 ? kReduceThreads / 32 : kReduceThreads) * kReduceRowsPerThread;
+}
+inline int64_t reduce_tiles(int64_t n, int64_t batch) {
+  const int64_t r = reduce_rows_per_cta(batch);
+  return (n + r - 1) / r;
+}
+
+template <class Term>
+__global__ void __launch_bounds__(kReduceThreads)
+reduce_partial_kernel(Term term, int64_t lo, int64_t hi, int64_t B, double *__restrict__ partial) {
+  __shared__ double sh[kReduceThreads];
+  const int TM = blockDim.x, TR = blockDim.y;
+  const int64_t m = (int64_t)blockIdx.y * TM + threadIdx.x;
+  const int64_t q0 = lo + (int64_t)blockIdx.x * TR * kReduceRowsPerThread + threadIdx.y;
+  double acc = 0.0;
+  if (m < B) {
+#pragma unroll
+    for (int k = 0; k < kReduceRowsPerThread; ++k) {
+      const int64_t q = q0 + (int64_t)k * TR;
+      if (q < hi) acc += term(q, m);
+    }
+  }
+  sh[threadIdx.y * TM + threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && m < B) {
+    double tot = sh[threadIdx.x];
+    for (int r = 1; r < TR; ++r) tot += sh[r * TM + threadIdx.x];
+    partial[(int64_t)blockIdx.x * B + m] = tot;
+  }
+}
+
+static __global__ void reduce_final_kernel(const double *__restrict__ partial, int64_t ntiles, int64_t B,
+                                    double *__restrict__ out) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= B) return;
+  double acc = 0.0;
+  for (int64_t k = 0; k < ntiles; ++k) acc += partial[k * B + m];
+  out[m] = acc;
+}
+
+// work must hold reduce_tiles(hi - lo, batch) * batch doubles
+template <class Term>
+static void reduce_rows(Term term, int64_t lo, int64_t hi, int64_t batch, double *out, double *work, cudaStream_t st) {
+  const int64_t ntiles = reduce_tiles(hi - lo, batch);
+  if (ntiles > 0) {
+    dim3 b = batch >= 32 ? dim3(32, kReduceThreads / 32) : dim3(1, kReduceThreads);
+    dim3 g((unsigned)ntiles, (unsigned)((batch + b.x - 1) / b.x));
+    reduce_partial_kernel<Term><<<g, b, 0, st>>>(term, lo, hi, batch, work);
+  }
+  reduce_final_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(work, ntiles, batch, out);
+}
+
+}  // namespace sfxm

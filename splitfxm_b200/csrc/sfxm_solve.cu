@@ -11,6 +11,7 @@
 #include <cstdint>
 #include "../../include/sfxm_b200.h"
 #include "sfxm_host.h"
+#include "sfxm_reduce.cuh"
 
 namespace sfxm {
 
@@ -246,29 +247,14 @@ block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const doubl
   if (status && !ok) status[m] = 1;
 }
 
-// out[m] = sum_{q in [lo,hi)} v[q*B+m]^2, accumulated in increasing q (deterministic).  Stage 1 reduces
-// chunks of q, stage 2 adds the chunk partials in order.
-__global__ void sumsq_partial_kernel(const double *__restrict__ v, int64_t lo, int64_t hi, int64_t B, int64_t chunk,
-                                     double *__restrict__ partial) {
-  const int64_t m = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
-  const int64_t k = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;   // chunk index
-  const int64_t q0 = lo + k * chunk;
-  if (m >= B || q0 >= hi) return;
-  const int64_t q1 = q0 + chunk < hi ? q0 + chunk : hi;
-  double acc = 0.0;
-  for (int64_t q = q0; q < q1; ++q) {
+struct SquareTerm {   // the norms of the Newton convergence criterion
+  const double *v;
+  int64_t B;
+  __device__ __forceinline__ double operator()(int64_t q, int64_t m) const {
     const double a = __ldg(v + q * B + m);
-    acc += a * a;
+    return a * a;
   }
-  partial[k * B + m] = acc;
-}
-__global__ void sumsq_final_kernel(const double *__restrict__ partial, int64_t nchunk, int64_t B, double *__restrict__ out) {
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= B) return;
-  double acc = 0.0;
-  for (int64_t k = 0; k < nchunk; ++k) acc += partial[k * B + m];
-  out[m] = acc;
-}
+};
 
 __global__ void axpy_masked_kernel(double *__restrict__ y, const double *__restrict__ s, const double *__restrict__ alpha,
                                    const int32_t *__restrict__ active, int64_t lo, int64_t hi, int64_t B) {
@@ -352,21 +338,14 @@ extern "C" int sfxm_block_tridiag_solve(const sfxm_problem_t *prob, const double
 }
 
 extern "C" int64_t sfxm_sumsq_workspace_bytes(int64_t n, int64_t batch) {
-  return ((n + 1023) / 1024) * batch * (int64_t)sizeof(double);
+  return (reduce_tiles(n, batch) + 1) * batch * (int64_t)sizeof(double);
 }
 
 extern "C" int sfxm_sumsq(const double *v, int64_t lo, int64_t hi, int64_t batch, double *out, double *work,
                           void *stream) {
   if (!v || !out || !work || hi < lo) return set_error("sfxm_sumsq: bad argument");
-  cudaStream_t st = (cudaStream_t)stream;
-  const int64_t chunk = 1024;
-  const int64_t nchunk = (hi - lo + chunk - 1) / chunk;
-  if (nchunk > 0) {
-    dim3 b = batch >= 32 ? dim3(32, 8) : dim3(1, 256);
-    dim3 g((unsigned)((nchunk + b.y - 1) / b.y), (unsigned)((batch + b.x - 1) / b.x));
-    sumsq_partial_kernel<<<g, b, 0, st>>>(v, lo, hi, batch, chunk, work);
-  }
-  sumsq_final_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(work, nchunk, batch, out);
+  if (batch > 65535LL * 32) return set_error("sfxm_sumsq: batch too large");
+  reduce_rows(SquareTerm{v, batch}, lo, hi, batch, out, work, (cudaStream_t)stream);
   return check_launch("sfxm_sumsq");
 }
 
