@@ -296,6 +296,7 @@ def extras(torch, sf, ens, Y, dev, peak):
     """Secondary numbers (not the headline): Newton iteration throughput on the ensemble, residual and Jacobian
     on one large mesh."""
     from splitfxm_b200.models.advection_diffusion import AdvectionDiffusion
+    from splitfxm_b200 import _lib as _lib_mod
     out = {}
     eng = ens.eng
 
@@ -322,6 +323,8 @@ def extras(torch, sf, ens, Y, dev, peak):
     out["ensemble_block_tridiag_solve"] = {"ms": ms_solve, "GBps": solve_bytes / ms_solve / 1e6,
                                            "frac": solve_bytes / ms_solve / 1e6 / peak,
                                            "solves_per_s": B / (ms_solve * 1e-3)}
+    ens.steady_state(Y, split=SPLIT, split_locs=LOCS)       # warm the allocator (first call allocates ~2 GB)
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     Yf, its = ens.steady_state(Y, split=SPLIT, split_locs=LOCS)
     torch.cuda.synchronize()
@@ -357,6 +360,53 @@ def extras(torch, sf, ens, Y, dev, peak):
                       "residual_GBps": nx * 56 / ms_r / 1e6, "newton_iteration_ms": ms_n,
                       "newton_iterations_per_s": 1e3 / ms_n, "steady_state_api_s": t_ss, "steady_state_iterations": iters})
     out["single_mesh_sweep"] = sweep
+
+    # AMR pass and RK45 evolve on one large mesh (conservative Sod)
+    from splitfxm_b200.models.euler1d import Euler1DConservative
+    from splitfxm_b200.refine import Refiner
+    import contextlib
+    import io
+    comps = ["rho", "rhou", "E"]
+    nbc = {c: {"left": {"neumann": 0.0}, "right": {"neumann": 0.0}} for c in comps}
+    for nx in (100000, 1000000):
+        d = sf.Domain.from_size(nx, 1, 1, comps)
+        xs = d.interior_x()
+        d.interior_U()[:, 0] = np.where(xs < 0.5, 1.0, 0.125) + 0.01 * np.tanh(200 * (xs - 0.3))
+        d.interior_U()[:, 2] = np.where(xs < 0.5, 2.5, 0.25)
+        r = Refiner()
+        r.set_criteria(2.0, 0.05, 0.05, -0.001)
+        r.set_max_points(4 * nx)
+        xd = torch.from_numpy(np.ascontiguousarray(d.interior_x())).to(dev)
+        Ud = torch.from_numpy(np.ascontiguousarray(d.interior_U())).to(dev)
+        lib = _lib_mod.load()
+        work = torch.empty(lib.sfxm_refine_workspace_bytes(nx), dtype=torch.uint8, device=dev)
+        counts = torch.zeros(3, dtype=torch.int64, device=dev)
+        xo = torch.empty(2 * nx, dtype=torch.float64, device=dev)
+        Uo = torch.empty((2 * nx, 3), dtype=torch.float64, device=dev)
+
+        def amr_pass():
+            _lib_mod.check(lib.sfxm_refine_mark(xd.data_ptr(), Ud.data_ptr(), nx, 3, 2.0, 0.05, 0.05, -0.001, 0.01, 1e-10,
+                                                work.data_ptr(), counts.data_ptr(), _lib_mod.stream_ptr()))
+            _lib_mod.check(lib.sfxm_refine_apply(xd.data_ptr(), Ud.data_ptr(), nx, 3, work.data_ptr(), xo.data_ptr(),
+                                                 Uo.data_ptr(), _lib_mod.stream_ptr()))
+        ms_amr = timed(amr_pass, 5)
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            r.refine(d)
+        t_api = time.perf_counter() - t0
+        out.setdefault("amr", []).append({"nx": nx, "device_pass_ms": ms_amr, "GBps": nx * 96 / ms_amr / 1e6,
+                                          "cells_after": int(counts[0]), "refine_api_s": t_api})
+    d = sf.Domain.from_size(100000, 1, 1, comps)
+    xs = d.interior_x()
+    d.interior_U()[:, 0] = np.where(xs < 0.5, 1.0, 0.125)
+    d.interior_U()[:, 2] = np.where(xs < 0.5, 2.5, 0.25)
+    sim = sf.Simulation(d, Euler1DConservative(1.4, "FVM"), {}, nbc, sf.FVSchemes.LAX_FRIEDRICHS)
+    before = _lib_mod.LAUNCHES[0]
+    t0 = time.perf_counter()
+    sim.evolve(2.0e-4, split=True, split_locs=[1])          # ~20 CFL-limited RK45 steps at dx = 1e-5
+    t_ev = time.perf_counter() - t0
+    out["rk45_evolve_sod_nx1e5"] = {"t_diff": 2.0e-4, "seconds": t_ev, "launches": _lib_mod.LAUNCHES[0] - before,
+                                    "finite": bool(np.isfinite(d.values()).all())}
     return out
 
 

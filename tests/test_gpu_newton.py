@@ -22,6 +22,9 @@ def _dense_from_banded(eng, Jh, split, locs):
     ("ad_fdm_central_nonuniform_mixed", True, [2]),   # 2x2 + 1x1 segments on an AMR mesh
     ("sod_cons_nx60_unsplit_t0p02", False, None),     # dense 3x3 blocks (Euler)
     ("sod_cons_nx100_t0p05", True, [1]),
+    ("ad_fvm_lf_nonuniform", True, [1, 2]),           # README BCs: u fully cyclic, v plain, w right-periodic only
+    ("ad_fvm_lf_nonuniform", True, [1]),              # (v, w) 2x2 blocks with a lower-left corner block only
+    ("ad_fdm_central_nx250_split1", True, [1]),
 ])
 @pytest.mark.parametrize("method", ["thomas", "pcr"])
 def test_block_tridiag_solve(name, split, locs, method):
