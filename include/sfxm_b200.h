@@ -73,6 +73,11 @@ typedef struct sfxm_problem {
   /* device buffers [(g * nv + j) * batch + m] with the neighbouring slab's boundary cells, ghost g = 0 nearest
    * (used by variables whose BC type is SFXM_BC_HALO; NULL otherwise) */
   const double *halo_left, *halo_right;
+  /* fused halo exchange: when non-NULL, the explicit-Euler update (y_out of sfxm_residual) also stores this slab's
+   * first nbr / last nbl updated cells straight into the LEFT neighbour's halo_right / RIGHT neighbour's halo_left
+   * buffer - peer-mapped device memory of another GPU, written over NVLink by the same kernel (no pack, no NCCL
+   * call); sfxm_halo_signal / sfxm_halo_wait order the steps. */
+  double *peer_left_dst, *peer_right_dst;
 } sfxm_problem_t;
 
 int sfxm_abi_version(void);
@@ -172,6 +177,14 @@ int sfxm_refine_apply(const double *x, const double *U, int64_t n, int32_t nv, c
  * SFXM_MODEL_USER0 + slot.  The reference's equivalent is a Model whose _equation holds Python callables
  * F, D, S, dFdU (model.py:8, fv_transport.py:18, fd_transport.py:18). */
 int sfxm_register_user_model(int32_t slot, void *launch_fn);
+
+/* Step ordering for the fused halo exchange.  signal: after everything queued so far on `stream`, publish `value`
+ * (system scope) in the two neighbours' flag words (either may be NULL).  wait: a one-thread kernel that spins until
+ * both of this rank's flag words (either may be NULL) are >= value; it gives up after ~2 s and sets *timeout_flag.
+ * Flags are step counters in peer-mapped memory. */
+int sfxm_halo_signal(int64_t *left_peer_flag, int64_t *right_peer_flag, int64_t value, void *stream);
+int sfxm_halo_wait(const int64_t *from_left_flag, const int64_t *from_right_flag, int64_t value, int32_t *timeout_flag,
+                   void *stream);
 
 /* Device self-test: counts (into *mismatch_dev, a device uint64 the caller zeroes) operands for which the
  * five-FMA division by a known reciprocal used in the stencil kernels differs from the IEEE quotient.

@@ -37,6 +37,7 @@ class Problem(ctypes.Structure):
         ("var_base", c_i64 * MAX_NV),
         ("var_stride", c_i32 * MAX_NV), ("var_off", c_i32 * MAX_NV), ("var_seg", c_i32 * MAX_NV),
         ("halo_left", c_vp), ("halo_right", c_vp),
+        ("peer_left_dst", c_vp), ("peer_right_dst", c_vp),
     ]
 
 
@@ -67,6 +68,8 @@ SIGNATURES = {
     "sfxm_refine_flags": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_refine_apply": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_register_user_model": (ctypes.c_int, [c_i32, c_vp]),
+    "sfxm_halo_signal": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "sfxm_halo_wait": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "sfxm_selftest_div": (ctypes.c_int, [c_i64, ctypes.c_uint64, c_i32, c_vp, c_vp]),
 }
 

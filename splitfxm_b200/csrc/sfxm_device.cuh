@@ -102,6 +102,15 @@ __device__ inline double ghost_u_right(const sfxm_problem_t &P, const View &v, i
   return val;
 }
 
+// fused halo exchange: the updated value of a slab-boundary cell also goes into the neighbour's ghost buffer
+// (peer-mapped memory of another GPU; plain global stores that travel over NVLink)
+__device__ __forceinline__ void push_halo(const sfxm_problem_t &P, int64_t i, int j, int64_t m, double val) {
+  if (P.peer_left_dst != nullptr && i < P.nbr)            // my first cells are the left neighbour's right ghosts
+    P.peer_left_dst[(int64_t)(i * P.nv + j) * P.batch + m] = val;
+  if (P.peer_right_dst != nullptr && i >= P.nx - P.nbl)   // my last cells are the right neighbour's left ghosts
+    P.peer_right_dst[(int64_t)((P.nx - 1 - i) * P.nv + j) * P.batch + m] = val;
+}
+
 // stencil slot s of cell i -> position and values (system.py:58-61: cells[i - nbl .. i + nbr])
 // (j0: first variable of the group this thread handles - 0 for the coupled kernels, the thread's own variable for
 // the one-variable-per-thread kernels of decoupled models)

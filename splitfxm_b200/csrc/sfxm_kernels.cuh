@@ -66,7 +66,7 @@ residual_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restri
     if (r_out) r_out[off[j]] = r[j];
     // the cell's own value is slot nbl (selected, not indexed: a dynamic index would push u[][] to local memory)
     const double uc = (W == 3 || P.nbl == 1) ? u[1][j] : u[W == 3 ? 1 : 2][j];
-    if (y_out) y_out[off[j]] = uc + dt * r[j];              // sol.y += delta_t * f, simulation.py:459
+    if (y_out) { const double yn = uc + dt * r[j]; y_out[off[j]] = yn; push_halo(P, i, j, m, yn); }              // sol.y += delta_t * f, simulation.py:459
   }
   }
 }
@@ -94,7 +94,7 @@ __device__ __noinline__ void residual_member_noinline(const sfxm_problem_t &P, c
   for (int j = 0; j < NV; ++j) {
     if (r_out) r_out[off[j]] = r[j];
     const double uc = (W == 3 || P.nbl == 1) ? u[1][j] : u[W == 3 ? 1 : 2][j];
-    if (y_out) y_out[off[j]] = uc + dt * r[j];
+    if (y_out) { const double yn = uc + dt * r[j]; y_out[off[j]] = yn; push_halo(P, i, j, m, yn); }
   }
 }
 
@@ -159,7 +159,10 @@ residual_pair_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
       if (y_out) {
         const double c0 = (W == 3 || P.nbl == 1) ? u[0][1][j] : u[0][W == 3 ? 1 : 2][j];
         const double c1 = (W == 3 || P.nbl == 1) ? u[1][1][j] : u[1][W == 3 ? 1 : 2][j];
-        *reinterpret_cast<double2 *>(y_out + off[j]) = make_double2(c0 + dt * r[0][j], c1 + dt * r[1][j]);   // simulation.py:459
+        const double2 yn = make_double2(c0 + dt * r[0][j], c1 + dt * r[1][j]);                                // simulation.py:459
+        *reinterpret_cast<double2 *>(y_out + off[j]) = yn;
+        push_halo(P, i, j, m0, yn.x);
+        push_halo(P, i, j, m0 + 1, yn.y);
       }
     }
   }
@@ -236,7 +239,7 @@ residual_warp_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     if (r_out) r_out[off[j]] = r[j];
-    if (y_out) y_out[off[j]] = uc[j] + dt * r[j];           // sol.y += delta_t * f, simulation.py:459
+    if (y_out) { const double yn = uc[j] + dt * r[j]; y_out[off[j]] = yn; push_halo(P, i, j, m, yn); }           // sol.y += delta_t * f, simulation.py:459
   }
 }
 
@@ -567,7 +570,7 @@ residual_scalar_kernel(const __grid_constant__ sfxm_problem_t P, const double *_
   else cell_residual<M1, SCHEME, 1, W, false>(prm, u, geom, r);
   if (r_out) r_out[off[0]] = r[0];
   const double uc = (W == 3 || P.nbl == 1) ? u[1][0] : u[W == 3 ? 1 : 2][0];
-  if (y_out) y_out[off[0]] = uc + dt * r[0];                // sol.y += delta_t * f, simulation.py:459
+  if (y_out) { const double yn = uc + dt * r[0]; y_out[off[0]] = yn; push_halo(P, i, j, m, yn); }                // sol.y += delta_t * f, simulation.py:459
 }
 
 template <class M1, int SCHEME, int W, bool FAST>

@@ -167,6 +167,8 @@ class SlabSimulation:
                         P.gx_right = _lib.GX_MIRROR
             P.halo_left = self.halo_left.data_ptr()
             P.halo_right = self.halo_right.data_ptr()
+            P.peer_left_dst = None
+            P.peer_right_dst = None
 
         self.eng.set_bcs(fill)
         self.transport = transport if transport is not None else HaloTransport(rank, world, self.left, self.right)
@@ -218,3 +220,91 @@ class SlabSimulation:
             t_current += delta_t
             nsteps += 1
         return y, nsteps
+
+    # -- fused halo exchange over peer-mapped memory (NVLink) ---------------------------------------------
+    def enable_peer_halos(self, group=None):
+        """Put the halo buffers in symmetric memory and map the neighbours' buffers (one process per GPU, NCCL group
+        initialised).  After this, evolve_euler_fused() needs no communication call per step: the update kernel
+        stores the slab's boundary cells directly into the neighbours' ghost buffers."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        if self.world < 2:
+            raise SFXM("peer halos need at least 2 ranks")
+        B, nv = self.eng.batch, self.nv
+        self._n_l, self._n_r = self.nbl * nv * B, self.nbr * nv * B
+        total = 2 * self._n_l + 2 * self._n_r + 8
+        group = group if group is not None else dist.group.WORLD
+        buf = symm_mem.empty((total,), dtype=torch.float64, device=self.eng.device)
+        buf.zero_()
+        hdl = symm_mem.rendezvous(buf, group=group.group_name)
+        self._peer_buf, self._peer_hdl = buf, hdl
+        self._peer_base = list(hdl.buffer_ptrs)
+        self._timeout = torch.zeros(1, dtype=torch.int32, device=self.eng.device)
+        torch.cuda.synchronize()
+        hdl.barrier()
+
+    def _hl(self, rank, par):      # address of rank's halo_left[par]
+        return self._peer_base[rank] + 8 * (par * self._n_l)
+
+    def _hr(self, rank, par):      # address of rank's halo_right[par]
+        return self._peer_base[rank] + 8 * (2 * self._n_l + par * self._n_r)
+
+    def _flag(self, rank, which):  # which: 0 = "from left", 1 = "from right"
+        return self._peer_base[rank] + 8 * (2 * self._n_l + 2 * self._n_r + which)
+
+    def evolve_euler_fused(self, y, t_diff, max_step, split=False, split_locs=None):
+        """The explicit Euler loop of evolve_euler with the halo exchange fused into the update kernel.
+
+        Step k reads ghost buffers of parity k % 2 and stores its updated boundary cells into the neighbours' buffers
+        of parity (k + 1) % 2 (peer memory); a one-thread kernel then publishes the step counter in the neighbours'
+        flag words, and the next step starts with a one-thread kernel waiting for both neighbours' counters - so a
+        neighbour never overwrites a buffer that is still being read.  The first ghost values come from one ordinary
+        exchange."""
+        import torch.distributed as dist
+        lib, eng = self.eng.lib, self.eng
+        P, _ = eng.problem(split, split_locs)
+        n_l, n_r = self._n_l, self._n_r
+        B, nv = eng.batch, self.nv
+        hl0 = self._peer_buf[0:n_l].view(self.nbl, nv, B)
+        hr0 = self._peer_buf[2 * n_l:2 * n_l + n_r].view(self.nbr, nv, B)
+        # flags back to zero, then the parity-0 ghosts by the ordinary path
+        self._peer_buf[2 * n_l + 2 * n_r:].zero_()
+        self._timeout.zero_()
+        torch.cuda.synchronize()
+        self._peer_hdl.barrier()
+        sl, sr = self.pack(y, split, split_locs)
+        self.transport.exchange(sl, sr, hl0, hr0)
+        torch.cuda.synchronize()
+        self._peer_hdl.barrier()
+        me, L, R = self.rank, self.left, self.right
+        st = _lib.stream_ptr()
+        t_current, k = 0.0, 0
+        other = torch.empty_like(y)
+        keep = (P.halo_left, P.halo_right)
+        try:
+            while t_current < t_diff:
+                delta_t = min(t_diff - t_current, max_step)
+                par, nxt = k % 2, (k + 1) % 2
+                P.halo_left, P.halo_right = self._hl(me, par), self._hr(me, par)
+                P.peer_left_dst = self._hr(L, nxt) if L is not None else None
+                P.peer_right_dst = self._hl(R, nxt) if R is not None else None
+                if k > 0:
+                    _lib.check(lib.sfxm_halo_wait(self._flag(me, 0) if L is not None else None,
+                                                  self._flag(me, 1) if R is not None else None, k,
+                                                  self._timeout.data_ptr(), st))
+                eng.euler_step(y, other, delta_t, split, split_locs)
+                # my left neighbour sees me on its right: its "from right" flag; and vice versa
+                _lib.check(lib.sfxm_halo_signal(self._flag(L, 1) if L is not None else None,
+                                                self._flag(R, 0) if R is not None else None, k + 1, st))
+                _lib.count(2)
+                y, other = other, y
+                t_current += delta_t
+                k += 1
+            torch.cuda.synchronize()
+        finally:
+            P.halo_left, P.halo_right = keep
+            P.peer_left_dst = P.peer_right_dst = None
+        if int(self._timeout[0]) != 0:
+            raise SFXM("fused halo exchange: a neighbour's step counter did not arrive (timeout)")
+        self._peer_hdl.barrier()
+        return y, k
