@@ -186,6 +186,13 @@ int sfxm_halo_signal(int64_t *left_peer_flag, int64_t *right_peer_flag, int64_t 
 int sfxm_halo_wait(const int64_t *from_left_flag, const int64_t *from_right_flag, int64_t value, int32_t *timeout_flag,
                    void *stream);
 
+/* Same, with the step counter kept in device memory (`counter`, owned by this rank): signal increments it and
+ * publishes the new value, wait blocks until both neighbours' flags reach it.  No per-step kernel argument, so a
+ * (wait, update, signal) sequence is captured once in a CUDA graph and replayed. */
+int sfxm_halo_signal_counter(int64_t *counter, int64_t *left_peer_flag, int64_t *right_peer_flag, void *stream);
+int sfxm_halo_wait_counter(const int64_t *counter, const int64_t *from_left_flag, const int64_t *from_right_flag,
+                           int32_t *timeout_flag, void *stream);
+
 /* Device self-test: counts (into *mismatch_dev, a device uint64 the caller zeroes) operands for which the
  * five-FMA division by a known reciprocal used in the stencil kernels differs from the IEEE quotient.
  * mode 0 = random operands, mode 1 = adversarial (divisor mantissa all ones/zeros, half-way numerators). */

@@ -70,6 +70,8 @@ SIGNATURES = {
     "sfxm_register_user_model": (ctypes.c_int, [c_i32, c_vp]),
     "sfxm_halo_signal": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp]),
     "sfxm_halo_wait": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "sfxm_halo_signal_counter": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_halo_wait_counter": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_selftest_div": (ctypes.c_int, [c_i64, ctypes.c_uint64, c_i32, c_vp, c_vp]),
 }
 

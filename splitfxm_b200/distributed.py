@@ -252,22 +252,22 @@ class SlabSimulation:
     def _flag(self, rank, which):  # which: 0 = "from left", 1 = "from right"
         return self._peer_base[rank] + 8 * (2 * self._n_l + 2 * self._n_r + which)
 
-    def evolve_euler_fused(self, y, t_diff, max_step, split=False, split_locs=None):
+    def evolve_euler_fused(self, y, t_diff, max_step, split=False, split_locs=None, use_graph=True):
         """The explicit Euler loop of evolve_euler with the halo exchange fused into the update kernel.
 
         Step k reads ghost buffers of parity k % 2 and stores its updated boundary cells into the neighbours' buffers
         of parity (k + 1) % 2 (peer memory); a one-thread kernel then publishes the step counter in the neighbours'
         flag words, and the next step starts with a one-thread kernel waiting for both neighbours' counters - so a
         neighbour never overwrites a buffer that is still being read.  The first ghost values come from one ordinary
-        exchange."""
-        import torch.distributed as dist
+        exchange.  Pairs of full-size steps are captured once in a CUDA graph (the step number lives in device memory)
+        and replayed, so the host issues one graph launch per two steps."""
         lib, eng = self.eng.lib, self.eng
         P, _ = eng.problem(split, split_locs)
         n_l, n_r = self._n_l, self._n_r
         B, nv = eng.batch, self.nv
         hl0 = self._peer_buf[0:n_l].view(self.nbl, nv, B)
         hr0 = self._peer_buf[2 * n_l:2 * n_l + n_r].view(self.nbr, nv, B)
-        # flags back to zero, then the parity-0 ghosts by the ordinary path
+        # flags and the step counter back to zero, then the parity-0 ghosts by the ordinary path
         self._peer_buf[2 * n_l + 2 * n_r:].zero_()
         self._timeout.zero_()
         torch.cuda.synchronize()
@@ -277,28 +277,50 @@ class SlabSimulation:
         torch.cuda.synchronize()
         self._peer_hdl.barrier()
         me, L, R = self.rank, self.left, self.right
-        st = _lib.stream_ptr()
-        t_current, k = 0.0, 0
-        other = torch.empty_like(y)
+        counter = self._peer_base[me] + 8 * (2 * n_l + 2 * n_r + 2)
+        from_l = self._flag(me, 0) if L is not None else None
+        from_r = self._flag(me, 1) if R is not None else None
+        to_l = self._flag(L, 1) if L is not None else None      # my left neighbour sees me on its right
+        to_r = self._flag(R, 0) if R is not None else None
+        # the reference's step sequence (float-accumulated t, simulation.py:455-463)
+        dts, t_current = [], 0.0
+        while t_current < t_diff:
+            dts.append(min(t_diff - t_current, max_step))
+            t_current += dts[-1]
+        bufs = [y, torch.empty_like(y)]
         keep = (P.halo_left, P.halo_right)
+
+        def one_step(k, dt):
+            st = _lib.stream_ptr()
+            par, nxt = k % 2, (k + 1) % 2
+            P.halo_left, P.halo_right = self._hl(me, par), self._hr(me, par)
+            P.peer_left_dst = self._hr(L, nxt) if L is not None else None
+            P.peer_right_dst = self._hl(R, nxt) if R is not None else None
+            _lib.check(lib.sfxm_halo_wait_counter(counter, from_l, from_r, self._timeout.data_ptr(), st))
+            eng.euler_step(bufs[par], bufs[nxt], dt, split, split_locs)
+            _lib.check(lib.sfxm_halo_signal_counter(counter, to_l, to_r, st))
+            _lib.count(2)
+
         try:
-            while t_current < t_diff:
-                delta_t = min(t_diff - t_current, max_step)
-                par, nxt = k % 2, (k + 1) % 2
-                P.halo_left, P.halo_right = self._hl(me, par), self._hr(me, par)
-                P.peer_left_dst = self._hr(L, nxt) if L is not None else None
-                P.peer_right_dst = self._hl(R, nxt) if R is not None else None
-                if k > 0:
-                    _lib.check(lib.sfxm_halo_wait(self._flag(me, 0) if L is not None else None,
-                                                  self._flag(me, 1) if R is not None else None, k,
-                                                  self._timeout.data_ptr(), st))
-                eng.euler_step(y, other, delta_t, split, split_locs)
-                # my left neighbour sees me on its right: its "from right" flag; and vice versa
-                _lib.check(lib.sfxm_halo_signal(self._flag(L, 1) if L is not None else None,
-                                                self._flag(R, 0) if R is not None else None, k + 1, st))
-                _lib.count(2)
-                y, other = other, y
-                t_current += delta_t
+            k = 0
+            n_full = 0
+            while n_full < len(dts) and dts[n_full] == max_step:
+                n_full += 1
+            pairs = n_full // 2 if use_graph else 0
+            if pairs >= 2:
+                side = torch.cuda.Stream(device=eng.device)
+                side.wait_stream(torch.cuda.current_stream())
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.stream(side):
+                    with torch.cuda.graph(graph, stream=side):
+                        one_step(0, max_step)
+                        one_step(1, max_step)
+                    for _ in range(pairs):
+                        graph.replay()
+                torch.cuda.current_stream().wait_stream(side)
+                k = 2 * pairs
+            while k < len(dts):
+                one_step(k, dts[k])
                 k += 1
             torch.cuda.synchronize()
         finally:
@@ -307,4 +329,4 @@ class SlabSimulation:
         if int(self._timeout[0]) != 0:
             raise SFXM("fused halo exchange: a neighbour's step counter did not arrive (timeout)")
         self._peer_hdl.barrier()
-        return y, k
+        return bufs[len(dts) % 2], len(dts)
