@@ -1,2 +1,6 @@
+"""The package's one exception type.  Every error of the reference is ``splitfxm.error.SFXM``; callers catch it by
+that name, so it keeps it."""
+
+
 class SFXM(Exception):
-    """Error type of the package (same name as the reference's splitfxm/error.py:1)."""
+    """Raised for invalid input (sizes, boundary specifications, schemes) and for every CUDA-side failure."""

@@ -1,0 +1,107 @@
+"""Acceptance tests in the style of the reference's own suite, run against splitfxm_b200 through the public API:
+the properties tests/test_verification.py:20-109, tests/test_simulation.py:65-139, 203-265 and
+benchmark/test_jac_benchmark.py:14-111 pin for the reference must hold for the drop-in."""
+import copy
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+README_BCS = {"u": {"left": "periodic", "right": "periodic"},
+              "v": {"left": {"dirichlet": 3}, "right": {"dirichlet": 4}},
+              "w": {"left": {"dirichlet": 2}, "right": "periodic"}}
+
+
+def forward_difference_jacobian(f, x0, step=1e-8):
+    """What numdifftools.Jacobian(f, method='forward', step=1e-8) computes in the reference's tests."""
+    x0 = np.asarray(x0, dtype=np.float64)
+    f0 = f(x0)
+    J = np.zeros((f0.size, x0.size))
+    for k in range(x0.size):
+        xp = x0.copy()
+        xp[k] += step
+        J[:, k] = (f(xp) - f0) / step
+    return J
+
+
+@pytest.mark.parametrize("c,xmin,xmax", [(0.1, 0.0, 1.0), (-0.1, 0.2, 1.2)])
+@pytest.mark.parametrize("scheme_name", ["LAX_FRIEDRICHS", "UPWIND"])
+def test_advecting_a_tophat_once_around_the_domain(c, xmin, xmax, scheme_name):
+    """One period of pure advection with explicit Euler returns (nearly) the initial profile: L1 area of the
+    difference below 2e-2 (tests/test_verification.py:20-109)."""
+    import splitfxm_b200 as sf
+    from splitfxm_b200.initialize import set_initial_condition
+    from splitfxm_b200.models.advection_diffusion import AdvectionDiffusion
+    scheme = sf.FVSchemes[scheme_name]
+    nb = sf.stencil_sizes[scheme] // 2
+    d = sf.Domain.from_size(100, nb, nb, ["u"], xmin=xmin, xmax=xmax)
+    d0 = copy.deepcopy(d)
+    s = sf.Simulation(d, AdvectionDiffusion(c=c, nu=0.0, method="FVM"), {"u": "tophat"},
+                      {"u": {"left": "periodic", "right": "periodic"}}, scheme, {"limiter": None})
+    s.evolve(10.0, False, None, method="Euler", max_step=0.1)
+    set_initial_condition(d0, "u", "tophat")
+    diff = np.abs(d0.values(interior=True)[:, 0] - d.values(interior=True)[:, 0])
+    area = np.sum(0.5 * (diff[1:] + diff[:-1])) / diff.size          # trapezoidal rule, dx = 1 / n
+    assert area < 2e-2, (scheme_name, area)
+
+
+@pytest.mark.parametrize("method", ["FDM", "FVM"])
+def test_sparse_jacobian_equals_dense_forward_differences(method):
+    """Simulation.jacobian vs a dense forward-difference Jacobian of get_residuals_from_list, nx = 15,
+    split [1, 2], allclose(atol = 1e-7) (tests/test_simulation.py:203-265)."""
+    import splitfxm_b200 as sf
+    from splitfxm_b200.models.advection_diffusion import AdvectionDiffusion
+    d = sf.Domain.from_size(15, 1, 1, ["u", "v", "w"])
+    s = sf.Simulation(d, AdvectionDiffusion(c=0.2, nu=0.001, method=method), {"u": "gaussian", "v": "rarefaction"},
+                      README_BCS, sf.default_scheme(method))
+    split, locs = True, [1, 2]
+    x0 = d.listify_interior(split, locs)
+    dense = forward_difference_jacobian(lambda u: s.get_residuals_from_list(u, split, locs), x0)
+    with pytest.raises(sf.SFXM):
+        s.jacobian(x0, split)                       # split without split_locs
+    sparse = s.jacobian(x0, split, locs)
+    assert np.allclose(sparse.toarray(), dense, atol=1e-7)
+
+
+@pytest.mark.parametrize("scheme_name,nb", [("CENTRAL", (1, 1)), ("RIGHT_BIAS", (1, 2))])
+def test_jacobian_benchmark_shape_nx250(scheme_name, nb):
+    """benchmark/test_jac_benchmark.py:14-111: N = 250, u and v only; sparse faster than dense and equal to it.
+    Also the north-star target: at least 100x the reference's 0.16 s sparse assembly (BASELINE.md probe)."""
+    import splitfxm_b200 as sf
+    from splitfxm_b200.models.advection_diffusion import AdvectionDiffusion
+    d = sf.Domain.from_size(250, nb[0], nb[1], ["u", "v"])
+    bcs = {"u": README_BCS["u"], "v": README_BCS["v"]}
+    s = sf.Simulation(d, AdvectionDiffusion(c=0.2, nu=0.001, method="FDM"), {"u": "gaussian", "v": "rarefaction"}, bcs,
+                      sf.FDSchemes[scheme_name])
+    split, locs = True, [1]
+    x0 = d.listify_interior(split, locs)
+    t0 = time.perf_counter()
+    dense = forward_difference_jacobian(lambda u: s.get_residuals_from_list(u, split, locs), x0)
+    dense_time = time.perf_counter() - t0
+    s.jacobian(x0, split, locs)                      # warm-up (library load, allocations)
+    t0 = time.perf_counter()
+    sparse = s.jacobian(x0, split, locs)
+    sparse_time = time.perf_counter() - t0
+    assert sparse_time < dense_time
+    assert np.allclose(sparse.toarray(), dense, atol=1e-7)
+    assert sparse_time < 0.16 / 100.0, sparse_time
+
+
+def test_simulation_api_smoke():
+    """The calls tests/test_simulation.py:65-139 make: evolve, steady_state (iter >= 0), attributes."""
+    import splitfxm_b200 as sf
+    from splitfxm_b200.models.advection_diffusion import AdvectionDiffusion
+    d = sf.Domain.from_size(20, 1, 1, ["u", "v", "w"])
+    ics = {"u": "gaussian", "v": "rarefaction", "w": "tophat"}
+    s = sf.Simulation(d, AdvectionDiffusion(c=0.2, nu=0.001, method="FVM"), ics, README_BCS, sf.default_scheme("FVM"))
+    assert s._d is d and s._bcs is README_BCS and isinstance(s._r, sf.Refiner) and s._s._scheme is sf.FVSchemes.LAX_FRIEDRICHS
+    s.evolve(0.1, True, [1, 2])
+    bounds = [[-1.0, 0.0, -1.0], [5.0, 5.0, 5.0]]
+    s.evolve(0.01, method="Euler", max_step=0.005, bounds=bounds)
+    it = s.steady_state(split=True, split_locs=[1, 2], bounds=bounds)
+    assert it >= 0
+    assert np.isfinite(d.values()[:, 1:]).all()     # u is the singular periodic block
+    with pytest.raises(sf.SFXM):
+        s.evolve(0.1, method="Radau")               # implicit steppers are not on the device path yet
