@@ -109,6 +109,13 @@ int sfxm_fill_domain(const sfxm_problem_t *prob, const double *x_int, const doub
 int sfxm_jacobian(const sfxm_problem_t *prob, const double *x_int, const double *params, int64_t param_stride,
                   const double *geom, const double *y, double eps, double *J, double *r0, void *stream);
 
+/* sfxm_jacobian restricted to the variable segments [seg_lo, seg_hi) of a split layout: only those segments' blocks
+ * are evaluated and stored (the other entries of J are left untouched).  Split-Newton solves one segment at a time
+ * (simulation.py:520-523); the reference re-assembles the whole matrix for every sub-solve and slices it. */
+int sfxm_jacobian_segments(const sfxm_problem_t *prob, const double *x_int, const double *params, int64_t param_stride,
+                           const double *geom, const double *y, double eps, int32_t seg_lo, int32_t seg_hi, double *J,
+                           double *r0, void *stream);
+
 /* Solve, for every member and every variable segment, (J_seg + shift_m I) s = -f  with the block-tridiagonal
  * (cyclic if wrap slots are non-zero) J from sfxm_jacobian; W must be 3.  `shift` is per member (NULL = 0):
  * the pseudo-transient term of Newton's method.  `active` (NULL = all) masks members.  `work` needs

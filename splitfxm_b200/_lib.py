@@ -50,6 +50,7 @@ SIGNATURES = {
     "sfxm_geometry": (ctypes.c_int, [_PP, c_vp, c_vp, c_vp]),
     "sfxm_fill_domain": (ctypes.c_int, [_PP, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_jacobian": (ctypes.c_int, [_PP, c_vp, c_vp, c_i64, c_vp, c_vp, c_f64, c_vp, c_vp, c_vp]),
+    "sfxm_jacobian_segments": (ctypes.c_int, [_PP, c_vp, c_vp, c_i64, c_vp, c_vp, c_f64, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "sfxm_solve_workspace_bytes": (c_i64, [_PP]),
     "sfxm_block_tridiag_solve": (ctypes.c_int, [_PP, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_pcr_workspace_bytes": (c_i64, [_PP]),

@@ -59,7 +59,7 @@ extern "C" int sfxm_residual(const sfxm_problem_t *prob, const double *x_int, co
                              int64_t param_stride, const double *geom, const double *y, double *r, double *y_out,
                              double dt, void *stream) {
   if (!prob || !x_int || !params || !y || (!r && !y_out)) return set_error("sfxm_residual: null argument");
-  Launch L{OP_RESIDUAL, prob, x_int, params, param_stride, y, r, y_out, dt, (cudaStream_t)stream, geom};
+  Launch L{OP_RESIDUAL, prob, x_int, params, param_stride, y, r, y_out, dt, (cudaStream_t)stream, geom, 0, SFXM_MAX_NV + 1};
   return dispatch(L);
 }
 
@@ -68,7 +68,17 @@ extern "C" int sfxm_jacobian(const sfxm_problem_t *prob, const double *x_int, co
                              double *r0, void *stream) {
   if (!prob || !x_int || !params || !y || !J) return set_error("sfxm_jacobian: null argument");
   if (!(eps > 0.0)) return set_error("sfxm_jacobian: epsilon must be positive");
-  Launch L{OP_JACOBIAN, prob, x_int, params, param_stride, y, J, r0, eps, (cudaStream_t)stream, geom};
+  Launch L{OP_JACOBIAN, prob, x_int, params, param_stride, y, J, r0, eps, (cudaStream_t)stream, geom, 0, SFXM_MAX_NV + 1};
+  return dispatch(L);
+}
+
+extern "C" int sfxm_jacobian_segments(const sfxm_problem_t *prob, const double *x_int, const double *params,
+                                      int64_t param_stride, const double *geom, const double *y, double eps,
+                                      int32_t seg_lo, int32_t seg_hi, double *J, double *r0, void *stream) {
+  if (!prob || !x_int || !params || !y || !J) return set_error("sfxm_jacobian_segments: null argument");
+  if (!(eps > 0.0)) return set_error("sfxm_jacobian_segments: epsilon must be positive");
+  if (seg_lo < 0 || seg_hi <= seg_lo) return set_error("sfxm_jacobian_segments: empty segment range");
+  Launch L{OP_JACOBIAN, prob, x_int, params, param_stride, y, J, r0, eps, (cudaStream_t)stream, geom, seg_lo, seg_hi};
   return dispatch(L);
 }
 

@@ -167,10 +167,17 @@ class Engine:
         _lib.count()
         return x_all, U_all
 
-    def jacobian(self, y, split=False, split_locs=None, eps=1e-8, J=None, r0=None):
-        P, _ = self.problem(split, split_locs)
+    def jacobian(self, y, split=False, split_locs=None, eps=1e-8, J=None, r0=None, seg_lo=None, seg_hi=None):
+        """Block-banded Jacobian; seg_lo/seg_hi restrict the assembly to those variable segments (Split-Newton)."""
+        P, segs = self.problem(split, split_locs)
         if J is None:
             J = self.jacobian_buffer()
+        if seg_lo is not None and not (seg_lo == 0 and seg_hi == len(segs)):
+            _lib.check(self.lib.sfxm_jacobian_segments(ctypes.byref(P), _lib.ptr(self.x_int), _lib.ptr(self.params),
+                                                       self.param_stride, _lib.ptr(self._geom), _lib.ptr(y), float(eps),
+                                                       int(seg_lo), int(seg_hi), _lib.ptr(J), _lib.ptr(r0), _lib.stream_ptr()))
+            _lib.count()
+            return J
         _lib.check(self.lib.sfxm_jacobian(ctypes.byref(P), _lib.ptr(self.x_int), _lib.ptr(self.params), self.param_stride,
                                           _lib.ptr(self._geom), _lib.ptr(y), float(eps), _lib.ptr(J), _lib.ptr(r0),
                                           _lib.stream_ptr()))

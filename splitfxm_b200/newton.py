@@ -65,7 +65,8 @@ class NewtonDriver:
             if not bool(run.any()):
                 break
             run32 = run.to(torch.int32)
-            J = eng.jacobian(y, self.split, self.split_locs, self.eps, r0=self.r)   # r = f(y), J = f'(y)
+            # r = f(y) and the blocks of J = f'(y) that belong to segment k (the only ones this solve reads)
+            J = eng.jacobian(y, self.split, self.split_locs, self.eps, r0=self.r, seg_lo=k, seg_hi=k + 1)
             shift = (-1.0 / dt) if self.dt0 > 0 else None
             eng.solve(J, self.r, self.s, self.split, self.split_locs, k, k + 1, shift=shift, active=run32,
                       status=self.status)

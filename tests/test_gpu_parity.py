@@ -120,3 +120,49 @@ def test_large_mesh_linearity_and_oracle_sample():
     assert np.max(np.abs(rab - (ra + 2.0 * rb))) < 1e-9 * scale
     P = core.Problem(core.AdvectionDiffusion(0.2, 0.001), "FDM", "CENTRAL", np.linspace(0, 1, nx), 1, 1, bcs, comps)
     assert np.array_equal(ra, P.residual(a))
+
+
+@pytest.mark.parametrize("case,scheme_name,nb,split,locs", [
+    ("ad_fvm_lf_nx40_mixedbc", "LAX_FRIEDRICHS", (1, 1), False, None),
+    ("ad_fdm_central_nx250_split1", "CENTRAL", (1, 1), True, [1]),
+    ("ad_fdm_rbias_nx40_mixedbc", "RIGHT_BIAS", (1, 2), True, [1, 2]),
+    ("sod_cons_nx100_t0p05", "LAX_FRIEDRICHS", (1, 1), True, [1]),
+])
+def test_pair_kernels_equal_per_member_kernels(case, scheme_name, nb, split, locs):
+    """Even batches >= 64 run the two-members-per-lane kernels; an odd batch runs the one-member kernels.  The
+    members the two runs share must agree bit for bit (residual, Euler update, Jacobian), including members whose
+    state is made insane on purpose (zero / huge values force the IEEE-division fallback inside a pair)."""
+    import torch
+    import splitfxm_b200 as sf
+    from splitfxm_b200.ensemble import EnsembleSimulation
+    from oracle import core
+    z = load(case)
+    m = __import__("helpers").case_meta(z)
+    nv = len(m["comps"])
+    rng = np.random.default_rng(11)
+    B = 128
+    base = core.to_flat(core.to_block(z["x0"], m["nx"], nv, m["split"], m["locs"]), split, locs)
+    Y = np.repeat(base[:, None], B, axis=1) * (1.0 + 0.01 * rng.standard_normal((base.shape[0], B)))
+    if m["model"] == "ad":
+        Y[5, 3] = 0.0
+        Y[7, 10] = 1e200            # fails the sanity check: this member's cells use the IEEE division
+        params = {"c": rng.uniform(-0.5, 0.5, B), "nu": 10.0 ** rng.uniform(-4, -2, B)}
+    else:
+        params = {"gamma": np.full(B, 1.4)}
+    d = sf.Domain.from_arrays(z["x_all"], z["U_all"], nb[0], nb[1], m["comps"])
+    scheme = (sf.FVSchemes if m["method"] == "FVM" else sf.FDSchemes)[scheme_name]
+    outs = []
+    for nb_members in (B, B - 1):
+        p = {k: v[:nb_members] for k, v in params.items()}
+        ens = EnsembleSimulation(d, m["model"], p, m["bcs"], scheme, method=m["method"])
+        Yd = ens.eng.to_device(np.ascontiguousarray(Y[:, :nb_members]))
+        r = ens.residual(Yd, split, locs)
+        yn = torch.empty_like(Yd)
+        ens.eng.euler_step(Yd, yn, 1e-4, split, locs)
+        J = ens.jacobian(Yd, split, locs)
+        outs.append((r.cpu().numpy(), yn.cpu().numpy(), J.cpu().numpy()))
+    (r2, y2, J2), (r1, y1, J1) = outs
+    with np.errstate(invalid="ignore"):
+        assert np.array_equal(r2[:, :B - 1], r1, equal_nan=True)
+        assert np.array_equal(y2[:, :B - 1], y1, equal_nan=True)
+        assert np.array_equal(J2[..., :B - 1], J1, equal_nan=True)
