@@ -561,6 +561,10 @@ jacobian_pair_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
   }
 }
 
+// (A strip variant - the warp walks several cells with the stencil as a sliding register window and prefetches the
+// next cell's slot before evaluating the current one - was tried to overlap the load, compute and store phases: the
+// loop body needs > 255 registers, spills, and runs at 0.77 ms against 0.57 ms for one cell per CTA; removed.)
+
 // ------------------------------------------------------------------------------------------------
 // Decoupled models (every variable obeys the same scalar equation): ONE THREAD PER (cell, variable, member).
 // Three times the warps of the cell-per-thread kernels at a third of the registers (latency hiding instead of
