@@ -116,6 +116,11 @@ int sfxm_jacobian_segments(const sfxm_problem_t *prob, const double *x_int, cons
                            const double *geom, const double *y, double eps, int32_t seg_lo, int32_t seg_hi, double *J,
                            double *r0, void *stream);
 
+/* Compact copy of a split Jacobian for the trip to the host: J_packed[((i*W + d)*L + e)*batch + m] holds the L
+ * same-segment (r, c) entries of every block in row-major (r, c) order - the only entries Simulation.jacobian stores
+ * in split mode (simulation.py:373-392).  *n_live_host receives L; with J == NULL the call only reports L. */
+int sfxm_pack_jacobian(const sfxm_problem_t *prob, const double *J, double *J_packed, int32_t *n_live_host, void *stream);
+
 /* Solve, for every member and every variable segment, (J_seg + shift_m I) s = -f  with the block-tridiagonal
  * (cyclic if wrap slots are non-zero) J from sfxm_jacobian; W must be 3.  `shift` is per member (NULL = 0):
  * the pseudo-transient term of Newton's method.  `active` (NULL = all) masks members.  `work` needs

@@ -51,6 +51,7 @@ SIGNATURES = {
     "sfxm_fill_domain": (ctypes.c_int, [_PP, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_jacobian": (ctypes.c_int, [_PP, c_vp, c_vp, c_i64, c_vp, c_vp, c_f64, c_vp, c_vp, c_vp]),
     "sfxm_jacobian_segments": (ctypes.c_int, [_PP, c_vp, c_vp, c_i64, c_vp, c_vp, c_f64, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "sfxm_pack_jacobian": (ctypes.c_int, [_PP, c_vp, c_vp, ctypes.POINTER(c_i32), c_vp]),
     "sfxm_solve_workspace_bytes": (c_i64, [_PP]),
     "sfxm_block_tridiag_solve": (ctypes.c_int, [_PP, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_pcr_workspace_bytes": (c_i64, [_PP]),

@@ -365,6 +365,23 @@ block_thomas_ll_kernel(const __grid_constant__ sfxm_problem_t P, int o, const do
   if (status && !ok) status[m] = 1;
 }
 
+// Compact copy of the same-segment entries of a split Jacobian (the only ones that exist, simulation.py:373-392):
+// dst[((i*W + d)*L + e) * B + m] = src[((i*W + d)*nv*nv + rc[e]) * B + m],  rc = the L live (r, c) pairs in
+// row-major order.  Pure row gather (coalesced 8-byte per lane reads/writes): what the host transfer moves.
+struct PackMap {
+  int32_t rc[SFXM_MAX_NV * SFXM_MAX_NV];
+  int32_t L;
+};
+__global__ void pack_jacobian_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t rows, int nvnv,
+                                     const __grid_constant__ PackMap map, int64_t B) {
+  const int64_t m = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;   // (row, e)
+  if (m >= B || t >= rows * map.L) return;
+  const int64_t row = t / map.L;
+  const int e = (int)(t - row * map.L);
+  dst[t * B + m] = __ldg(src + (row * nvnv + map.rc[e]) * B + m);
+}
+
 struct SquareTerm {   // the norms of the Newton convergence criterion
   const double *v;
   int64_t B;
@@ -457,6 +474,25 @@ extern "C" int sfxm_block_tridiag_solve(const sfxm_problem_t *prob, const double
     if (e) return e;
   }
   return 0;
+}
+
+extern "C" int sfxm_pack_jacobian(const sfxm_problem_t *prob, const double *J, double *J_packed, int32_t *n_live_host,
+                                  void *stream) {
+  if (!prob || !n_live_host) return set_error("sfxm_pack_jacobian: null argument");
+  const sfxm_problem_t &P = *prob;
+  PackMap map;
+  map.L = 0;
+  for (int r = 0; r < P.nv; ++r)
+    for (int c = 0; c < P.nv; ++c)
+      if (P.var_seg[r] == P.var_seg[c]) map.rc[map.L++] = r * P.nv + c;
+  *n_live_host = map.L;
+  if (!J || !J_packed) return 0;     // query only
+  const int64_t rows = P.nx * (P.nbl + P.nbr + 1);
+  dim3 b = P.batch >= 32 ? dim3(32, 8) : dim3(1, 256);
+  dim3 g((unsigned)((rows * map.L + b.y - 1) / b.y), (unsigned)((P.batch + b.x - 1) / b.x));
+  if (g.y > 65535) return set_error("sfxm_pack_jacobian: batch too large");
+  pack_jacobian_kernel<<<g, b, 0, (cudaStream_t)stream>>>(J, J_packed, rows, P.nv * P.nv, map, P.batch);
+  return check_launch("sfxm_pack_jacobian");
 }
 
 extern "C" int64_t sfxm_sumsq_workspace_bytes(int64_t n, int64_t batch) {

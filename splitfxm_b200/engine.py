@@ -184,6 +184,26 @@ class Engine:
         _lib.count()
         return J
 
+    def live_entries(self, split=False, split_locs=None):
+        """(r, c) pairs of a block that exist in this layout (same variable segment), row-major."""
+        _, segs = self.problem(split, split_locs)
+        seg_of = {}
+        for k, (o, s) in enumerate(segs):
+            for j in range(o, o + s):
+                seg_of[j] = k
+        return [(r, c) for r in range(self.nv) for c in range(self.nv) if seg_of[r] == seg_of[c]]
+
+    def pack_jacobian(self, J, split=False, split_locs=None, out=None):
+        """-> [nx, W, L, batch] device tensor with the live entries only (sfxm_pack_jacobian)."""
+        P, _ = self.problem(split, split_locs)
+        L = ctypes.c_int32(0)
+        _lib.check(self.lib.sfxm_pack_jacobian(ctypes.byref(P), None, None, ctypes.byref(L), None))
+        if out is None:
+            out = torch.empty((self.nx, self.W, L.value, self.batch), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.sfxm_pack_jacobian(ctypes.byref(P), _lib.ptr(J), _lib.ptr(out), ctypes.byref(L), _lib.stream_ptr()))
+        _lib.count()
+        return out
+
     def solve(self, J, f, s, split=False, split_locs=None, seg_lo=0, seg_hi=None, shift=None, active=None, status=None,
               method=None):
         """(J_seg + shift I) s = -f for segments [seg_lo, seg_hi)."""

@@ -58,6 +58,43 @@ class EnsembleSimulation:
         """Block-banded Jacobians [nx, W, nv, nv, batch] (include/sfxm_b200.h)."""
         return self.eng.jacobian(self._state(Y), split, split_locs, epsilon, J=out)
 
+    def jacobian_host(self, Y_host, out_host, split=False, split_locs=None, epsilon=1e-8, slot=0):
+        """Host buffers in, host buffers out, asynchronously: Y_host [n, batch] (pinned) -> out_host
+        [nx, W, L, batch] (pinned) with the L same-segment entries of every block (`eng.live_entries`).
+
+        The upload, the assembly and the packing run on one stream, the download on a second one; with two slots
+        (`slot` 0 / 1, each with its own device buffers) consecutive calls overlap the download of one step with the
+        upload and assembly of the next.  Call `sync_host()` before reading `out_host`."""
+        eng = self.eng
+        if not hasattr(self, "_slots"):
+            self._slots = {}
+            self._copy_stream = torch.cuda.Stream(device=eng.device)
+        st = self._slots.get(slot)
+        if st is None:
+            L = len(eng.live_entries(split, split_locs))
+            st = {"Y": torch.empty((eng.n, eng.batch), dtype=torch.float64, device=eng.device),
+                  "J": torch.zeros((eng.nx, eng.W, eng.nv, eng.nv, eng.batch), dtype=torch.float64, device=eng.device),
+                  "Jc": torch.empty((eng.nx, eng.W, L, eng.batch), dtype=torch.float64, device=eng.device),
+                  "done": torch.cuda.Event(), "free": torch.cuda.Event()}
+            st["free"].record()
+            self._slots[slot] = st
+        main = torch.cuda.current_stream()
+        main.wait_event(st["free"])                     # the previous download from this slot has finished
+        st["Y"].copy_(Y_host, non_blocking=True)
+        eng.jacobian(st["Y"], split, split_locs, epsilon, J=st["J"])
+        eng.pack_jacobian(st["J"], split, split_locs, out=st["Jc"])
+        st["done"].record(main)
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(st["done"])
+            out_host.copy_(st["Jc"], non_blocking=True)
+            st["free"].record(self._copy_stream)
+        return out_host
+
+    def sync_host(self):
+        if hasattr(self, "_copy_stream"):
+            self._copy_stream.synchronize()
+        torch.cuda.current_stream().synchronize()
+
     def steady_state(self, Y, split=False, split_locs=None, dt0=0.0, dtmax=1.0, armijo=False, bounds=None,
                      maxiter=math.inf):
         """-> (Y_final [n, batch] device tensor, iterations int64[batch])."""

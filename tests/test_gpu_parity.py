@@ -166,3 +166,30 @@ def test_pair_kernels_equal_per_member_kernels(case, scheme_name, nb, split, loc
         assert np.array_equal(r2[:, :B - 1], r1, equal_nan=True)
         assert np.array_equal(y2[:, :B - 1], y1, equal_nan=True)
         assert np.array_equal(J2[..., :B - 1], J1, equal_nan=True)
+
+
+def test_host_round_trip_of_packed_jacobians():
+    """EnsembleSimulation.jacobian_host (pinned host in, packed pinned host out, two overlapping slots) returns the
+    same-segment entries of the device Jacobian, entry for entry."""
+    import torch
+    import splitfxm_b200 as sf
+    from splitfxm_b200.ensemble import EnsembleSimulation
+    z = load("ad_fdm_central_nx250_split1")
+    m = __import__("helpers").case_meta(z)
+    B = 96
+    rng = np.random.default_rng(2)
+    d = sf.Domain.from_arrays(z["x_all"], z["U_all"], 1, 1, m["comps"])
+    ens = EnsembleSimulation(d, "ad", {"c": rng.uniform(0.05, 0.5, B), "nu": 10.0 ** rng.uniform(-4, -2, B)}, m["bcs"],
+                             sf.FDSchemes.CENTRAL, method="FDM")
+    Ys = [torch.from_numpy(np.repeat(z["x0"][:, None], B, axis=1) + 0.01 * rng.standard_normal((z["x0"].shape[0], B))).pin_memory()
+          for _ in range(3)]
+    live = ens.eng.live_entries(True, [1])
+    assert live == [(0, 0), (1, 1), (1, 2), (2, 1), (2, 2)]
+    outs = [torch.empty((250, 3, len(live), B), dtype=torch.float64).pin_memory() for _ in range(3)]
+    for k in range(3):
+        ens.jacobian_host(Ys[k], outs[k], True, [1], slot=k % 2)
+    ens.sync_host()
+    for k in range(3):
+        full = ens.jacobian(Ys[k], True, [1]).cpu().numpy()
+        for e, (r, c) in enumerate(live):
+            assert np.array_equal(outs[k].numpy()[:, :, e, :], full[:, :, r, c, :])
