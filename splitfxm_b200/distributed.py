@@ -221,6 +221,33 @@ class SlabSimulation:
             nsteps += 1
         return y, nsteps
 
+    def evolve_rk45(self, y, t_diff, max_step=float("inf"), split=False, split_locs=None, n_global=None):
+        """scipy's RK45 (ode.RK45Stepper) on the decomposed mesh: every right-hand side is preceded by a halo
+        exchange and the error / initial-step norms are summed over the slabs with one scalar all-reduce each, so all
+        ranks take identical steps.  Returns the dense-output end value of this slab."""
+        import torch.distributed as dist
+        from .ode import RK45Stepper
+
+        def rhs(v, out):
+            self.exchange(v, split, split_locs)
+            self.eng.residual(v, out, split, split_locs)
+
+        def reduce(local):
+            if self.world == 1 or not dist.is_initialized():
+                return local
+            t = torch.tensor([local], dtype=torch.float64, device=self.eng.device)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return float(t[0])
+
+        if n_global is None:
+            n_loc = torch.tensor([self.eng.n], dtype=torch.int64, device=self.eng.device)
+            if self.world > 1 and dist.is_initialized():
+                dist.all_reduce(n_loc, op=dist.ReduceOp.SUM)
+            n_global = int(n_loc[0])
+        stepper = RK45Stepper(self.eng, split, split_locs, 1e-3, 1e-6, max_step, rhs=rhs, reduce=reduce, n_global=n_global)
+        out = stepper.integrate(y, t_diff)
+        return out, stepper.nfev
+
     # -- fused halo exchange over peer-mapped memory (NVLink) ---------------------------------------------
     def enable_peer_halos(self, group=None):
         """Put the halo buffers in symmetric memory and map the neighbours' buffers (one process per GPU, NCCL group

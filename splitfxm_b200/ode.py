@@ -50,7 +50,11 @@ def euler(eng, y, t_diff, max_step, split=False, split_locs=None, on_step=None):
 
 
 class RK45Stepper:
-    def __init__(self, eng, split=False, split_locs=None, rtol=1e-3, atol=1e-6, max_step=np.inf):
+    """rhs(y, out): right-hand side (default: the engine's residual).  reduce(x): combines a local sum of squares
+    over all slabs of a decomposed mesh (default: identity); n_global: number of unknowns of the whole mesh."""
+
+    def __init__(self, eng, split=False, split_locs=None, rtol=1e-3, atol=1e-6, max_step=np.inf, rhs=None, reduce=None,
+                 n_global=None):
         if eng.batch != 1:
             raise SFXM("adaptive RK45 drives one mesh; ensembles use Euler stepping or per-member Simulations")
         if max_step <= 0:
@@ -68,9 +72,15 @@ class RK45Stepper:
         self.work = torch.empty(max(nbytes // 8, 1), dtype=torch.float64, device=dev)
         self.nfev = 0
         self.last_rhs_state = None     # state of the last RHS evaluation (the reference's ghosts belong to it)
+        self._rhs = rhs
+        self._reduce = reduce if reduce is not None else (lambda v: v)
+        self._n_global = int(n_global) if n_global is not None else eng.n
 
     def f(self, y, out):
-        self.eng.residual(y, out, self.split, self.split_locs)
+        if self._rhs is not None:
+            self._rhs(y, out)
+        else:
+            self.eng.residual(y, out, self.split, self.split_locs)
         self.nfev += 1
 
     def _rms(self, a, a2, b):
@@ -79,7 +89,7 @@ class RK45Stepper:
         _lib.check(eng.lib.sfxm_scaled_diff_sumsq(_lib.ptr(a), _lib.ptr(a2), _lib.ptr(b), self.atol, self.rtol, eng.n,
                                                   eng.batch, _lib.ptr(self.out1), _lib.ptr(self.work), _lib.stream_ptr()))
         _lib.count(2)
-        return math.sqrt(float(self.out1[0])) / eng.n ** 0.5
+        return math.sqrt(self._reduce(float(self.out1[0]))) / self._n_global ** 0.5
 
     def _lincomb(self, y, coef, nstage, h, out):
         eng = self.eng
@@ -150,7 +160,7 @@ class RK45Stepper:
                                                        _lib.ptr(y_new), self.atol, self.rtol, eng.n, eng.batch,
                                                        _lib.ptr(self.out1), _lib.ptr(self.work), _lib.stream_ptr()))
                 _lib.count(2)
-                error_norm = math.sqrt(float(self.out1[0])) / eng.n ** 0.5
+                error_norm = math.sqrt(self._reduce(float(self.out1[0]))) / self._n_global ** 0.5
                 if error_norm < 1:
                     if error_norm == 0:
                         factor = MAX_FACTOR
