@@ -52,7 +52,18 @@ def member_params(first, count, total):
 
 
 def initial_state():
-    """Flat split-major initial vector [750] of the benchmark problem (host, NumPy)."""
+    """Flat split-major initial vector [750] of the benchmark problem, built with the product's host API
+    (the GPU arm never touches oracle/)."""
+    import splitfxm_b200 as sf
+    from splitfxm_b200.initialize import set_initial_condition
+    d = sf.Domain.from_size(NX, 1, 1, COMPS)
+    for c in COMPS:
+        set_initial_condition(d, c, ICS[c])
+    return np.array(d.positions(interior=True)), d.listify_interior(SPLIT, LOCS)
+
+
+def initial_state_oracle():
+    """The same vector from the oracle's own restatement (CPU arm)."""
     from oracle import core
     x = np.linspace(0.0, 1.0, NX)
     U = np.stack([core.initial_condition(x, ICS[c]) for c in COMPS], axis=1)
@@ -72,7 +83,7 @@ def member_states(y0, first, count):
 def _cpu_assemble(args):
     first, count, total = args
     from oracle import core
-    x, y0 = initial_state()
+    x, y0 = initial_state_oracle()
     c, nu = member_params(first, count, total)
     Y = member_states(y0, first, count)
     acc = 0.0

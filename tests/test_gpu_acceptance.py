@@ -105,3 +105,31 @@ def test_simulation_api_smoke():
     assert np.isfinite(d.values()[:, 1:]).all()     # u is the singular periodic block
     with pytest.raises(sf.SFXM):
         s.evolve(0.1, method="Radau")               # implicit steppers are not on the device path yet
+
+
+def test_error_paths_on_the_device_path():
+    """Inputs the kernels cannot take raise SFXM (never a silent fallback): meshes smaller than twice the stencil,
+    UPWIND with a non-diagonal flux Jacobian, Newton on a 4-cell stencil, a state of the wrong length."""
+    import splitfxm_b200 as sf
+    from splitfxm_b200.models.advection_diffusion import AdvectionDiffusion
+    from splitfxm_b200.models.euler1d import Euler1DConservative
+    per = {"left": "periodic", "right": "periodic"}
+    d = sf.Domain.from_size(4, 1, 1, ["u"])
+    s = sf.Simulation(d, AdvectionDiffusion(0.2, 0.001, "FVM"), {"u": "sine"}, {"u": per}, sf.FVSchemes.LAX_FRIEDRICHS)
+    with pytest.raises(sf.SFXM):
+        s.get_residuals_from_list(d.listify_interior(False))
+    names = ["rho", "rhou", "E"]
+    d = sf.Domain.from_size(30, 1, 1, names)
+    for c in d.interior():
+        c.set_values(np.array([1.0, 0.0, 2.5]))
+    s = sf.Simulation(d, Euler1DConservative(1.4, "FVM"), {}, {n: per for n in names}, sf.FVSchemes.UPWIND)
+    with pytest.raises(sf.SFXM):
+        s.get_residuals_from_list(d.listify_interior(False))
+    d = sf.Domain.from_size(30, 1, 2, ["u"])
+    s = sf.Simulation(d, AdvectionDiffusion(0.2, 0.001, "FDM"), {"u": "sine"}, {"u": per}, sf.FDSchemes.RIGHT_BIAS)
+    with pytest.raises(sf.SFXM):
+        s.steady_state()
+    with pytest.raises(sf.SFXM):
+        s.get_residuals_from_list(np.zeros(29))
+    with pytest.raises(sf.SFXM):
+        s.jacobian(np.zeros(30), True, [5])
