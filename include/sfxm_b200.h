@@ -205,6 +205,16 @@ int sfxm_halo_signal_counter(int64_t *counter, int64_t *left_peer_flag, int64_t 
 int sfxm_halo_wait_counter(const int64_t *counter, const int64_t *from_left_flag, const int64_t *from_right_flag,
                            int32_t *timeout_flag, void *stream);
 
+/* ---- kernel-level entry points on ONE stencil: the cdef workers behind the reference's Python wrappers fluxes /
+ * diffusion_fluxes (flux.pyx:42-124, 302-327) and Dx / D2x / dx / d2x (derivatives.pyx:196-281).  The wrappers
+ * evaluate the user's Python callables on the stencil cells (host) and pass the values; arrays are device pointers,
+ * [slots][nv] row-major. ---- */
+int sfxm_fv_fluxes(int32_t scheme, int32_t nv, const double *F, const double *u, double sigma, const double *eig,
+                   double *Fw, double *Fe, void *stream);
+int sfxm_fv_diffusion_fluxes(int32_t nv, const double *D, const double *x, double *Dw, double *De, void *stream);
+int sfxm_fd_derivative(int32_t scheme, int32_t order, int32_t nv, const double *F, const double *x, double *out,
+                       void *stream);
+
 /* Device self-test: counts (into *mismatch_dev, a device uint64 the caller zeroes) operands for which the
  * five-FMA division by a known reciprocal used in the stencil kernels differs from the IEEE quotient.
  * mode 0 = random operands, mode 1 = adversarial (divisor mantissa all ones/zeros, half-way numerators). */

@@ -74,6 +74,9 @@ SIGNATURES = {
     "sfxm_halo_wait": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "sfxm_halo_signal_counter": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "sfxm_halo_wait_counter": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_fv_fluxes": (ctypes.c_int, [c_i32, c_i32, c_vp, c_vp, c_f64, c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_fv_diffusion_fluxes": (ctypes.c_int, [c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_fd_derivative": (ctypes.c_int, [c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_selftest_div": (ctypes.c_int, [c_i64, ctypes.c_uint64, c_i32, c_vp, c_vp]),
 }
 
