@@ -24,3 +24,25 @@ def report_bounds(y, bounds, t_current):
 
 
 apply_bounds = report_bounds
+
+
+def create_bound_events(y0, bounds):
+    """One non-terminal scipy event per unknown that prints the reference's warning when the unknown leaves its
+    bounds (simhelper.py:31-88); [] when there are no bounds."""
+    if bounds is None:
+        return []
+    lower, upper = bounds[0], bounds[1]
+
+    def make(index, lo, hi):
+        def event(t, y):
+            if y[index] < lo:
+                print(f"Warning: At t={t}, bounds exceeded for variable index {index}, value = {y[index]}, lower bound = {lo}")
+                return y[index] - lo
+            if y[index] > hi:
+                print(f"Warning: At t={t}, bounds exceeded for variable index {index}, value = {y[index]}, upper bound = {hi}")
+                return hi - y[index]
+            return 1
+        event.terminal = False
+        event.direction = 0
+        return event
+    return [make(i, lower[i], upper[i]) for i in range(len(y0))]

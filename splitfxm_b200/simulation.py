@@ -22,7 +22,7 @@ from .newton import NewtonDriver
 from .ode import RK45Stepper, euler
 from .refine import Refiner
 from .schemes import FDSchemes, FVSchemes, _scheme_ids, stencil_sizes
-from .simhelper import array_list_reshape, report_bounds
+from .simhelper import array_list_reshape, create_bound_events, report_bounds
 from .system import System
 
 JAC_REQUIRED = ["Radau", "BDF"]
@@ -202,7 +202,26 @@ class Simulation:
             if bounds is not None:
                 report_bounds(y.cpu().numpy().reshape(-1), ext_bounds, t_diff)
         else:
-            raise SFXM(f"evolve method '{method}' is not available on the device path (Euler, RK45)")
+            # Any other scipy method (RK23, DOP853, LSODA, Radau, BDF ...): scipy.integrate.solve_ivp drives, exactly as
+            # in the reference (simulation.py:466-469), with the right-hand side and - for the implicit methods - the
+            # constant Jacobian at y0 (simulation.py:441-443) evaluated on the device.  scipy's own step control and
+            # linear algebra stay scipy's, as they are in the reference.
+            from scipy.integrate import solve_ivp
+            last = {}
+
+            def f(_, yv):
+                yd = eng.to_device(np.asarray(yv, dtype=np.float64))
+                last["y"] = yd
+                return eng.residual(yd, None, split, split_locs).cpu().numpy().reshape(-1)
+
+            jac = None
+            if method in JAC_REQUIRED:
+                jac = self.jacobian(y0, split, split_locs)
+                eng = self._engine()
+            events = create_bound_events(y0, ext_bounds)
+            sol = solve_ivp(f, (0, t_diff), y0, method=method, t_eval=[t_diff], jac=jac, max_step=max_step, events=events)
+            y = eng.to_device(np.ascontiguousarray(sol.y.reshape(-1)))
+            ghost_state = last.get("y")
         self._store(eng, y, split, split_locs, ghost_state)
 
     def steady_state(self, split=False, split_locs=None, sparse=True, dt0=0.0, dtmax=1.0, armijo=False, bounds=None):

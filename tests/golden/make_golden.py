@@ -268,6 +268,9 @@ def evolve_case(tag, method_name, t, max_step, nx=20, split=False, locs=None, fv
 evolve_case("evolve_readme_rk45", "RK45", 0.1, np.inf)
 evolve_case("evolve_readme_rk45_split", "RK45", 0.25, np.inf, split=True, locs=[1, 2])
 evolve_case("evolve_rk45_maxstep", "RK45", 0.3, 0.05, nx=40, fv=False)
+evolve_case("evolve_readme_radau", "Radau", 0.1, np.inf)
+evolve_case("evolve_readme_bdf_split", "BDF", 0.2, np.inf, split=True, locs=[1, 2], fv=False)
+evolve_case("evolve_readme_rk23", "RK23", 0.1, np.inf)
 evolve_case("evolve_euler", "Euler", 1.0, 0.03, nx=30)
 evolve_case("evolve_euler_split_fd", "Euler", 0.5, 0.01, nx=25, split=True, locs=[1], fv=False)
 
