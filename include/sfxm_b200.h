@@ -139,6 +139,13 @@ int sfxm_block_tridiag_solve_pcr(const sfxm_problem_t *prob, const double *J, co
                                  const int32_t *active, int32_t seg_lo, int32_t seg_hi, double *s, double *work,
                                  int32_t *status, void *stream);
 
+/* The same solve for 4-cell stencils (FD RIGHT_BIAS, nb_left + nb_right = 3): cells are folded into two-cell
+ * super-blocks, which makes the band block tridiagonal again, then PCR.  Periodic variables need an even nx. */
+int64_t sfxm_band4_workspace_bytes(const sfxm_problem_t *prob);
+int sfxm_block_band4_solve_pcr(const sfxm_problem_t *prob, const double *J, const double *f, const double *shift,
+                               const int32_t *active, int32_t seg_lo, int32_t seg_hi, double *s, double *work,
+                               int32_t *status, void *stream);
+
 /* Per-member sums of squares over a flat-index range [lo, hi): out[m] = sum v[q*batch+m]^2, accumulated in a
  * fixed order (deterministic).  work: sfxm_sumsq_workspace_bytes(hi - lo, batch).  The norms of
  * splitnewton's convergence criterion. */

@@ -17,74 +17,9 @@
 #include <cstdint>
 #include "../../include/sfxm_b200.h"
 #include "sfxm_host.h"
+#include "sfxm_pcr.cuh"
 
 namespace sfxm {
-
-template <int S, int NC>
-__device__ __forceinline__ bool gj_solve_pcr(double (&A)[S][S], double (&R)[S][NC]) {
-  bool ok = true;
-#pragma unroll
-  for (int k = 0; k < S; ++k) {
-    int piv = k;
-    double best = fabs(A[k][k]);
-#pragma unroll
-    for (int r = k + 1; r < S; ++r) {
-      const double a = fabs(A[r][k]);
-      if (a > best) { best = a; piv = r; }
-    }
-    if (best == 0.0) ok = false;
-#pragma unroll
-    for (int r = k + 1; r < S; ++r) {
-      if (r == piv) {
-#pragma unroll
-        for (int c = 0; c < S; ++c) { const double t = A[k][c]; A[k][c] = A[r][c]; A[r][c] = t; }
-#pragma unroll
-        for (int c = 0; c < NC; ++c) { const double t = R[k][c]; R[k][c] = R[r][c]; R[r][c] = t; }
-      }
-    }
-    const double inv = 1.0 / A[k][k];
-#pragma unroll
-    for (int c = 0; c < S; ++c) A[k][c] *= inv;
-#pragma unroll
-    for (int c = 0; c < NC; ++c) R[k][c] *= inv;
-#pragma unroll
-    for (int r = 0; r < S; ++r) {
-      if (r == k) continue;
-      const double f = A[r][k];
-#pragma unroll
-      for (int c = 0; c < S; ++c) A[r][c] -= f * A[k][c];
-#pragma unroll
-      for (int c = 0; c < NC; ++c) R[r][c] -= f * R[k][c];
-    }
-  }
-  return ok;
-}
-
-// row storage: ROW = 2 S^2 + S NR doubles per (cell, member): [Abar | Cbar | Dbar], element e at (i*ROW + e)*B + m
-template <int S, int NR>
-struct Row {
-  static constexpr int kRow = 2 * S * S + S * NR;
-  double R[S][2 * S + NR];   // columns: Abar (S) | Cbar (S) | Dbar (NR)
-  __device__ __forceinline__ void load(const double *__restrict__ w, int64_t i, int64_t B, int64_t m) {
-    const double *p = w + (i * kRow) * B + m;
-#pragma unroll
-    for (int r = 0; r < S; ++r)
-#pragma unroll
-      for (int c = 0; c < 2 * S + NR; ++c) R[r][c] = __ldg(p + (int64_t)(r * (2 * S + NR) + c) * B);
-  }
-  __device__ __forceinline__ void store(double *__restrict__ w, int64_t i, int64_t B, int64_t m) const {
-    double *p = w + (i * kRow) * B + m;
-#pragma unroll
-    for (int r = 0; r < S; ++r)
-#pragma unroll
-      for (int c = 0; c < 2 * S + NR; ++c) p[(int64_t)(r * (2 * S + NR) + c) * B] = R[r][c];
-  }
-};
-
-__device__ __forceinline__ void pcr_coords(int64_t &m, int64_t &i) {
-  m = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
-  i = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
-}
 
 // J (banded, W = 3) + f -> normalised rows of the (condensed) system of ne = n or n-1 block rows
 template <int NV, int S, bool CYCLIC>
@@ -116,67 +51,6 @@ __global__ void pcr_init_kernel(const __grid_constant__ sfxm_problem_t P, int o,
   }
   if (!gj_solve_pcr<S, 2 * S + NR>(Bd, row.R) && status) status[m] = 1;
   row.store(w, i, B, m);
-}
-
-template <int S, int NR>
-__global__ void pcr_step_kernel(int64_t ne, int64_t B, int64_t h, const double *__restrict__ win,
-                                double *__restrict__ wout, int32_t *__restrict__ status) {
-  int64_t m, i;
-  pcr_coords(m, i);
-  if (m >= B || i >= ne) return;
-  Row<S, NR> me, nb;
-  me.load(win, i, B, m);
-  double Bd[S][S];
-  double out[S][2 * S + NR];
-#pragma unroll
-  for (int r = 0; r < S; ++r) {
-#pragma unroll
-    for (int c = 0; c < S; ++c) {
-      Bd[r][c] = (r == c) ? 1.0 : 0.0;
-      out[r][c] = 0.0;
-      out[r][S + c] = 0.0;
-    }
-#pragma unroll
-    for (int c = 0; c < NR; ++c) out[r][2 * S + c] = me.R[r][2 * S + c];
-  }
-  if (i - h >= 0) {
-    nb.load(win, i - h, B, m);
-#pragma unroll
-    for (int r = 0; r < S; ++r)
-#pragma unroll
-      for (int k = 0; k < S; ++k) {
-        const double a = me.R[r][k];                        // Abar_i
-#pragma unroll
-        for (int c = 0; c < S; ++c) {
-          out[r][c] -= a * nb.R[k][c];                      // A' = -Abar_i Abar_{i-h}
-          Bd[r][c] -= a * nb.R[k][S + c];                   // B' -= Abar_i Cbar_{i-h}
-        }
-#pragma unroll
-        for (int c = 0; c < NR; ++c) out[r][2 * S + c] -= a * nb.R[k][2 * S + c];
-      }
-  }
-  if (i + h < ne) {
-    nb.load(win, i + h, B, m);
-#pragma unroll
-    for (int r = 0; r < S; ++r)
-#pragma unroll
-      for (int k = 0; k < S; ++k) {
-        const double g = me.R[r][S + k];                    // Cbar_i
-#pragma unroll
-        for (int c = 0; c < S; ++c) {
-          out[r][S + c] -= g * nb.R[k][S + c];              // C' = -Cbar_i Cbar_{i+h}
-          Bd[r][c] -= g * nb.R[k][c];                       // B' -= Cbar_i Abar_{i+h}
-        }
-#pragma unroll
-        for (int c = 0; c < NR; ++c) out[r][2 * S + c] -= g * nb.R[k][2 * S + c];
-      }
-  }
-  if (!gj_solve_pcr<S, 2 * S + NR>(Bd, out) && status) status[m] = 1;
-#pragma unroll
-  for (int r = 0; r < S; ++r)
-#pragma unroll
-    for (int c = 0; c < 2 * S + NR; ++c) me.R[r][c] = out[r][c];
-  me.store(wout, i, B, m);
 }
 
 // non-cyclic: s = Dbar
@@ -266,11 +140,6 @@ __global__ void pcr_cyclic_fold_kernel(const __grid_constant__ sfxm_problem_t P,
     const int64_t q = (P.var_base[o + r] + i * (int64_t)P.var_stride[o + r] + P.var_off[o + r]) * B + m;
     s_out[q] = xv;
   }
-}
-
-static dim3 pcr_block(int64_t B) { return B >= 32 ? dim3(32, 4) : dim3(1, 128); }
-static dim3 pcr_grid(int64_t B, int64_t n, dim3 b) {
-  return dim3((unsigned)((n + b.y - 1) / b.y), (unsigned)((B + b.x - 1) / b.x));
 }
 
 template <int NV, int S, bool CYCLIC>

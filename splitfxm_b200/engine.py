@@ -210,11 +210,18 @@ class Engine:
         P, segs = self.problem(split, split_locs)
         if seg_hi is None:
             seg_hi = len(segs)
+        if self.W == 4:
+            method = "band4"          # 4-cell stencil: two-cell super-blocks + PCR
         if method is None:
             # one thread per member (Thomas) needs thousands of members to fill the GPU; below that, one thread per
             # (cell, member) and log2(nx) passes (parallel cyclic reduction)
             method = "thomas" if self.batch >= 2048 else "pcr"
-        if method == "thomas":
+        if method == "band4":
+            nbytes = self.lib.sfxm_band4_workspace_bytes(ctypes.byref(P))
+            work = self._scratch("band4", nbytes // 8)
+            fn = self.lib.sfxm_block_band4_solve_pcr
+            _lib.count((seg_hi - seg_lo) * (2 + max((self.nx + 1) // 2 - 1, 1).bit_length()))
+        elif method == "thomas":
             nbytes = self.lib.sfxm_solve_workspace_bytes(ctypes.byref(P))
             work = self._scratch("solve", nbytes // 8)
             fn = self.lib.sfxm_block_tridiag_solve

@@ -233,8 +233,6 @@ class Simulation:
             self._check_split(nv, split, split_locs, "Split location must be specified in this case",
                               "Split locations must be between 0 and nv-1")
         eng = self._engine()
-        if eng.W != 3:
-            raise SFXM("steady_state needs a 3-cell stencil (block-tridiagonal Jacobian)")
         y = eng.to_device(x0)
         drv = NewtonDriver(eng, split, split_locs, dt0, dtmax, armijo, ext_bounds)
         maxiter = self._ss.get("maxiter", math.inf) if isinstance(self._ss, dict) else math.inf

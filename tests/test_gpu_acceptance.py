@@ -109,7 +109,7 @@ def test_simulation_api_smoke():
 
 def test_error_paths_on_the_device_path():
     """Inputs the kernels cannot take raise SFXM (never a silent fallback): meshes smaller than twice the stencil,
-    UPWIND with a non-diagonal flux Jacobian, Newton on a 4-cell stencil, a state of the wrong length."""
+    UPWIND with a non-diagonal flux Jacobian, Newton on an odd periodic mesh with a 4-cell stencil, wrong lengths."""
     import splitfxm_b200 as sf
     from splitfxm_b200.models.advection_diffusion import AdvectionDiffusion
     from splitfxm_b200.models.euler1d import Euler1DConservative
@@ -125,10 +125,12 @@ def test_error_paths_on_the_device_path():
     s = sf.Simulation(d, Euler1DConservative(1.4, "FVM"), {}, {n: per for n in names}, sf.FVSchemes.UPWIND)
     with pytest.raises(sf.SFXM):
         s.get_residuals_from_list(d.listify_interior(False))
-    d = sf.Domain.from_size(30, 1, 2, ["u"])
+    d = sf.Domain.from_size(31, 1, 2, ["u"])       # 4-cell stencil + periodic variable needs an even mesh
     s = sf.Simulation(d, AdvectionDiffusion(0.2, 0.001, "FDM"), {"u": "sine"}, {"u": per}, sf.FDSchemes.RIGHT_BIAS)
     with pytest.raises(sf.SFXM):
-        s.steady_state()
+        s.steady_state(dt0=0.1)
+    d = sf.Domain.from_size(30, 1, 2, ["u"])
+    s = sf.Simulation(d, AdvectionDiffusion(0.2, 0.001, "FDM"), {"u": "sine"}, {"u": per}, sf.FDSchemes.RIGHT_BIAS)
     with pytest.raises(sf.SFXM):
         s.get_residuals_from_list(np.zeros(29))
     with pytest.raises(sf.SFXM):

@@ -146,3 +146,49 @@ def test_pcr_large_single_mesh(bcs_kind):
         Ax += np.einsum("irc,ic->ir", Jh[:, dslot], xn)
     f = r.cpu().numpy()[:, 0].reshape(nx, 3)
     assert np.max(np.abs(Ax + f)) <= 1e-9 * max(1.0, np.max(np.abs(f)))
+
+
+@pytest.mark.parametrize("name,split,locs", [
+    ("ad_fdm_rbias_nx40_mixedbc", False, None),       # nb (1, 2), w left-periodic, 3x3 blocks -> 6x6 super-blocks
+    ("ad_fdm_rbias_nx40_mixedbc", True, [1, 2]),
+    ("ad_fdm_rbias_nx40_nb21", False, None),          # nb (2, 1)
+    ("ad_fdm_rbias_nx250_split1", True, [1]),         # README BCs: u periodic on both sides
+])
+def test_band4_solve_right_bias(name, split, locs):
+    import torch
+    from oracle import core
+    z = load(name)
+    s, d, m = product_simulation(z)
+    eng = s._engine()
+    y_host = core.to_flat(core.to_block(z["x0"], m["nx"], len(m["comps"]), m["split"], m["locs"]), split, locs)
+    y = eng.to_device(y_host)
+    r = torch.empty_like(y)
+    J = eng.jacobian(y, split, locs, r0=r)
+    shift = torch.full((1,), -50.0, dtype=torch.float64, device=y.device)
+    sol = torch.zeros_like(y)
+    status = torch.zeros(1, dtype=torch.int32, device=y.device)
+    eng.solve(J, r, sol, split, locs, shift=shift, status=status)
+    A = _dense_from_banded(eng, J.cpu().numpy()[..., 0], split, locs) - 50.0 * np.eye(eng.n)
+    ref = np.linalg.solve(A, -r.cpu().numpy()[:, 0])
+    assert int(status[0]) == 0
+    assert rel_err(sol.cpu().numpy()[:, 0], ref) < 1e-9 * max(1.0, np.linalg.cond(A) * 1e-6)
+
+
+def test_steady_state_right_bias_matches_oracle_spec():
+    """Newton with the 4-cell RIGHT_BIAS stencil (odd mesh, no periodic variable): same iterates and iteration count
+    as the specification in oracle/newton.py."""
+    import splitfxm_b200 as sf
+    from splitfxm_b200.models.advection_diffusion import AdvectionDiffusion
+    from oracle import core, newton as onewton
+    comps = ["u", "v"]
+    bcs = {"u": {"left": {"dirichlet": 1.0}, "right": {"dirichlet": 0.0}},
+           "v": {"left": {"dirichlet": 3}, "right": {"neumann": 0.0}}}
+    d = sf.Domain.from_size(41, 1, 2, comps)
+    s = sf.Simulation(d, AdvectionDiffusion(0.2, 0.05, "FDM"), {"u": "gaussian", "v": "rarefaction"}, bcs, sf.FDSchemes.RIGHT_BIAS)
+    P = core.Problem(core.AdvectionDiffusion(0.2, 0.05), "FDM", "RIGHT_BIAS", np.array(d.positions(interior=True)), 1, 2, bcs, comps)
+    x0 = d.listify_interior(True, [1])
+    xf, _, it_ref = onewton.split_newton(lambda u: P.residual(u, True, [1]), lambda u: P.jacobian_matrix(u, True, [1]), x0,
+                                         [41], sparse=True, dt0=0.05, dtmax=10.0)
+    it = s.steady_state(split=True, split_locs=[1], dt0=0.05, dtmax=10.0)
+    assert it == it_ref
+    assert rel_err(d.listify_interior(True, [1]), xf) < 1e-9
