@@ -30,6 +30,86 @@ def sod_state(x):
     return np.stack([np.where(left, 1.0, 0.125), np.zeros_like(x), np.where(left, 2.5, 0.25)], axis=1)
 
 
+AD_COMPS = ["u", "v", "w"]
+AD_BCS = {"u": {"left": {"dirichlet": 1.0}, "right": {"dirichlet": 0.0}},
+          "v": {"left": {"dirichlet": 3}, "right": {"dirichlet": 4}},
+          "w": {"left": {"dirichlet": 2}, "right": {"neumann": 0.0}}}
+AD_ICS = {"u": "gaussian", "v": "rarefaction", "w": "tophat"}
+
+
+def newton_on_slabs(args, rank, world, dev):
+    """Split-Newton on a slab-decomposed advection-diffusion mesh: parity against the single-GPU
+    Simulation.steady_state on a small mesh, then the time per Newton iteration at --newton-nx.  Nothing raises on
+    one rank only (the others would wait in the next collective): the outcome is reported."""
+    import torch
+    import torch.distributed as dist
+    import splitfxm_b200 as sf
+    from splitfxm_b200.engine import flat_index_table, split_segments
+    from splitfxm_b200.distributed import SlabSimulation
+    from splitfxm_b200.models.advection_diffusion import AdvectionDiffusion
+    from splitfxm_b200.spike import DistComm, ThreadGroup
+    comm = DistComm() if world > 1 else ThreadGroup(1).comm(0)
+
+    def to_flat(block, split, locs):          # [nx, nv] -> the flat (split-major) vector, simulation.py:137-143
+        out = np.empty(block.size)
+        out[flat_index_table(block.shape[0], block.shape[1], split_segments(block.shape[1], split, locs))] = block
+        return out
+
+    def to_block(flat, nx, nv, split, locs):
+        return np.asarray(flat)[flat_index_table(nx, nv, split_segments(nv, split, locs))]
+    scheme = sf.FVSchemes.LAX_FRIEDRICHS
+
+    def setup(nx):
+        d = sf.Domain.from_size(nx, 1, 1, AD_COMPS)
+        sim = sf.Simulation(d, AdvectionDiffusion(0.2, 0.05, "FVM"), AD_ICS, AD_BCS, scheme)
+        xg = np.array(d.positions(interior=True))
+        slab = SlabSimulation(xg, AD_COMPS, "ad", {"c": 0.2, "nu": 0.05}, AD_BCS, scheme, "FVM", rank, world, device=dev)
+        return d, sim, slab
+
+    out = {}
+    # -- parity on a small mesh
+    nx, split, locs = 3000, True, [1, 2]
+    d, sim, slab = setup(nx)
+    U0 = d.values(interior=True).copy()
+    y = slab.eng.to_device(to_flat(U0[slab.lo:slab.hi], split, locs))
+    its = slab.steady_state(y, split, locs, comm=comm)
+    mine = (slab.lo, slab.hi, int(its[0]), to_block(y.cpu().numpy()[:, 0], slab.hi - slab.lo, 3, split, locs))
+    parts = [mine]
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+    if rank == 0:
+        it_ref = sim.steady_state(split=split, split_locs=locs)
+        ref = d.values(interior=True)
+        U = np.concatenate([p[3] for p in parts])
+        err = float(np.max(np.abs(U - ref)) / np.max(np.abs(ref)))
+        out["parity"] = {"nx": nx, "iterations": [p[2] for p in parts], "iterations_single_gpu": it_ref,
+                         "max_rel_diff_vs_single_gpu": err,
+                         "ok": bool(err < 1e-10 and all(p[2] == it_ref for p in parts))}
+    # -- timing
+    nx = args.newton_nx
+    d, sim, slab = setup(nx)
+    y0 = slab.eng.to_device(to_flat(d.values(interior=True)[slab.lo:slab.hi], False, None))
+    for timed in (False, True):
+        y = y0.clone()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        its = slab.steady_state(y, False, None, comm=comm)
+        t1.record()
+        torch.cuda.synchronize()
+    ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    rmax = comm.all_reduce_sum(slab.eng.sumsq(slab.residual(y)))
+    out["timing"] = {"nx": nx, "n_gpus": world, "iterations": int(its[0]), "ms_total": float(ms[0]),
+                     "ms_per_newton_iteration": float(ms[0]) / max(int(its[0]), 1),
+                     "residual_l2_after": float(torch.sqrt(rmax)[0])}
+    return out
+
+
 def main():
     if os.environ.get("SFXM_HANG_DUMP"):          # debugging aid: print where every rank is after N seconds and exit
         import faulthandler
@@ -41,6 +121,9 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--fused", action="store_true", help="halo exchange fused into the update kernel (peer memory)")
     ap.add_argument("--rk45-check", action="store_true", help="also check adaptive RK45 on slabs against one GPU")
+    ap.add_argument("--newton", action="store_true",
+                    help="also run Newton on slabs (partitioned block solve): parity check + timing at --newton-nx")
+    ap.add_argument("--newton-nx", type=int, default=1_000_000)
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -108,6 +191,10 @@ def main():
             # the slabs sum the error norm in a different order than one GPU does: step sizes agree to round-off only
             rk_check = {"nfev": nfev, "max_rel_diff_vs_single_gpu": err, "ok": bool(err < 1e-9)}
 
+    newton = None
+    if args.newton:
+        newton = newton_on_slabs(args, rank, world, dev)
+
     x, slab, y = make(args.nx)
     dt = 0.4 * (x[1] - x[0]) / 2.2
     other = torch.empty_like(y)
@@ -151,7 +238,8 @@ def main():
                                       f"slab-decomposed x{world} with " + ("halo exchange fused into the update kernel (peer stores over NVLink)" if (args.fused and world > 1) else "NCCL halo exchange"),
                           "n_gpus": world, "steps": args.steps, "ms_per_step": per_step, "cell_updates_per_s": cells_s,
                           "GBps_per_gpu": (args.nx / world) * 56 / (per_step * 1e-3) / 1e9, "scaling": "strong",
-                          "parity_vs_single_gpu": check, "rk45_on_slabs": rk_check, "finite": finite}), flush=True)
+                          "parity_vs_single_gpu": check, "rk45_on_slabs": rk_check, "newton_on_slabs": newton,
+                          "finite": finite}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

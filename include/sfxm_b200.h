@@ -146,6 +146,24 @@ int sfxm_block_band4_solve_pcr(const sfxm_problem_t *prob, const double *J, cons
                                const int32_t *active, int32_t seg_lo, int32_t seg_hi, double *s, double *work,
                                int32_t *status, void *stream);
 
+/* ---- Newton linear solve of ONE mesh decomposed into slabs, one slab per GPU (no reference equivalent: the
+ * reference solves the whole mesh in one process, simulation.py:515-523).  J is this slab's block-tridiagonal
+ * Jacobian whose wrap slots (cell 0, slot 0) / (cell nx-1, slot 2) hold the coupling blocks to the neighbouring
+ * slabs (sfxm_jacobian fills them for SFXM_BC_HALO ghosts).
+ * reduce: PCR with 1 + 2 s right-hand sides; leaves x_i = q_i - V_i xl_prev - W_i xf_next in `work` and copies the
+ *         first/last rows out: iface[((e*s + r)*(1+2s) + c)*batch + m], e = 0 first cell, 1 last cell.
+ * (all-gather iface, solve the 2 G s interface system on every rank: splitfxm_b200/spike.py)
+ * fold:   s = q - V xl_prev - W xf_next with nbr[(e*s + c)*batch + m], e = 0 the left neighbour's last block
+ *         unknown, e = 1 the right neighbour's first.  One segment per call; W must be 3. ---- */
+int64_t sfxm_spike_workspace_bytes(const sfxm_problem_t *prob);
+int sfxm_spike_reduce(const sfxm_problem_t *prob, const double *J, const double *f, const double *shift, int32_t seg,
+                      double *work, double *iface, int32_t *status, void *stream);
+int sfxm_spike_fold(const sfxm_problem_t *prob, int32_t seg, double *work, const double *nbr, const int32_t *active,
+                    double *s, void *stream);
+/* The interface system itself: aug[(m*n + r)*(n+1) + c] = [M | rhs] per member (n = 2 G s <= 76), z[m*n + r] the
+ * solution; Gaussian elimination with partial pivoting, one CTA per member.  status[m] = 1 on a zero pivot. */
+int sfxm_dense_solve(const double *aug, int32_t n, int64_t batch, double *z, int32_t *status, void *stream);
+
 /* Per-member sums of squares over a flat-index range [lo, hi): out[m] = sum v[q*batch+m]^2, accumulated in a
  * fixed order (deterministic).  work: sfxm_sumsq_workspace_bytes(hi - lo, batch).  The norms of
  * splitnewton's convergence criterion. */

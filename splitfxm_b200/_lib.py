@@ -58,6 +58,10 @@ SIGNATURES = {
     "sfxm_block_tridiag_solve_pcr": (ctypes.c_int, [_PP, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_band4_workspace_bytes": (c_i64, [_PP]),
     "sfxm_block_band4_solve_pcr": (ctypes.c_int, [_PP, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_spike_workspace_bytes": (c_i64, [_PP]),
+    "sfxm_spike_reduce": (ctypes.c_int, [_PP, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_spike_fold": (ctypes.c_int, [_PP, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_dense_solve": (ctypes.c_int, [c_vp, c_i32, c_i64, c_vp, c_vp, c_vp]),
     "sfxm_sumsq_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "sfxm_sumsq": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "sfxm_axpy_masked": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),

@@ -248,6 +248,26 @@ class SlabSimulation:
         out = stepper.integrate(y, t_diff)
         return out, stepper.nfev
 
+    # -- Newton / Split-Newton on the decomposed mesh -----------------------------------------------------
+    def steady_state(self, y, split=False, split_locs=None, dt0=0.0, dtmax=1.0, armijo=False, bounds=None,
+                     maxiter=float("inf"), comm=None):
+        """Simulation.steady_state (simulation.py:474-526) for this rank's slab, in place on y [n_local, batch]:
+        the ordinary NewtonDriver over spike.SlabNewtonEngine (halo exchange before every residual / Jacobian,
+        partitioned block solve with one small all-gather, all-reduced norms), so all ranks iterate in lock-step.
+        bounds: [lower, upper] per variable, as in the reference.  Returns the iteration count(s) [batch]."""
+        from .newton import NewtonDriver
+        from .spike import DistComm, SlabNewtonEngine
+        if comm is None:
+            comm = DistComm()
+        ext = None
+        if bounds is not None:
+            _, segs = self.eng.problem(split, split_locs)
+            nx = self.eng.nx
+            ext = [np.concatenate([np.tile(np.asarray(b[o:o + s], dtype=np.float64), nx) for (o, s) in segs])
+                   for b in bounds]                                         # extend_bounds, simulation.py:204-264
+        drv = NewtonDriver(SlabNewtonEngine(self, comm), split, split_locs, dt0, dtmax, armijo, ext)
+        return drv.run(y, maxiter)
+
     # -- fused halo exchange over peer-mapped memory (NVLink) ---------------------------------------------
     def enable_peer_halos(self, group=None):
         """Put the halo buffers in symmetric memory and map the neighbours' buffers (one process per GPU, NCCL group

@@ -43,13 +43,16 @@ class NewtonDriver:
         self.yt = torch.empty((eng.n, B), dtype=torch.float64, device=dev) if armijo else None
         self.status = torch.zeros(B, dtype=torch.int32, device=dev)
         self.all_active = torch.ones(B, dtype=torch.bool, device=dev)
+        # a slab-decomposed mesh (spike.SlabNewtonEngine) reduces the host-side decisions over the ranks
+        self._reduce_min = getattr(eng, "reduce_min", lambda t: t)
+        self._reduce_any = getattr(eng, "reduce_any", lambda flag: flag)
 
     def rows(self, k):
         o, s = self.segs[k]
         return o * self.eng.nx, (o + s) * self.eng.nx
 
     def check_initial(self, y):
-        if self.lb is not None and bool(((y < self.lb) | (y > self.ub)).any()):
+        if self.lb is not None and self._reduce_any(bool(((y < self.lb) | (y > self.ub)).any())):
             raise ValueError("Initial guess is outside the bounds")
 
     # -- Newton on ONE segment (all segments when unsplit) -------------------------------------------
@@ -110,7 +113,7 @@ class NewtonDriver:
         one = torch.ones((), dtype=torch.float64, device=y.device)
         up = torch.where(xn > ub, self.bound_fac * (ub - x) / s, one)
         dn = torch.where(xn < lb, self.bound_fac * (lb - x) / s, one)
-        return torch.minimum(up.min(dim=0).values, dn.min(dim=0).values).clamp(max=1.0)
+        return self._reduce_min(torch.minimum(up.min(dim=0).values, dn.min(dim=0).values).clamp(max=1.0))
 
     # -- Split-Newton over segments k0 .. last --------------------------------------------------------
     def split_newton(self, y, k0, maxiter, parent):
