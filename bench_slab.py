@@ -110,6 +110,57 @@ def newton_on_slabs(args, rank, world, dev):
     return out
 
 
+def amr_on_slabs(rank, world, dev, n=1_000_000):
+    """Refiner on a slab-decomposed mesh: three fronts on n cells, pruning on; the gathered result
+    must equal the single-GPU Refiner's mesh bit for bit.  Reported, never raised on one rank only."""
+    import contextlib
+    import io
+    import torch
+    import torch.distributed as dist
+    from splitfxm_b200.distributed import slab_bounds
+    from splitfxm_b200.refine import Refiner
+    from splitfxm_b200.slab_refine import SlabRefiner
+    from splitfxm_b200.spike import DistComm, ThreadGroup
+    comm = DistComm() if world > 1 else ThreadGroup(1).comm(0)
+    x = np.linspace(0.0, 1.0, n)
+    U = np.stack([np.tanh(4000 * (x - 0.3)), np.where(x < 0.5, 1.0, 0.125) + 0.05 * np.sin(40 * x),
+                  np.exp(-((x - 0.7) / 0.0005) ** 2)], axis=1)
+    crit = (2.0, 0.05, 0.05, 0.01)
+    lo, hi = slab_bounds(n, world, rank)
+    r = SlabRefiner()
+    r.set_criteria(*crit)
+    r.set_max_points(4 * n)
+    xd, Ud = torch.from_numpy(x[lo:hi].copy()).to(dev), torch.from_numpy(U[lo:hi].copy()).to(dev)
+    for timed in (False, True):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        x_new, U_new, lo_new, total = r.refine_slab(xd, Ud, lo, n, comm, rebalance=True, report=False)
+        t1.record()
+        torch.cuda.synchronize()
+    ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    mine = (lo_new, x_new.cpu().numpy(), U_new.cpu().numpy())
+    parts = [mine]
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+    if rank != 0:
+        return None
+    parts.sort(key=lambda p: p[0])
+    ref = Refiner()
+    ref.set_criteria(*crit)
+    ref.set_max_points(4 * n)
+    x_ref, U_ref, _ = ref.refine_arrays(x, U, want_flags=False)
+    same = bool(np.array_equal(np.concatenate([p[1] for p in parts]), x_ref)
+                and np.array_equal(np.concatenate([p[2] for p in parts]), U_ref))
+    return {"cells_before": n, "cells_after": int(total), "slab_sizes_after": [int(p[1].shape[0]) for p in parts],
+            "ms_refine_incl_rebalance": float(ms[0]), "identical_to_single_gpu": same}
+
+
 def main():
     if os.environ.get("SFXM_HANG_DUMP"):          # debugging aid: print where every rank is after N seconds and exit
         import faulthandler
@@ -124,6 +175,7 @@ def main():
     ap.add_argument("--newton", action="store_true",
                     help="also run Newton on slabs (partitioned block solve): parity check + timing at --newton-nx")
     ap.add_argument("--newton-nx", type=int, default=1_000_000)
+    ap.add_argument("--amr", action="store_true", help="also refine a slab-decomposed mesh and compare with one GPU")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -191,6 +243,7 @@ def main():
             # the slabs sum the error norm in a different order than one GPU does: step sizes agree to round-off only
             rk_check = {"nfev": nfev, "max_rel_diff_vs_single_gpu": err, "ok": bool(err < 1e-9)}
 
+    amr = amr_on_slabs(rank, world, dev) if args.amr else None
     newton = None
     if args.newton:
         newton = newton_on_slabs(args, rank, world, dev)
@@ -238,7 +291,7 @@ def main():
                                       f"slab-decomposed x{world} with " + ("halo exchange fused into the update kernel (peer stores over NVLink)" if (args.fused and world > 1) else "NCCL halo exchange"),
                           "n_gpus": world, "steps": args.steps, "ms_per_step": per_step, "cell_updates_per_s": cells_s,
                           "GBps_per_gpu": (args.nx / world) * 56 / (per_step * 1e-3) / 1e9, "scaling": "strong",
-                          "parity_vs_single_gpu": check, "rk45_on_slabs": rk_check, "newton_on_slabs": newton,
+                          "parity_vs_single_gpu": check, "rk45_on_slabs": rk_check, "newton_on_slabs": newton, "amr_on_slabs": amr,
                           "finite": finite}), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -208,6 +208,29 @@ int sfxm_refine_flags(const void *work, int64_t n, uint8_t *loc_out, uint8_t *ke
 int sfxm_refine_apply(const double *x, const double *U, int64_t n, int32_t nv, const void *work, double *x_out,
                       double *U_out, void *stream);
 
+/* The same refinement on a WINDOW of a slab-decomposed mesh (AMR over several GPUs).  x[ne], U[ne * nv] hold
+ * the global cells g0 .. g0 + ne - 1 of a mesh of ng cells; [own_lo, own_hi) (window indices) are this rank's cells, the
+ * rest is overlap copied from the neighbours (6 cells per side, fewer at a domain end).  Phases, with the two global
+ * exchanges between them done by the caller:
+ *   stats    -> stats_dev[16] = vmin[4] | vmax[4] | smin[4] | smax[4] over the own cells   (all-reduce min / max)
+ *   mark     -> flags; last_run_dev[0] = global index of the last deletion-run start so far, -1 if none (all-gather;
+ *               carry = max over the ranks before this one)
+ *   finalize -> the adjacent-deletion rule with `carry_run_start`, output slots, counts_dev[3] for the own cells
+ *   apply    -> x_out / U_out: this rank's refined cells (midpoints after own cells included)
+ *   flags    -> decision flags of the own cells.   `work`: sfxm_refine_workspace_bytes(ne). */
+int sfxm_refine_window_stats(const double *x, const double *U, int64_t ne, int32_t nv, int64_t g0, int64_t ng,
+                             int64_t own_lo, int64_t own_hi, void *work, double *stats_dev, void *stream);
+int sfxm_refine_window_mark(const double *x, const double *U, int64_t ne, int32_t nv, int64_t g0, int64_t ng,
+                            int64_t own_lo, int64_t own_hi, double ratio, double slope, double curve, double prune,
+                            double min_range, double min_grid, const double *stats_dev, void *work,
+                            int64_t *last_run_dev, void *stream);
+int sfxm_refine_window_finalize(int64_t ne, int64_t g0, int64_t ng, int64_t own_lo, int64_t own_hi,
+                                int64_t carry_run_start, void *work, int64_t *counts_dev, void *stream);
+int sfxm_refine_window_apply(const double *x, const double *U, int64_t ne, int32_t nv, int64_t g0, int64_t ng,
+                             int64_t own_lo, int64_t own_hi, const void *work, double *x_out, double *U_out, void *stream);
+int sfxm_refine_window_flags(const void *work, int64_t ne, int64_t own_lo, int64_t own_hi, uint8_t *loc_out,
+                             uint8_t *keep_out, uint8_t *gridpt_out, int32_t *comp_out, void *stream);
+
 /* Register the launcher of a user-model plugin (built by splitfxm_b200/custom.py from the user's device functor:
  * the same residual/Jacobian kernel templates instantiated for that functor).  launch_fn has the signature
  * int (*)(const void *launch) and is called by sfxm_residual / sfxm_jacobian when prob->model is

@@ -75,6 +75,12 @@ SIGNATURES = {
     "sfxm_refine_mark": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_f64, c_f64, c_f64, c_f64, c_f64, c_f64, c_vp, c_vp, c_vp]),
     "sfxm_refine_flags": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_refine_apply": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_refine_window_stats": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "sfxm_refine_window_mark": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, c_i64, c_i64, c_f64, c_f64, c_f64,
+                                               c_f64, c_f64, c_f64, c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_refine_window_finalize": (ctypes.c_int, [c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "sfxm_refine_window_apply": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_refine_window_flags": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_register_user_model": (ctypes.c_int, [c_i32, c_vp]),
     "sfxm_halo_signal": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp]),
     "sfxm_halo_wait": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),

@@ -13,6 +13,13 @@
 // strictly between its two parents, so the sort is this merge).
 //
 // All kernels stream x and U once: HBM-bound (~96 B per cell over the mark and apply passes).
+//
+// Slab-decomposed meshes: every kernel works on a WINDOW of the global mesh - `ne` cells starting at
+// global index g0, of which [own_lo, own_hi) are this rank's own and the rest are overlap copied from the neighbours.
+// A rule evaluated at cell j reads cells j-2 .. j+2 and sets flags on j-2 .. j+2, so six overlap cells per side make
+// the flags of every own cell (and the deletion state of the cell before the first own one) complete.  Global
+// quantities cross ranks between the phases: the min/max statistics (one 16-double all-reduce) and the start of the
+// deletion run that reaches into the slab (one int64 all-gather).  One mesh on one GPU is the window g0 = 0, ne = n.
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
 #include <cstdint>
@@ -22,6 +29,10 @@
 namespace sfxm {
 
 static constexpr double kUlp = 2.220446049250313e-16;   // math.ulp(1.0), refine.py:7
+
+struct Window {   // a rank's view of the global mesh: array index t <-> global cell g0 + t
+  int64_t ne, g0, ng, own_lo, own_hi;
+};
 
 struct Stats {   // per variable: min/max of values and of slopes (refine.py:146-153)
   double vmin[SFXM_MAX_NV], vmax[SFXM_MAX_NV], smin[SFXM_MAX_NV], smax[SFXM_MAX_NV];
@@ -39,12 +50,12 @@ __device__ __forceinline__ double warp_max(double v) {
 // stage 1: per-block min/max of v_j and s_j = (v_{j+1} - v_j) / (z_{j+1} - z_j); stage 2 (one block) folds them
 template <int NV>
 __global__ void __launch_bounds__(256)
-amr_stats_kernel(const double *__restrict__ z, const double *__restrict__ U, int64_t n, double *__restrict__ part) {
+amr_stats_kernel(const double *__restrict__ z, const double *__restrict__ U, const Window wd, double *__restrict__ part) {
   double lo_v[NV], hi_v[NV], lo_s[NV], hi_s[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) { lo_v[i] = lo_s[i] = INFINITY; hi_v[i] = hi_s[i] = -INFINITY; }
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
-    const bool has_s = j + 1 < n;
+  for (int64_t j = wd.own_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < wd.own_hi; j += (int64_t)gridDim.x * blockDim.x) {
+    const bool has_s = wd.g0 + j + 1 < wd.ng;       // the slope of interval j belongs to the rank that owns cell j
     const double dz = has_s ? __ldg(z + j + 1) - __ldg(z + j) : 1.0;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -96,120 +107,137 @@ struct Criteria {
 // gridpt[j] = the grid-ratio rule named "point j" (refine.py:203,211)
 template <int NV>
 __global__ void __launch_bounds__(256)
-amr_mark_kernel(const double *__restrict__ z, const double *__restrict__ U, int64_t n, const Criteria cr,
+amr_mark_kernel(const double *__restrict__ z, const double *__restrict__ U, const Window wd, const Criteria cr,
                 const Stats *__restrict__ st, uint8_t *__restrict__ keep1, uint8_t *__restrict__ visited,
                 uint8_t *__restrict__ loc, int32_t *__restrict__ comp, uint8_t *__restrict__ gridpt) {
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  if (j == 0 || j == n - 1) keep1[j] = 1;                              // refine.py:120-121
-  const double zj = __ldg(z + j);
-  const double dzj = j + 1 < n ? __ldg(z + j + 1) - zj : 0.0;          // dz[j]
-  const double dzj1 = j + 2 < n ? __ldg(z + j + 2) - __ldg(z + j + 1) : 0.0;   // dz[j+1]
+  // t: index into the window arrays; j: the global cell index every rule of refine.py is written in
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= wd.ne) return;
+  const int64_t j = wd.g0 + t, n = wd.ng;
+  // cells of the overlap whose own stencil leaves the window are someone else's to evaluate
+#pragma unroll
+  for (int o = -2; o <= 2; ++o)
+    if (j + o >= 0 && j + o < n && (t + o < 0 || t + o >= wd.ne)) return;
+  if (j == 0 || j == n - 1) keep1[t] = 1;                              // refine.py:120-121
+  const bool own = t >= wd.own_lo && t < wd.own_hi;                    // only own cells report the component
+  const double zj = __ldg(z + t);
+  const double dzj = j + 1 < n ? __ldg(z + t + 1) - zj : 0.0;          // dz[j]
+  const double dzj1 = j + 2 < n ? __ldg(z + t + 2) - __ldg(z + t + 1) : 0.0;   // dz[j+1]
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const double vmin = st->vmin[i], vmax = st->vmax[i], smin = st->smin[i], smax = st->smax[i];
     const double aa = fmax(fabs(vmin), fabs(vmax));
     const double ss = fmax(fabs(smin), fabs(smax));
-    const double v0 = __ldg(U + j * NV + i);
-    const double v1 = j + 1 < n ? __ldg(U + (j + 1) * NV + i) : 0.0;
+    const double v0 = __ldg(U + t * NV + i);
+    const double v1 = j + 1 < n ? __ldg(U + (t + 1) * NV + i) : 0.0;
     // slope criterion on interval j (refine.py:159-173)
     if (j + 1 < n && (vmax - vmin) > cr.min_range * aa) {
       const double dmax = cr.slope * (vmax - vmin) + kUlp;
       const double r = fabs(v1 - v0) / dmax;
-      if (r > 1.0 && dzj >= 2 * cr.min_grid) { loc[j] = 1; comp[i] = 1; }
-      if (r >= cr.prune) { keep1[j] = 1; keep1[j + 1] = 1; }
-      else visited[j] = 1;
+      if (r > 1.0 && dzj >= 2 * cr.min_grid) { loc[t] = 1; if (own) comp[i] = 1; }
+      if (r >= cr.prune) { keep1[t] = 1; keep1[t + 1] = 1; }
+      else visited[t] = 1;
     }
     // curvature criterion on the pair of intervals (j, j+1) (refine.py:179-197)
     if (j + 2 < n && (smax - smin) > cr.min_range * ss) {
-      const double v2 = __ldg(U + (j + 2) * NV + i);
+      const double v2 = __ldg(U + (t + 2) * NV + i);
       const double s0 = (v1 - v0) / dzj;
       const double s1 = (v2 - v1) / dzj1;
       const double dmax = cr.curve * (smax - smin);
       const double r = fabs(s1 - s0) / (dmax + (kUlp / dzj));
-      if (r > 1.0 && dzj >= 2 * cr.min_grid && dzj1 >= 2 * cr.min_grid) { comp[i] = 1; loc[j] = 1; loc[j + 1] = 1; }
-      if (r >= cr.prune) keep1[j + 1] = 1;
-      else visited[j + 1] = 1;
+      if (r > 1.0 && dzj >= 2 * cr.min_grid && dzj1 >= 2 * cr.min_grid) { if (own) comp[i] = 1; loc[t] = 1; loc[t + 1] = 1; }
+      if (r >= cr.prune) keep1[t + 1] = 1;
+      else visited[t + 1] = 1;
     }
   }
   // grid-ratio rules (refine.py:200-227), j = 1 .. n-2
   if (j >= 1 && j <= n - 2) {
-    const double dzm1 = zj - __ldg(z + j - 1);                         // dz[j-1]
+    const double dzm1 = zj - __ldg(z + t - 1);                         // dz[j-1]
     if (dzj > cr.ratio * dzm1) {
-      loc[j] = 1; gridpt[j] = 1;
-      keep1[j - 1] = 1; keep1[j] = 1; keep1[j + 1] = 1;
-      if (j + 2 < n) keep1[j + 2] = 1;
+      loc[t] = 1; gridpt[t] = 1;
+      keep1[t - 1] = 1; keep1[t] = 1; keep1[t + 1] = 1;
+      if (j + 2 < n) keep1[t + 2] = 1;
     }
     if (dzj < dzm1 / cr.ratio) {
-      loc[j - 1] = 1; gridpt[j - 1] = 1;
-      if (j >= 2) keep1[j - 2] = 1;
-      keep1[j - 1] = 1; keep1[j] = 1; keep1[j + 1] = 1;
+      loc[t - 1] = 1; gridpt[t - 1] = 1;
+      if (j >= 2) keep1[t - 2] = 1;
+      keep1[t - 1] = 1; keep1[t] = 1; keep1[t + 1] = 1;
     }
-    const double span = __ldg(z + j + 1) - __ldg(z + j - 1);
-    if (j > 1 && span > cr.ratio * (__ldg(z + j - 1) - __ldg(z + j - 2))) keep1[j] = 1;
-    if (j < n - 2 && span > cr.ratio * dzj1) keep1[j] = 1;
+    const double span = __ldg(z + t + 1) - __ldg(z + t - 1);
+    if (j > 1 && span > cr.ratio * (__ldg(z + t - 1) - __ldg(z + t - 2))) keep1[t] = 1;
+    if (j < n - 2 && span > cr.ratio * dzj1) keep1[t] = 1;
   }
 }
 
-// start[j] = j if j begins a maximal run of deletions, else -1
-__global__ void amr_run_start_kernel(const uint8_t *__restrict__ keep1, const uint8_t *__restrict__ visited, int64_t n,
+// start[t] = global index of cell t if it begins a maximal run of deletions, else -1
+__global__ void amr_run_start_kernel(const uint8_t *__restrict__ keep1, const uint8_t *__restrict__ visited, const Window wd,
                                      int64_t *__restrict__ start) {
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const bool del = visited[j] && !keep1[j];
-  const bool prev = j > 0 && visited[j - 1] && !keep1[j - 1];
-  start[j] = (del && !prev) ? j : -1;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= wd.ne) return;
+  const bool del = visited[t] && !keep1[t];
+  const bool prev = t > 0 && visited[t - 1] && !keep1[t - 1];
+  start[t] = (del && !prev) ? wd.g0 + t : -1;
 }
 
 struct MaxOp {
   __device__ __forceinline__ int64_t operator()(int64_t a, int64_t b) const { return a > b ? a : b; }
 };
 
-// final flags: keepf[j] = 0 only for deletions at even offsets of their run (refine.py:231-233); counts for the scans
+// final flags: keepf[t] = 0 only for deletions at even offsets of their run (refine.py:231-233); counts for the scans.
+// carry: start of the deletion run that reaches this slab from the ranks before it (-1: none / one mesh).
 __global__ void amr_finalize_kernel(const uint8_t *__restrict__ keep1, const uint8_t *__restrict__ visited,
-                                    const int64_t *__restrict__ run_start, const uint8_t *__restrict__ loc, int64_t n,
-                                    uint8_t *__restrict__ keepf, int64_t *__restrict__ kept_cnt, int64_t *__restrict__ ins_cnt) {
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const bool del0 = visited[j] && !keep1[j];
-  const bool del = del0 && (((j - run_start[j]) & 1) == 0);
-  keepf[j] = del ? 0 : 1;
-  kept_cnt[j] = del ? 0 : 1;
-  ins_cnt[j] = (loc[j] && j + 1 < n) ? 1 : 0;
+                                    const int64_t *__restrict__ run_start, const uint8_t *__restrict__ loc, const Window wd,
+                                    int64_t carry, uint8_t *__restrict__ keepf, int64_t *__restrict__ kept_cnt,
+                                    int64_t *__restrict__ ins_cnt) {
+  const int64_t t = wd.own_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= wd.own_hi) return;
+  const int64_t j = wd.g0 + t;
+  const bool del0 = visited[t] && !keep1[t];
+  const int64_t rs = run_start[t] > carry ? run_start[t] : carry;
+  const bool del = del0 && (((j - rs) & 1) == 0);
+  keepf[t] = del ? 0 : 1;
+  kept_cnt[t] = del ? 0 : 1;
+  ins_cnt[t] = (loc[t] && j + 1 < wd.ng) ? 1 : 0;
+}
+
+// last own value of the run-start scan: what the ranks after this one need (the latest run start so far)
+__global__ void amr_last_run_kernel(const int64_t *__restrict__ run_start, const Window wd, int64_t *__restrict__ out) {
+  out[0] = run_start[wd.own_hi - 1];
 }
 
 template <int NV>
-__global__ void amr_apply_kernel(const double *__restrict__ z, const double *__restrict__ U, int64_t n,
+__global__ void amr_apply_kernel(const double *__restrict__ z, const double *__restrict__ U, const Window wd,
                                  const uint8_t *__restrict__ keepf, const uint8_t *__restrict__ loc,
                                  const int64_t *__restrict__ kept_before, const int64_t *__restrict__ ins_before,
                                  double *__restrict__ z_out, double *__restrict__ U_out) {
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const int64_t kb = kept_before[j], ib = ins_before[j];
-  if (keepf[j]) {
+  const int64_t t = wd.own_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= wd.own_hi) return;
+  const int64_t kb = kept_before[t], ib = ins_before[t];
+  const bool ins = loc[t] && wd.g0 + t + 1 < wd.ng;       // the midpoint after an own cell is this rank's
+  if (keepf[t]) {
     const int64_t o = kb + ib;
-    z_out[o] = __ldg(z + j);
+    z_out[o] = __ldg(z + t);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) U_out[o * NV + i] = __ldg(U + j * NV + i);
+    for (int i = 0; i < NV; ++i) U_out[o * NV + i] = __ldg(U + t * NV + i);
   }
-  if (loc[j] && j + 1 < n) {
-    const int64_t o = kb + (keepf[j] ? 1 : 0) + ib;
-    z_out[o] = 0.5 * (__ldg(z + j + 1) + __ldg(z + j));                               // refine.py:268
+  if (ins) {
+    const int64_t o = kb + (keepf[t] ? 1 : 0) + ib;
+    z_out[o] = 0.5 * (__ldg(z + t + 1) + __ldg(z + t));                               // refine.py:268
 #pragma unroll
-    for (int i = 0; i < NV; ++i) U_out[o * NV + i] = 0.5 * (__ldg(U + (j + 1) * NV + i) + __ldg(U + j * NV + i));   // :269
+    for (int i = 0; i < NV; ++i) U_out[o * NV + i] = 0.5 * (__ldg(U + (t + 1) * NV + i) + __ldg(U + t * NV + i));   // :269
   }
 }
 
 __global__ void amr_count_kernel(const int64_t *__restrict__ kept_before, const int64_t *__restrict__ ins_before,
-                                 const uint8_t *__restrict__ keepf, const uint8_t *__restrict__ loc, int64_t n,
+                                 const int64_t *__restrict__ kept_cnt, const int64_t *__restrict__ ins_cnt, const Window wd,
                                  int64_t *__restrict__ counts) {
-  // counts[0] = new size, counts[1] = inserted, counts[2] = deleted
-  const int64_t last = n - 1;
-  const int64_t kept = kept_before[last] + (keepf[last] ? 1 : 0);
-  const int64_t ins = ins_before[last];   // loc[n-1] is never set: points are inserted after j <= n-2 only
+  // counts[0] = new size, counts[1] = inserted, counts[2] = deleted   (own cells)
+  const int64_t last = wd.own_hi - 1;
+  const int64_t kept = kept_before[last] + kept_cnt[last];
+  const int64_t ins = ins_before[last] + ins_cnt[last];
   counts[0] = kept + ins;
   counts[1] = ins;
-  counts[2] = n - kept;
+  counts[2] = (wd.own_hi - wd.own_lo) - kept;
 }
 
 static inline int64_t align256(int64_t b) { return (b + 255) / 256 * 256; }
@@ -247,36 +275,86 @@ static AmrWork amr_layout(int64_t n) {
   return w;
 }
 
+static bool window_ok(const Window &wd) {
+  return wd.ne >= 3 && wd.g0 >= 0 && wd.g0 + wd.ne <= wd.ng && wd.own_lo >= 0 && wd.own_lo < wd.own_hi && wd.own_hi <= wd.ne &&
+         wd.ne <= 2147483647LL;
+}
+
+// phase 1: local min/max of own values and slopes -> stats_dev[16] = vmin[4] | vmax[4] | smin[4] | smax[4]
 template <int NV>
-static int refine_mark_t(const double *z, const double *U, int64_t n, const Criteria &cr, char *work, cudaStream_t st) {
-  const AmrWork w = amr_layout(n);
-  const int threads = 256;
-  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+static int amr_stats_t(const double *z, const double *U, const Window &wd, char *work, double *stats_dev, cudaStream_t st) {
+  const AmrWork w = amr_layout(wd.ne);
+  const int64_t n_own = wd.own_hi - wd.own_lo;
+  const unsigned blocks = (unsigned)((n_own + 255) / 256);
   const int sblocks = (int)(blocks < 1024 ? blocks : 1024);
+  amr_stats_kernel<NV><<<sblocks, 256, 0, st>>>(z, U, wd, (double *)(work + w.off_part));
+  amr_stats_final_kernel<NV><<<1, 32, 0, st>>>((const double *)(work + w.off_part), sblocks, (Stats *)stats_dev);
+  return check_launch("sfxm_refine stats");
+}
+
+// phase 2: flags over the window, run starts, max-scan over the own cells
+template <int NV>
+static int amr_mark_t(const double *z, const double *U, const Window &wd, const Criteria &cr, const double *stats_dev,
+                      char *work, int64_t *last_run_dev, cudaStream_t st) {
+  const AmrWork w = amr_layout(wd.ne);
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((wd.ne + threads - 1) / threads);
+  const int64_t n_own = wd.own_hi - wd.own_lo;
   cudaMemsetAsync(work + w.off_keep1, 0, w.off_comp + align256(SFXM_MAX_NV * 4) - w.off_keep1, st);
-  amr_stats_kernel<NV><<<sblocks, 256, 0, st>>>(z, U, n, (double *)(work + w.off_part));
-  amr_stats_final_kernel<NV><<<1, 32, 0, st>>>((const double *)(work + w.off_part), sblocks, (Stats *)(work + w.off_stats));
-  amr_mark_kernel<NV><<<blocks, threads, 0, st>>>(z, U, n, cr, (const Stats *)(work + w.off_stats),
+  amr_mark_kernel<NV><<<blocks, threads, 0, st>>>(z, U, wd, cr, (const Stats *)stats_dev,
                                                   (uint8_t *)(work + w.off_keep1), (uint8_t *)(work + w.off_visited),
                                                   (uint8_t *)(work + w.off_loc), (int32_t *)(work + w.off_comp),
                                                   (uint8_t *)(work + w.off_gridpt));
   amr_run_start_kernel<<<blocks, threads, 0, st>>>((const uint8_t *)(work + w.off_keep1),
-                                                   (const uint8_t *)(work + w.off_visited), n, (int64_t *)(work + w.off_start));
+                                                   (const uint8_t *)(work + w.off_visited), wd, (int64_t *)(work + w.off_start));
   size_t cb = (size_t)w.cub_bytes;
-  cub::DeviceScan::InclusiveScan((void *)(work + w.off_cub), cb, (const int64_t *)(work + w.off_start),
-                                 (int64_t *)(work + w.off_run), MaxOp(), (int)n, st);
-  amr_finalize_kernel<<<blocks, threads, 0, st>>>((const uint8_t *)(work + w.off_keep1), (const uint8_t *)(work + w.off_visited),
-                                                  (const int64_t *)(work + w.off_run), (const uint8_t *)(work + w.off_loc), n,
-                                                  (uint8_t *)(work + w.off_keepf), (int64_t *)(work + w.off_kcnt),
-                                                  (int64_t *)(work + w.off_icnt));
-  cb = (size_t)w.cub_bytes;
-  cub::DeviceScan::ExclusiveSum((void *)(work + w.off_cub), cb, (const int64_t *)(work + w.off_kcnt),
-                                (int64_t *)(work + w.off_kbef), (int)n, st);
-  cb = (size_t)w.cub_bytes;
-  cub::DeviceScan::ExclusiveSum((void *)(work + w.off_cub), cb, (const int64_t *)(work + w.off_icnt),
-                                (int64_t *)(work + w.off_ibef), (int)n, st);
-  return check_launch("sfxm_refine_mark");
+  cub::DeviceScan::InclusiveScan((void *)(work + w.off_cub), cb, (const int64_t *)(work + w.off_start) + wd.own_lo,
+                                 (int64_t *)(work + w.off_run) + wd.own_lo, MaxOp(), (int)n_own, st);
+  if (last_run_dev) amr_last_run_kernel<<<1, 1, 0, st>>>((const int64_t *)(work + w.off_run), wd, last_run_dev);
+  return check_launch("sfxm_refine mark");
 }
+
+// phase 3: adjacent-deletion rule with the carried-in run start, output slots of the own cells, counts
+static int amr_finalize_t(const Window &wd, int64_t carry, char *work, int64_t *counts_dev, cudaStream_t st) {
+  const AmrWork w = amr_layout(wd.ne);
+  const int threads = 256;
+  const int64_t n_own = wd.own_hi - wd.own_lo;
+  const unsigned blocks = (unsigned)((n_own + threads - 1) / threads);
+  amr_finalize_kernel<<<blocks, threads, 0, st>>>((const uint8_t *)(work + w.off_keep1), (const uint8_t *)(work + w.off_visited),
+                                                  (const int64_t *)(work + w.off_run), (const uint8_t *)(work + w.off_loc), wd,
+                                                  carry, (uint8_t *)(work + w.off_keepf), (int64_t *)(work + w.off_kcnt),
+                                                  (int64_t *)(work + w.off_icnt));
+  size_t cb = (size_t)w.cub_bytes;
+  cub::DeviceScan::ExclusiveSum((void *)(work + w.off_cub), cb, (const int64_t *)(work + w.off_kcnt) + wd.own_lo,
+                                (int64_t *)(work + w.off_kbef) + wd.own_lo, (int)n_own, st);
+  cb = (size_t)w.cub_bytes;
+  cub::DeviceScan::ExclusiveSum((void *)(work + w.off_cub), cb, (const int64_t *)(work + w.off_icnt) + wd.own_lo,
+                                (int64_t *)(work + w.off_ibef) + wd.own_lo, (int)n_own, st);
+  amr_count_kernel<<<1, 1, 0, st>>>((const int64_t *)(work + w.off_kbef), (const int64_t *)(work + w.off_ibef),
+                                    (const int64_t *)(work + w.off_kcnt), (const int64_t *)(work + w.off_icnt), wd, counts_dev);
+  return check_launch("sfxm_refine finalize");
+}
+
+template <int NV>
+static int amr_apply_t(const double *z, const double *U, const Window &wd, const char *wk, double *x_out, double *U_out,
+                       cudaStream_t st) {
+  const AmrWork w = amr_layout(wd.ne);
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((wd.own_hi - wd.own_lo + threads - 1) / threads);
+  amr_apply_kernel<NV><<<blocks, threads, 0, st>>>(z, U, wd, (const uint8_t *)(wk + w.off_keepf),
+                                                   (const uint8_t *)(wk + w.off_loc), (const int64_t *)(wk + w.off_kbef),
+                                                   (const int64_t *)(wk + w.off_ibef), x_out, U_out);
+  return check_launch("sfxm_refine_apply");
+}
+
+#define SFXM_NV_SWITCH(nv, CALL)                                   \
+  switch (nv) {                                                    \
+    case 1: { constexpr int NVV = 1; e = CALL; } break;            \
+    case 2: { constexpr int NVV = 2; e = CALL; } break;            \
+    case 3: { constexpr int NVV = 3; e = CALL; } break;            \
+    case 4: { constexpr int NVV = 4; e = CALL; } break;            \
+    default: return set_error("nv must be 1..4");                  \
+  }
 
 }  // namespace sfxm
 
@@ -290,56 +368,86 @@ extern "C" int sfxm_refine_mark(const double *x, const double *U, int64_t n, int
   if (!x || !U || !work || !counts_dev) return set_error("sfxm_refine_mark: null argument");
   if (n < 3) return set_error("sfxm_refine_mark: need at least 3 interior cells");
   if (n > 2147483647LL) return set_error("sfxm_refine_mark: mesh too large for one scan");
-  Criteria cr{ratio, slope, curve, prune, min_range, min_grid};
+  const Criteria cr{ratio, slope, curve, prune, min_range, min_grid};
+  const Window wd{n, 0, n, 0, n};
   cudaStream_t st = (cudaStream_t)stream;
-  int e;
-  switch (nv) {
-    case 1: e = refine_mark_t<1>(x, U, n, cr, (char *)work, st); break;
-    case 2: e = refine_mark_t<2>(x, U, n, cr, (char *)work, st); break;
-    case 3: e = refine_mark_t<3>(x, U, n, cr, (char *)work, st); break;
-    case 4: e = refine_mark_t<4>(x, U, n, cr, (char *)work, st); break;
-    default: return set_error("nv must be 1..4");
-  }
-  if (e) return e;
-  const AmrWork w = amr_layout(n);
   char *wk = (char *)work;
-  amr_count_kernel<<<1, 1, 0, st>>>((const int64_t *)(wk + w.off_kbef), (const int64_t *)(wk + w.off_ibef),
-                                    (const uint8_t *)(wk + w.off_keepf), (const uint8_t *)(wk + w.off_loc), n, counts_dev);
-  return check_launch("sfxm_refine_mark");
+  double *stats = (double *)(wk + amr_layout(n).off_stats);
+  int e = 0;
+  SFXM_NV_SWITCH(nv, (amr_stats_t<NVV>(x, U, wd, wk, stats, st)));
+  if (e) return e;
+  SFXM_NV_SWITCH(nv, (amr_mark_t<NVV>(x, U, wd, cr, stats, wk, nullptr, st)));
+  if (e) return e;
+  return amr_finalize_t(wd, -1, wk, counts_dev, st);
 }
 
 extern "C" int sfxm_refine_flags(const void *work, int64_t n, uint8_t *loc_out, uint8_t *keep_out, uint8_t *gridpt_out,
                                  int32_t *comp_out, void *stream) {
-  if (!work) return set_error("sfxm_refine_flags: null argument");
-  const AmrWork w = amr_layout(n);
-  const char *wk = (const char *)work;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (loc_out) cudaMemcpyAsync(loc_out, wk + w.off_loc, n, cudaMemcpyDeviceToDevice, st);
-  if (keep_out) cudaMemcpyAsync(keep_out, wk + w.off_keepf, n, cudaMemcpyDeviceToDevice, st);
-  if (gridpt_out) cudaMemcpyAsync(gridpt_out, wk + w.off_gridpt, n, cudaMemcpyDeviceToDevice, st);
-  if (comp_out) cudaMemcpyAsync(comp_out, wk + w.off_comp, SFXM_MAX_NV * 4, cudaMemcpyDeviceToDevice, st);
-  return check_launch("sfxm_refine_flags");
+  return sfxm_refine_window_flags(work, n, 0, n, loc_out, keep_out, gridpt_out, comp_out, stream);
 }
 
 extern "C" int sfxm_refine_apply(const double *x, const double *U, int64_t n, int32_t nv, const void *work, double *x_out,
                                  double *U_out, void *stream) {
   if (!x || !U || !work || !x_out || !U_out) return set_error("sfxm_refine_apply: null argument");
-  const AmrWork w = amr_layout(n);
+  const Window wd{n, 0, n, 0, n};
+  int e = 0;
+  SFXM_NV_SWITCH(nv, (amr_apply_t<NVV>(x, U, wd, (const char *)work, x_out, U_out, (cudaStream_t)stream)));
+  return e;
+}
+
+// ---- the same phases on a window of a slab-decomposed mesh ----
+extern "C" int sfxm_refine_window_stats(const double *x, const double *U, int64_t ne, int32_t nv, int64_t g0, int64_t ng,
+                                        int64_t own_lo, int64_t own_hi, void *work, double *stats_dev, void *stream) {
+  if (!x || !U || !work || !stats_dev) return set_error("sfxm_refine_window_stats: null argument");
+  const Window wd{ne, g0, ng, own_lo, own_hi};
+  if (!window_ok(wd)) return set_error("sfxm_refine_window_stats: bad window");
+  int e = 0;
+  SFXM_NV_SWITCH(nv, (amr_stats_t<NVV>(x, U, wd, (char *)work, stats_dev, (cudaStream_t)stream)));
+  return e;
+}
+
+extern "C" int sfxm_refine_window_mark(const double *x, const double *U, int64_t ne, int32_t nv, int64_t g0, int64_t ng,
+                                       int64_t own_lo, int64_t own_hi, double ratio, double slope, double curve,
+                                       double prune, double min_range, double min_grid, const double *stats_dev,
+                                       void *work, int64_t *last_run_dev, void *stream) {
+  if (!x || !U || !work || !stats_dev || !last_run_dev) return set_error("sfxm_refine_window_mark: null argument");
+  const Window wd{ne, g0, ng, own_lo, own_hi};
+  if (!window_ok(wd)) return set_error("sfxm_refine_window_mark: bad window");
+  const Criteria cr{ratio, slope, curve, prune, min_range, min_grid};
+  int e = 0;
+  SFXM_NV_SWITCH(nv, (amr_mark_t<NVV>(x, U, wd, cr, stats_dev, (char *)work, last_run_dev, (cudaStream_t)stream)));
+  return e;
+}
+
+extern "C" int sfxm_refine_window_finalize(int64_t ne, int64_t g0, int64_t ng, int64_t own_lo, int64_t own_hi,
+                                           int64_t carry_run_start, void *work, int64_t *counts_dev, void *stream) {
+  if (!work || !counts_dev) return set_error("sfxm_refine_window_finalize: null argument");
+  const Window wd{ne, g0, ng, own_lo, own_hi};
+  if (!window_ok(wd)) return set_error("sfxm_refine_window_finalize: bad window");
+  return amr_finalize_t(wd, carry_run_start, (char *)work, counts_dev, (cudaStream_t)stream);
+}
+
+extern "C" int sfxm_refine_window_apply(const double *x, const double *U, int64_t ne, int32_t nv, int64_t g0, int64_t ng,
+                                        int64_t own_lo, int64_t own_hi, const void *work, double *x_out, double *U_out,
+                                        void *stream) {
+  if (!x || !U || !work || !x_out || !U_out) return set_error("sfxm_refine_window_apply: null argument");
+  const Window wd{ne, g0, ng, own_lo, own_hi};
+  if (!window_ok(wd)) return set_error("sfxm_refine_window_apply: bad window");
+  int e = 0;
+  SFXM_NV_SWITCH(nv, (amr_apply_t<NVV>(x, U, wd, (const char *)work, x_out, U_out, (cudaStream_t)stream)));
+  return e;
+}
+
+extern "C" int sfxm_refine_window_flags(const void *work, int64_t ne, int64_t own_lo, int64_t own_hi, uint8_t *loc_out,
+                                        uint8_t *keep_out, uint8_t *gridpt_out, int32_t *comp_out, void *stream) {
+  if (!work || own_lo < 0 || own_hi > ne || own_lo >= own_hi) return set_error("sfxm_refine_window_flags: bad argument");
+  const AmrWork w = amr_layout(ne);
   const char *wk = (const char *)work;
-  const int threads = 256;
-  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  const int64_t n = own_hi - own_lo;
   cudaStream_t st = (cudaStream_t)stream;
-#define SFXM_APPLY(NV)                                                                                                   \
-  amr_apply_kernel<NV><<<blocks, threads, 0, st>>>(x, U, n, (const uint8_t *)(wk + w.off_keepf),                         \
-                                                   (const uint8_t *)(wk + w.off_loc), (const int64_t *)(wk + w.off_kbef), \
-                                                   (const int64_t *)(wk + w.off_ibef), x_out, U_out)
-  switch (nv) {
-    case 1: SFXM_APPLY(1); break;
-    case 2: SFXM_APPLY(2); break;
-    case 3: SFXM_APPLY(3); break;
-    case 4: SFXM_APPLY(4); break;
-    default: return set_error("nv must be 1..4");
-  }
-#undef SFXM_APPLY
-  return check_launch("sfxm_refine_apply");
+  if (loc_out) cudaMemcpyAsync(loc_out, wk + w.off_loc + own_lo, n, cudaMemcpyDeviceToDevice, st);
+  if (keep_out) cudaMemcpyAsync(keep_out, wk + w.off_keepf + own_lo, n, cudaMemcpyDeviceToDevice, st);
+  if (gridpt_out) cudaMemcpyAsync(gridpt_out, wk + w.off_gridpt + own_lo, n, cudaMemcpyDeviceToDevice, st);
+  if (comp_out) cudaMemcpyAsync(comp_out, wk + w.off_comp, SFXM_MAX_NV * 4, cudaMemcpyDeviceToDevice, st);
+  return check_launch("sfxm_refine_flags");
 }

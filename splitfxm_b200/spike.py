@@ -41,6 +41,21 @@ class DistComm:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
         return t
 
+    def gather_objects(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def exchange(self, send, recv_shapes, like):
+        """Point-to-point: send {dst: tensor}, recv_shapes {src: shape} -> {src: tensor} (dtype/device of `like`)."""
+        got = {src: torch.empty(shape, dtype=like.dtype, device=like.device) for src, shape in recv_shapes.items()}
+        ops = [self.dist.P2POp(self.dist.isend, send[dst], dst, self.group) for dst in sorted(send)]
+        ops += [self.dist.P2POp(self.dist.irecv, got[src], src, self.group) for src in sorted(got)]
+        if ops:
+            for req in self.dist.batch_isend_irecv(ops):
+                req.wait()
+        return got
+
     def any(self, flag, device):
         t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
@@ -95,6 +110,10 @@ class ThreadComm:
 
     def all_gather(self, t):
         return torch.stack(self.gather_objects(t.clone()))
+
+    def exchange(self, send, recv_shapes, like):
+        posted = self.gather_objects({dst: t.clone() for dst, t in send.items()})
+        return {src: posted[src][self.rank] for src in recv_shapes}
 
     def all_reduce_sum(self, t):
         parts = self.gather_objects(t.clone())

@@ -96,6 +96,8 @@ def test_thread_group_collectives():
         total = comm.all_reduce_sum(t.clone())
         low = comm.all_reduce_min(t.clone())
         flag = comm.any(rank == 1)
+        got = comm.exchange({(rank + 1) % G: torch.tensor([float(rank)])}, {(rank - 1) % G: (1,)}, t)
+        assert float(got[(rank - 1) % G][0]) == float((rank - 1) % G)
         left, right = (rank - 1) % G, (rank + 1) % G
         rl, rr = torch.zeros(1), torch.zeros(1)
         ThreadTransport(comm, left, right).exchange(torch.tensor([float(rank)]), torch.tensor([rank + 0.5]), rl, rr)
@@ -136,6 +138,11 @@ def _gloo_worker(rank, world, port, periodic, out):
     x = r[:, :, 0, 0] - r[:, :, 1:1 + S, 0] @ z[(rank - 1) % world, 1, :, 0] - r[:, :, 1 + S:, 0] @ z[(rank + 1) % world, 0, :, 0]
     nrm = comm.all_reduce_sum(torch.tensor([float((x ** 2).sum())], dtype=torch.float64))
     low = comm.all_reduce_min(torch.tensor([float(rank)], dtype=torch.float64))
+    # the point-to-point range exchange of the slab re-balancing, and the object gather of the refinement report
+    other = 1 - rank
+    got = comm.exchange({other: torch.full((2 + rank, 3), float(rank))}, {other: (2 + other, 3)}, torch.zeros(1, dtype=torch.float32))
+    assert got[other].shape == (2 + other, 3) and bool((got[other] == float(other)).all())
+    assert comm.gather_objects(("r", rank)) == [("r", 0), ("r", 1)]
     out[rank] = (lo, hi, x, float(nrm[0]), float(low[0]), comm.any(rank == 1, "cpu"))
     dist.barrier()
     dist.destroy_process_group()
