@@ -131,6 +131,18 @@ int sfxm_block_tridiag_solve(const sfxm_problem_t *prob, const double *J, const 
                              const int32_t *active, int32_t seg_lo, int32_t seg_hi, double *s, double *work,
                              int32_t *status, void *stream);
 
+/* Newton linear solve with the Jacobian assembled INSIDE the sweep (ensembles): (J_seg(y) + shift_m I) s = -f(y) for one
+ * variable segment, where the thread that walks a member's cells evaluates the finite-difference block row of each cell
+ * (sfxm_jacobian's arithmetic, simulation.py:320-354) in registers - J is never written to or read from HBM.  The
+ * result is bit-identical to sfxm_jacobian_segments + sfxm_block_tridiag_solve.  r0 (optional) receives the segment's
+ * rows of f(y).
+ * work: sfxm_solve_workspace_bytes().  sfxm_newton_fused_supported() says whether kernels exist for the problem's
+ * model / scheme (3-cell stencils of the built-in models); otherwise use the two calls above. */
+int sfxm_newton_fused_supported(const sfxm_problem_t *prob);
+int sfxm_newton_solve_fused(const sfxm_problem_t *prob, const double *x_int, const double *params, int64_t param_stride,
+                            const double *geom, const double *y, double eps, const double *shift, const int32_t *active,
+                            int32_t seg, double *s, double *r0, double *work, int32_t *status, void *stream);
+
 /* Same contract as sfxm_block_tridiag_solve, by block parallel cyclic reduction: one thread per (cell, member)
  * and ceil(log2 nx) streaming passes instead of one thread per member - the solver for a single large mesh or
  * a small batch.  work: sfxm_pcr_workspace_bytes(). */

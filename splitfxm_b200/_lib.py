@@ -9,7 +9,7 @@ import os
 from .error import SFXM
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsfxm_b200.so")
+LIB_PATH = os.environ.get("SFXM_LIB") or os.path.join(_HERE, "csrc", "libsfxm_b200.so")   # SFXM_LIB: kernel-variant builds
 
 MAX_NV, MAX_NB, MAX_PARAMS = 4, 2, 4
 
@@ -54,6 +54,9 @@ SIGNATURES = {
     "sfxm_pack_jacobian": (ctypes.c_int, [_PP, c_vp, c_vp, ctypes.POINTER(c_i32), c_vp]),
     "sfxm_solve_workspace_bytes": (c_i64, [_PP]),
     "sfxm_block_tridiag_solve": (ctypes.c_int, [_PP, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_newton_fused_supported": (ctypes.c_int, [_PP]),
+    "sfxm_newton_solve_fused": (ctypes.c_int, [_PP, c_vp, c_vp, c_i64, c_vp, c_vp, c_f64, c_vp, c_vp, c_i32, c_vp, c_vp,
+                                               c_vp, c_vp, c_vp]),
     "sfxm_pcr_workspace_bytes": (c_i64, [_PP]),
     "sfxm_block_tridiag_solve_pcr": (ctypes.c_int, [_PP, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_band4_workspace_bytes": (c_i64, [_PP]),

@@ -1,8 +1,14 @@
 // sfxm_dispatch.cu - C ABI of the residual / Jacobian / domain-fill kernels and the model dispatch.
 #include <cuda_runtime.h>
 #include "sfxm_kernels.cuh"
+#include "sfxm_fused.cuh"
 
 namespace sfxm {
+
+// fused Jacobian + block-Thomas kernels (sfxm_fused_*.cu); -2 = combination not instantiated
+int fused_ad3(const FusedLaunch &L);
+int fused_euler_cons(const FusedLaunch &L);
+int fused_euler_prim(const FusedLaunch &L);
 
 // one translation unit per model (sfxm_inst_*.cu)
 int launch_ad1(const Launch &L);
@@ -131,4 +137,35 @@ extern "C" int sfxm_register_user_model(int32_t slot, void *launch_fn) {
   if (slot < 0 || slot >= SFXM_MAX_USER_MODELS || !launch_fn) return set_error("sfxm_register_user_model: bad argument");
   g_user[slot] = (user_launch_fn)launch_fn;
   return 0;
+}
+
+// 1 if sfxm_newton_solve_fused has kernels for this problem (model / scheme / stencil), else 0
+extern "C" int sfxm_newton_fused_supported(const sfxm_problem_t *prob) {
+  if (!prob) return 0;
+  const sfxm_problem_t &P = *prob;
+  if (P.nbl != 1 || P.nbr != 1 || P.nx < 3) return 0;
+  if (P.model == SFXM_MODEL_AD && P.nv == 3)
+    return P.scheme == SFXM_FV_LAX_FRIEDRICHS || P.scheme == SFXM_FV_CENTRAL || P.scheme == SFXM_FD_CENTRAL;
+  if (P.model == SFXM_MODEL_EULER_CONS || P.model == SFXM_MODEL_EULER_PRIM) return P.nv == 3 && P.scheme == SFXM_FV_LAX_FRIEDRICHS;
+  return 0;
+}
+
+extern "C" int sfxm_newton_solve_fused(const sfxm_problem_t *prob, const double *x_int, const double *params,
+                                       int64_t param_stride, const double *geom, const double *y, double eps,
+                                       const double *shift, const int32_t *active, int32_t seg, double *s, double *r0,
+                                       double *work, int32_t *status, void *stream) {
+  if (!prob || !x_int || !params || !y || !s || !work) return set_error("sfxm_newton_solve_fused: null argument");
+  if (!(eps > 0.0)) return set_error("sfxm_newton_solve_fused: epsilon must be positive");
+  if (int e = validate(*prob)) return e;
+  if (!sfxm_newton_fused_supported(prob)) return set_error("sfxm_newton_solve_fused: no fused kernel for this model / scheme");
+  FusedLaunch L{prob, FusedArgs{x_int, params, param_stride, y, eps, geom, 0u, r0}, seg, shift, active, s, work, status,
+                (cudaStream_t)stream};
+  int e = -2;
+  switch (prob->model) {
+    case SFXM_MODEL_AD: e = fused_ad3(L); break;
+    case SFXM_MODEL_EULER_CONS: e = fused_euler_cons(L); break;
+    case SFXM_MODEL_EULER_PRIM: e = fused_euler_prim(L); break;
+  }
+  if (e == -2) return set_error("sfxm_newton_solve_fused: no fused kernel for this model / scheme");
+  return e;
 }

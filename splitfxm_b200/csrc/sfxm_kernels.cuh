@@ -331,10 +331,11 @@ __device__ __forceinline__ void jacobian_cell(const sfxm_problem_t &P, const dou
                                               const double *__restrict__ y, const double *prm, int64_t i, int64_t m,
                                               bool interior, const int64_t (&off)[NV], const double (&u)[W][NV],
                                               const Geom<SCHEME, W> &geom, double eps,
-                                              double *__restrict__ p, double *__restrict__ r0_out, uint32_t entry_mask) {
-  const int64_t B = P.batch;
+                                              double *__restrict__ p, double *__restrict__ r0_out, uint32_t entry_mask,
+                                              const int64_t B, double (&r0)[NV]) {
+  // B: distance between consecutive entries at p (the batch size for the banded layout in HBM; 1 when the block row
+  // goes to a thread-local array, sfxm_fused.cuh).  r0: the unperturbed residual, also returned to the caller.
   const double reps = 1.0 / eps;
-  double r0[NV];
   cell_residual<Model, SCHEME, NV, W, FAST>(prm, u, geom, r0);   // unperturbed rhs, simulation.py:320
   if (r0_out) {
 #pragma unroll
@@ -431,10 +432,11 @@ __device__ __forceinline__ void jacobian_member(const sfxm_problem_t &P, const d
   geom.and_inputs(u, prm);
   geom.fast = geom.fast && sane(eps, 120);
   double *p = J + (i * W) * (int64_t)(NV * NV) * P.batch + m;
+  double r0[NV];
   if (geom.fast)
-    jacobian_cell<Model, SCHEME, NV, W, true, RESTRICT>(P, x_int, y, prm, i, m, interior, off, u, geom, eps, p, r0_out, entry_mask);
+    jacobian_cell<Model, SCHEME, NV, W, true, RESTRICT>(P, x_int, y, prm, i, m, interior, off, u, geom, eps, p, r0_out, entry_mask, P.batch, r0);
   else
-    jacobian_cell<Model, SCHEME, NV, W, false, RESTRICT>(P, x_int, y, prm, i, m, interior, off, u, geom, eps, p, r0_out, entry_mask);
+    jacobian_cell<Model, SCHEME, NV, W, false, RESTRICT>(P, x_int, y, prm, i, m, interior, off, u, geom, eps, p, r0_out, entry_mask, P.batch, r0);
 }
 
 // out-of-line copy for the rare paths of the pair kernel (keeps its straight-line path free of their registers)

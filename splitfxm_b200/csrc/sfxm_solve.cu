@@ -12,358 +12,9 @@
 #include "../../include/sfxm_b200.h"
 #include "sfxm_host.h"
 #include "sfxm_reduce.cuh"
+#include "sfxm_thomas.cuh"
 
 namespace sfxm {
-
-// R <- A^{-1} R by Gauss-Jordan elimination with partial (row) pivoting; returns false on a zero pivot
-template <int S, int NC>
-__device__ __forceinline__ bool gj_solve(double (&A)[S][S], double (&R)[S][NC]) {
-  bool ok = true;
-#pragma unroll
-  for (int k = 0; k < S; ++k) {
-    int piv = k;
-    double best = fabs(A[k][k]);
-#pragma unroll
-    for (int r = k + 1; r < S; ++r) {
-      const double a = fabs(A[r][k]);
-      if (a > best) { best = a; piv = r; }
-    }
-    if (best == 0.0) ok = false;
-#pragma unroll
-    for (int r = k + 1; r < S; ++r) {
-      if (r == piv) {
-#pragma unroll
-        for (int c = 0; c < S; ++c) { const double t = A[k][c]; A[k][c] = A[r][c]; A[r][c] = t; }
-#pragma unroll
-        for (int c = 0; c < NC; ++c) { const double t = R[k][c]; R[k][c] = R[r][c]; R[r][c] = t; }
-      }
-    }
-    const double inv = 1.0 / A[k][k];
-#pragma unroll
-    for (int c = 0; c < S; ++c) A[k][c] *= inv;
-#pragma unroll
-    for (int c = 0; c < NC; ++c) R[k][c] *= inv;
-#pragma unroll
-    for (int r = 0; r < S; ++r) {
-      if (r == k) continue;
-      const double f = A[r][k];
-#pragma unroll
-      for (int c = 0; c < S; ++c) A[r][c] -= f * A[k][c];
-#pragma unroll
-      for (int c = 0; c < NC; ++c) R[r][c] -= f * R[k][c];
-    }
-  }
-  return ok;
-}
-
-// J block (i, slot d) restricted to rows/cols [o, o+S)
-template <int NV, int S>
-__device__ __forceinline__ void load_block(const double *__restrict__ J, int64_t i, int d, int o, int64_t B, int64_t m,
-                                           double (&blk)[S][S]) {
-  const double *p = J + ((i * 3 + d) * (int64_t)(NV * NV)) * B + m;
-#pragma unroll
-  for (int r = 0; r < S; ++r)
-#pragma unroll
-    for (int c = 0; c < S; ++c) blk[r][c] = __ldg(p + (int64_t)((o + r) * NV + (o + c)) * B);
-}
-
-// Block Thomas.  CYCLIC: rows 0..n-2 form an acyclic system with 1 + S right-hand sides (the extra S columns
-// carry the coupling to the last block unknown), the last block row is then solved for x_{n-1} and folded back.
-//   workC[(i*NV*NV + (o+r)*NV + (o+c))*B + m] : C'_i           workR[((i*NV + (o+r))*(1+NV) + k)*B + m] : rhs'_i / X_i
-template <int NV, int S, bool CYCLIC>
-__global__ void __launch_bounds__(128)
-block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const double *__restrict__ J,
-                    const double *__restrict__ f, const double *__restrict__ shift,
-                    const int32_t *__restrict__ active, double *__restrict__ s_out, double *__restrict__ workC,
-                    double *__restrict__ workR, int32_t *__restrict__ status) {
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t B = P.batch;
-  if (m >= B) return;
-  if (active && !active[m]) return;
-  constexpr int NR = CYCLIC ? 1 + S : 1;
-  constexpr int NC = S + NR;
-  const double sh = shift ? shift[m] : 0.0;
-  const int64_t n = P.nx;
-  const int64_t ne = CYCLIC ? n - 1 : n;
-  bool ok = true;
-  double Cp[S][S], Rp[S][NR];   // C'_{i-1}, rhs'_{i-1}
-  auto fidx = [&](int64_t i, int r) { return (P.var_base[o + r] + i * (int64_t)P.var_stride[o + r] + P.var_off[o + r]) * B + m; };
-  for (int64_t i = 0; i < ne; ++i) {
-    double A[S][S], Bd[S][S], R[S][NC];
-    load_block<NV, S>(J, i, 1, o, B, m, Bd);
-#pragma unroll
-    for (int r = 0; r < S; ++r) Bd[r][r] += sh;
-    {
-      double C[S][S];
-      load_block<NV, S>(J, i, 2, o, B, m, C);
-#pragma unroll
-      for (int r = 0; r < S; ++r) {
-#pragma unroll
-        for (int c = 0; c < S; ++c) R[r][c] = (CYCLIC && i == ne - 1) ? 0.0 : C[r][c];
-        R[r][S] = -__ldg(f + fidx(i, r));
-        if constexpr (CYCLIC) {
-#pragma unroll
-          for (int c = 0; c < S; ++c) R[r][S + 1 + c] = (i == ne - 1) ? C[r][c] : 0.0;
-        }
-      }
-    }
-    load_block<NV, S>(J, i, 0, o, B, m, A);
-    if (i == 0) {
-      if constexpr (CYCLIC) {
-#pragma unroll
-        for (int r = 0; r < S; ++r)
-#pragma unroll
-          for (int c = 0; c < S; ++c) R[r][S + 1 + c] += A[r][c];   // wrap block couples row 0 to x_{n-1}
-      }
-    } else {
-#pragma unroll
-      for (int r = 0; r < S; ++r) {
-#pragma unroll
-        for (int k = 0; k < S; ++k) {
-          const double a = A[r][k];
-#pragma unroll
-          for (int c = 0; c < S; ++c) Bd[r][c] -= a * Cp[k][c];
-#pragma unroll
-          for (int c = 0; c < NR; ++c) R[r][S + c] -= a * Rp[k][c];
-        }
-      }
-    }
-    ok = gj_solve<S, NC>(Bd, R) && ok;
-#pragma unroll
-    for (int r = 0; r < S; ++r) {
-#pragma unroll
-      for (int c = 0; c < S; ++c) {
-        Cp[r][c] = R[r][c];
-        workC[(i * (int64_t)(NV * NV) + (o + r) * NV + (o + c)) * B + m] = R[r][c];
-      }
-#pragma unroll
-      for (int c = 0; c < NR; ++c) {
-        Rp[r][c] = R[r][S + c];
-        if (CYCLIC || i < ne - 1) workR[((i * NV + (o + r)) * (int64_t)(1 + NV) + c) * B + m] = R[r][S + c];
-      }
-    }
-  }
-  // back substitution: X_i = rhs'_i - C'_i X_{i+1}
-  double X[S][NR];
-#pragma unroll
-  for (int r = 0; r < S; ++r)
-#pragma unroll
-    for (int c = 0; c < NR; ++c) X[r][c] = Rp[r][c];
-  if constexpr (!CYCLIC) {
-#pragma unroll
-    for (int r = 0; r < S; ++r) s_out[fidx(ne - 1, r)] = X[r][0];
-  } else {
-#pragma unroll
-    for (int r = 0; r < S; ++r)
-#pragma unroll
-      for (int c = 0; c < NR; ++c) workR[(((ne - 1) * NV + (o + r)) * (int64_t)(1 + NV) + c) * B + m] = X[r][c];
-  }
-  double Xfirst[S][NR];   // X_0 (needed by the last row in the cyclic case)
-#pragma unroll
-  for (int r = 0; r < S; ++r)
-#pragma unroll
-    for (int c = 0; c < NR; ++c) Xfirst[r][c] = X[r][c];
-  double Xlast[S][NR];    // X_{n-2}
-#pragma unroll
-  for (int r = 0; r < S; ++r)
-#pragma unroll
-    for (int c = 0; c < NR; ++c) Xlast[r][c] = X[r][c];
-  for (int64_t i = ne - 2; i >= 0; --i) {
-    double C[S][S], Rn[S][NR];
-#pragma unroll
-    for (int r = 0; r < S; ++r) {
-#pragma unroll
-      for (int c = 0; c < S; ++c) C[r][c] = workC[(i * (int64_t)(NV * NV) + (o + r) * NV + (o + c)) * B + m];
-#pragma unroll
-      for (int c = 0; c < NR; ++c) Rn[r][c] = workR[((i * NV + (o + r)) * (int64_t)(1 + NV) + c) * B + m];
-    }
-#pragma unroll
-    for (int r = 0; r < S; ++r)
-#pragma unroll
-      for (int k = 0; k < S; ++k) {
-        const double a = C[r][k];
-#pragma unroll
-        for (int c = 0; c < NR; ++c) Rn[r][c] -= a * X[k][c];
-      }
-#pragma unroll
-    for (int r = 0; r < S; ++r)
-#pragma unroll
-      for (int c = 0; c < NR; ++c) X[r][c] = Rn[r][c];
-    if constexpr (!CYCLIC) {
-#pragma unroll
-      for (int r = 0; r < S; ++r) s_out[fidx(i, r)] = X[r][0];
-    } else {
-#pragma unroll
-      for (int r = 0; r < S; ++r)
-#pragma unroll
-        for (int c = 0; c < NR; ++c) workR[((i * NV + (o + r)) * (int64_t)(1 + NV) + c) * B + m] = X[r][c];
-      if (i == 0) {
-#pragma unroll
-        for (int r = 0; r < S; ++r)
-#pragma unroll
-          for (int c = 0; c < NR; ++c) Xfirst[r][c] = X[r][c];
-      }
-    }
-  }
-  if constexpr (CYCLIC) {
-    // last block row: C_{n-1} x_0 + A_{n-1} x_{n-2} + B_{n-1} x_{n-1} = -f_{n-1},  x_i = q_i - Q_i x_{n-1}
-    if (ne == 1) {
-#pragma unroll
-      for (int r = 0; r < S; ++r)
-#pragma unroll
-        for (int c = 0; c < NR; ++c) Xfirst[r][c] = Xlast[r][c];
-    }
-    double A[S][S], Bd[S][S], C[S][S], rhs[S][1];
-    load_block<NV, S>(J, n - 1, 0, o, B, m, A);
-    load_block<NV, S>(J, n - 1, 1, o, B, m, Bd);
-    load_block<NV, S>(J, n - 1, 2, o, B, m, C);
-#pragma unroll
-    for (int r = 0; r < S; ++r) {
-      Bd[r][r] += sh;
-      rhs[r][0] = -__ldg(f + fidx(n - 1, r));
-    }
-#pragma unroll
-    for (int r = 0; r < S; ++r)
-#pragma unroll
-      for (int k = 0; k < S; ++k) {
-        rhs[r][0] -= C[r][k] * Xfirst[k][0] + A[r][k] * Xlast[k][0];
-#pragma unroll
-        for (int c = 0; c < S; ++c) Bd[r][c] -= C[r][k] * Xfirst[k][1 + c] + A[r][k] * Xlast[k][1 + c];
-      }
-    ok = gj_solve<S, 1>(Bd, rhs) && ok;
-#pragma unroll
-    for (int r = 0; r < S; ++r) s_out[fidx(n - 1, r)] = rhs[r][0];
-    for (int64_t i = 0; i < ne; ++i) {
-#pragma unroll
-      for (int r = 0; r < S; ++r) {
-        const double *w = workR + ((i * NV + (o + r)) * (int64_t)(1 + NV)) * B + m;
-        double xv = w[0];
-#pragma unroll
-        for (int c = 0; c < S; ++c) xv -= w[(int64_t)(1 + c) * B] * rhs[c][0];
-        s_out[fidx(i, r)] = xv;
-      }
-    }
-  }
-  if (status && !ok) status[m] = 1;
-}
-
-// Right-periodic only (lower-left corner block F = C_{n-1} at (n-1, 0), no upper-right one): plain Thomas on rows
-// 0..n-2 while the fill that eliminating x_0, x_1, ... creates in the LAST row is carried in registers:
-//   G_0 = F ;  (G_{n-2} += A_{n-1}) ;  d_last -= G_i rhs'_i ;  G_{i+1} = -G_i C'_i
-// then (B_{n-1} + G_{n-1}) x_{n-1} = d_last and the usual back substitution.  One right-hand side, no extra
-// workspace columns: ~40 % less traffic than the condensation the fully cyclic case needs.
-template <int NV, int S>
-__global__ void __launch_bounds__(128)
-block_thomas_ll_kernel(const __grid_constant__ sfxm_problem_t P, int o, const double *__restrict__ J,
-                       const double *__restrict__ f, const double *__restrict__ shift,
-                       const int32_t *__restrict__ active, double *__restrict__ s_out, double *__restrict__ workC,
-                       double *__restrict__ workR, int32_t *__restrict__ status) {
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t B = P.batch;
-  if (m >= B) return;
-  if (active && !active[m]) return;
-  const double sh = shift ? shift[m] : 0.0;
-  const int64_t n = P.nx;
-  bool ok = true;
-  auto fidx = [&](int64_t i, int r) { return (P.var_base[o + r] + i * (int64_t)P.var_stride[o + r] + P.var_off[o + r]) * B + m; };
-  double G[S][S], Alast[S][S], Blast[S][S], dl[S];
-  load_block<NV, S>(J, n - 1, 0, o, B, m, Alast);
-  load_block<NV, S>(J, n - 1, 1, o, B, m, Blast);
-  load_block<NV, S>(J, n - 1, 2, o, B, m, G);             // F = wrap block of the last row
-#pragma unroll
-  for (int r = 0; r < S; ++r) {
-    Blast[r][r] += sh;
-    dl[r] = -__ldg(f + fidx(n - 1, r));
-  }
-  double Cp[S][S], Rp[S];
-  for (int64_t i = 0; i < n - 1; ++i) {
-    double A[S][S], Bd[S][S], R[S][S + 1];
-    load_block<NV, S>(J, i, 1, o, B, m, Bd);
-    {
-      double C[S][S];
-      load_block<NV, S>(J, i, 2, o, B, m, C);
-#pragma unroll
-      for (int r = 0; r < S; ++r) {
-        Bd[r][r] += sh;
-#pragma unroll
-        for (int c = 0; c < S; ++c) R[r][c] = C[r][c];
-        R[r][S] = -__ldg(f + fidx(i, r));
-      }
-    }
-    if (i > 0) {
-      load_block<NV, S>(J, i, 0, o, B, m, A);
-#pragma unroll
-      for (int r = 0; r < S; ++r)
-#pragma unroll
-        for (int k = 0; k < S; ++k) {
-          const double a = A[r][k];
-#pragma unroll
-          for (int c = 0; c < S; ++c) Bd[r][c] -= a * Cp[k][c];
-          R[r][S] -= a * Rp[k];
-        }
-    }
-    ok = gj_solve<S, S + 1>(Bd, R) && ok;
-#pragma unroll
-    for (int r = 0; r < S; ++r) {
-#pragma unroll
-      for (int c = 0; c < S; ++c) {
-        Cp[r][c] = R[r][c];
-        workC[(i * (int64_t)(NV * NV) + (o + r) * NV + (o + c)) * B + m] = R[r][c];
-      }
-      Rp[r] = R[r][S];
-      workR[((i * NV + (o + r)) * (int64_t)(1 + NV)) * B + m] = R[r][S];
-    }
-    // carry the last row's fill
-    if (i == n - 2) {
-#pragma unroll
-      for (int r = 0; r < S; ++r)
-#pragma unroll
-        for (int c = 0; c < S; ++c) G[r][c] += Alast[r][c];
-    }
-    double Gn[S][S];
-#pragma unroll
-    for (int r = 0; r < S; ++r) {
-#pragma unroll
-      for (int c = 0; c < S; ++c) Gn[r][c] = 0.0;
-#pragma unroll
-      for (int k = 0; k < S; ++k) {
-        dl[r] -= G[r][k] * Rp[k];
-#pragma unroll
-        for (int c = 0; c < S; ++c) Gn[r][c] -= G[r][k] * Cp[k][c];
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < S; ++r)
-#pragma unroll
-      for (int c = 0; c < S; ++c) G[r][c] = Gn[r][c];
-  }
-  double X[S][1];
-#pragma unroll
-  for (int r = 0; r < S; ++r) {
-    X[r][0] = dl[r];
-#pragma unroll
-    for (int c = 0; c < S; ++c) Blast[r][c] += G[r][c];
-  }
-  ok = gj_solve<S, 1>(Blast, X) && ok;
-#pragma unroll
-  for (int r = 0; r < S; ++r) s_out[fidx(n - 1, r)] = X[r][0];
-  for (int64_t i = n - 2; i >= 0; --i) {
-    double Xn[S];
-#pragma unroll
-    for (int r = 0; r < S; ++r) {
-      double v = workR[((i * NV + (o + r)) * (int64_t)(1 + NV)) * B + m];
-#pragma unroll
-      for (int c = 0; c < S; ++c) v -= workC[(i * (int64_t)(NV * NV) + (o + r) * NV + (o + c)) * B + m] * X[c][0];
-      Xn[r] = v;
-    }
-#pragma unroll
-    for (int r = 0; r < S; ++r) {
-      X[r][0] = Xn[r];
-      s_out[fidx(i, r)] = Xn[r];
-    }
-  }
-  if (status && !ok) status[m] = 1;
-}
 
 // Compact copy of the same-segment entries of a split Jacobian (the only ones that exist, simulation.py:373-392):
 // dst[((i*W + d)*L + e) * B + m] = src[((i*W + d)*nv*nv + rc[e]) * B + m],  rc = the L live (r, c) pairs in
@@ -408,13 +59,14 @@ static int launch_thomas(const sfxm_problem_t &P, int o, int cyclic, const doubl
   double *workC = work;
   double *workR = work + P.nx * (int64_t)(NV * NV) * P.batch;
   const int threads = P.batch >= 128 ? 128 : 32;
+  const typename MemSrc<NV>::Args src{J, f};
   const unsigned blocks = (unsigned)((P.batch + threads - 1) / threads);
   if (cyclic == 1)   // lower-left corner only
-    block_thomas_ll_kernel<NV, S><<<blocks, threads, 0, st>>>(P, o, J, f, shift, active, s, workC, workR, status);
+    block_thomas_ll_kernel<MemSrc<NV>, NV, S><<<blocks, threads, 0, st>>>(P, o, src, shift, active, s, workC, workR, status);
   else if (cyclic)
-    block_thomas_kernel<NV, S, true><<<blocks, threads, 0, st>>>(P, o, J, f, shift, active, s, workC, workR, status);
+    block_thomas_kernel<MemSrc<NV>, NV, S, true><<<blocks, threads, 0, st>>>(P, o, src, shift, active, s, workC, workR, status);
   else
-    block_thomas_kernel<NV, S, false><<<blocks, threads, 0, st>>>(P, o, J, f, shift, active, s, workC, workR, status);
+    block_thomas_kernel<MemSrc<NV>, NV, S, false><<<blocks, threads, 0, st>>>(P, o, src, shift, active, s, workC, workR, status);
   return check_launch("sfxm_block_tridiag_solve");
 }
 

@@ -235,6 +235,25 @@ class Engine:
                       _lib.ptr(s), _lib.ptr(work), _lib.ptr(status), _lib.stream_ptr()))
         return s
 
+    def fused_solve_supported(self, split=False, split_locs=None):
+        """True when the Newton linear solve can run with the Jacobian assembled inside the Thomas sweep
+        (sfxm_newton_solve_fused): ensembles large enough for one thread per member, built-in 3-cell models."""
+        P, _ = self.problem(split, split_locs)
+        return self.batch >= 2048 and bool(self.lib.sfxm_newton_fused_supported(ctypes.byref(P)))
+
+    def newton_solve_fused(self, y, s, split=False, split_locs=None, seg=0, eps=1e-8, shift=None, active=None,
+                           status=None, r0=None):
+        """(J_seg(y) + shift I) s = -f(y) for one segment without materialising J; r0 (optional) receives f(y)."""
+        P, _ = self.problem(split, split_locs)
+        nbytes = self.lib.sfxm_solve_workspace_bytes(ctypes.byref(P))
+        work = self._scratch("solve", nbytes // 8)
+        _lib.check(self.lib.sfxm_newton_solve_fused(ctypes.byref(P), _lib.ptr(self.x_int), _lib.ptr(self.params),
+                                                    self.param_stride, _lib.ptr(self._geom), _lib.ptr(y), float(eps),
+                                                    _lib.ptr(shift), _lib.ptr(active), int(seg), _lib.ptr(s), _lib.ptr(r0),
+                                                    _lib.ptr(work), _lib.ptr(status), _lib.stream_ptr()))
+        _lib.count()
+        return s
+
     def sumsq(self, v, lo=0, hi=None, out=None):
         if hi is None:
             hi = self.n

@@ -23,7 +23,7 @@ BOUND_FAC = 0.8
 
 class NewtonDriver:
     def __init__(self, eng, split=False, split_locs=None, dt0=0.0, dtmax=1.0, armijo=False, bounds=None,
-                 bound_fac=BOUND_FAC, eps=1e-8):
+                 bound_fac=BOUND_FAC, eps=1e-8, fused=True):
         if dt0 < 0 or dtmax < 0:
             raise ValueError("Must specify positive dt0 and dtmax")
         self.eng = eng
@@ -44,6 +44,8 @@ class NewtonDriver:
         self.status = torch.zeros(B, dtype=torch.int32, device=dev)
         self.all_active = torch.ones(B, dtype=torch.bool, device=dev)
         # a slab-decomposed mesh (spike.SlabNewtonEngine) reduces the host-side decisions over the ranks
+        fused_ok = getattr(eng, "fused_solve_supported", None)
+        self.fused = bool(fused_ok(split, split_locs)) if (fused and fused_ok is not None) else False
         self._reduce_min = getattr(eng, "reduce_min", lambda t: t)
         self._reduce_any = getattr(eng, "reduce_any", lambda flag: flag)
 
@@ -68,12 +70,17 @@ class NewtonDriver:
             if not bool(run.any()):
                 break
             run32 = run.to(torch.int32)
-            # r = f(y) and the blocks of J = f'(y) that belong to segment k (the only ones this solve reads)
-            J = eng.jacobian(y, self.split, self.split_locs, self.eps, r0=self.r, seg_lo=k, seg_hi=k + 1)
             shift = (-1.0 / dt) if self.dt0 > 0 else None
-            eng.solve(J, self.r, self.s, self.split, self.split_locs, k, k + 1, shift=shift, active=run32,
-                      status=self.status)
             need_rnorm = self.armijo or self.dt0 > 0
+            if self.fused:
+                # ensembles: the sweeping thread evaluates each cell's block row itself (J never touches HBM)
+                eng.newton_solve_fused(y, self.s, self.split, self.split_locs, k, self.eps, shift=shift, active=run32,
+                                       status=self.status, r0=self.r if need_rnorm else None)
+            else:
+                # r = f(y) and the blocks of J = f'(y) that belong to segment k (the only ones this solve reads)
+                J = eng.jacobian(y, self.split, self.split_locs, self.eps, r0=self.r, seg_lo=k, seg_hi=k + 1)
+                eng.solve(J, self.r, self.s, self.split, self.split_locs, k, k + 1, shift=shift, active=run32,
+                          status=self.status)
             rnorm = torch.sqrt(eng.sumsq(self.r, lo, hi)) if need_rnorm else None
             scale = None
             if self.armijo:

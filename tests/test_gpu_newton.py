@@ -192,3 +192,85 @@ def test_steady_state_right_bias_matches_oracle_spec():
     it = s.steady_state(split=True, split_locs=[1], dt0=0.05, dtmax=10.0)
     assert it == it_ref
     assert rel_err(d.listify_interior(True, [1]), xf) < 1e-9
+
+
+@pytest.mark.parametrize("case,split,locs", [
+    ("ad_dirichlet", True, [1]),        # plain Thomas, 1x1 and 2x2 segments
+    ("ad_dirichlet", False, None),      # 3x3 blocks
+    ("ad_bench", True, [1]),            # bench BCs: (v, w) segment with a lower-left corner block only
+    ("ad_readme", True, [1, 2]),        # u fully cyclic (condensation), v plain, w right-periodic
+    ("ad_readme", False, None),
+    ("ad_fvm_lf", True, [2]),
+    ("sod_cons", False, None),          # dense Euler blocks
+])
+def test_fused_newton_solve_bit_identical_to_assemble_then_solve(case, split, locs):
+    """sfxm_newton_solve_fused (Jacobian block rows evaluated inside the Thomas sweep) against sfxm_jacobian_segments +
+    sfxm_block_tridiag_solve on the same ensemble: same kernels, same operation order -> identical bits."""
+    import torch
+    import splitfxm_b200 as sf
+    from splitfxm_b200.ensemble import EnsembleSimulation
+    B, nx = 64, 37
+    rng = np.random.default_rng(3)
+    readme = {"u": {"left": "periodic", "right": "periodic"}, "v": {"left": {"dirichlet": 3}, "right": {"dirichlet": 4}},
+              "w": {"left": {"dirichlet": 2}, "right": "periodic"}}
+    if case == "sod_cons":
+        comps = ["rho", "rhou", "E"]
+        bcs = {n: {"left": {"neumann": 0.0}, "right": {"neumann": 0.0}} for n in comps}
+        d = sf.Domain.from_size(nx, 1, 1, comps)
+        ens = EnsembleSimulation(d, "euler_cons", {"gamma": np.linspace(1.3, 1.5, B)}, bcs, sf.FVSchemes.LAX_FRIEDRICHS, "FVM")
+        U = np.stack([1.0 + 0.1 * rng.random((nx, B)), 0.1 * rng.standard_normal((nx, B)), 2.5 + 0.1 * rng.random((nx, B))], axis=1)
+    else:
+        comps = ["u", "v", "w"]
+        bcs = {"ad_dirichlet": {c: {"left": {"dirichlet": 1.0}, "right": {"neumann": 0.5}} for c in comps},
+               "ad_bench": dict(readme, u={"left": {"dirichlet": 0.0}, "right": {"dirichlet": 0.0}}),
+               "ad_readme": readme, "ad_fvm_lf": readme}[case]
+        d = sf.Domain.from_size(nx, 1, 1, comps)
+        scheme, method = (sf.FVSchemes.LAX_FRIEDRICHS, "FVM") if case == "ad_fvm_lf" else (sf.FDSchemes.CENTRAL, "FDM")
+        ens = EnsembleSimulation(d, "ad", {"c": np.linspace(0.05, 0.5, B), "nu": np.logspace(-3, -1, B)}, bcs, scheme, method)
+        U = rng.standard_normal((nx, 3, B))
+    eng = ens.eng
+    from splitfxm_b200.engine import flat_index_table, split_segments
+    idx = flat_index_table(nx, 3, split_segments(3, split, locs))
+    Y = np.empty((3 * nx, B))
+    Y[idx.reshape(-1)] = U.reshape(3 * nx, B)
+    y = eng.to_device(Y)
+    _, segs = eng.problem(split, locs)
+    shift = torch.linspace(-30.0, -60.0, B, dtype=torch.float64, device=y.device)
+    active = torch.ones(B, dtype=torch.int32, device=y.device)
+    active[5] = 0
+    for k in range(len(segs)):
+        r_a, r_b = torch.zeros_like(y), torch.zeros_like(y)
+        s_a, s_b = torch.zeros_like(y), torch.zeros_like(y)
+        st_a = torch.zeros(B, dtype=torch.int32, device=y.device)
+        st_b = torch.zeros(B, dtype=torch.int32, device=y.device)
+        J = eng.jacobian(y, split, locs, 1e-8, r0=r_a, seg_lo=k, seg_hi=k + 1)
+        eng.solve(J, r_a, s_a, split, locs, k, k + 1, shift=shift, active=active, status=st_a, method="thomas")
+        eng.newton_solve_fused(y, s_b, split, locs, k, 1e-8, shift=shift, active=active, status=st_b, r0=r_b)
+        assert int(st_a.sum()) == 0 and int(st_b.sum()) == 0
+        assert torch.equal(s_a, s_b), f"segment {k}: max diff {float((s_a - s_b).abs().max())}"
+        assert float(s_b[:, 5].abs().max()) == 0.0                      # masked member untouched
+        act = active.bool()
+        lo, hi = segs[k][0] * nx, (segs[k][0] + segs[k][1]) * nx          # the segment's rows of f(y)
+        assert torch.equal(r_a[lo:hi][:, act], r_b[lo:hi][:, act])
+        assert float(s_b.abs().max()) > 0.0
+
+
+def test_ensemble_newton_fused_equals_unfused():
+    import torch
+    import splitfxm_b200 as sf
+    from splitfxm_b200.ensemble import EnsembleSimulation
+    from splitfxm_b200.newton import NewtonDriver
+    s, d, comps, bcs = _well_posed_case()
+    B = 2048
+    ens = EnsembleSimulation(d, "ad", {"c": np.linspace(0.05, 0.5, B), "nu": np.logspace(-2, -1, B)}, bcs,
+                             sf.FVSchemes.LAX_FRIEDRICHS, method="FVM")
+    x0 = d.listify_interior(True, [1])
+    Y0 = ens.eng.to_device(np.repeat(x0[:, None], B, axis=1))
+    assert ens.eng.fused_solve_supported(True, [1])
+    for kw in ({}, {"dt0": 0.05, "dtmax": 10.0}, {"armijo": True}):
+        ya, yb = Y0.clone(), Y0.clone()
+        drv_a = NewtonDriver(ens.eng, True, [1], fused=True, **kw)
+        drv_b = NewtonDriver(ens.eng, True, [1], fused=False, **kw)
+        assert drv_a.fused and not drv_b.fused
+        ita, itb = drv_a.run(ya), drv_b.run(yb)
+        assert torch.equal(ita, itb) and torch.equal(ya, yb)
