@@ -372,6 +372,26 @@ def extras(torch, sf, ens, Y, dev, peak):
     out["ensemble_block_tridiag_solve"] = {"ms": ms_solve, "GBps": solve_bytes / ms_solve / 1e6,
                                            "frac": solve_bytes / ms_solve / 1e6 / peak,
                                            "solves_per_s": B / (ms_solve * 1e-3)}
+    # Newton linear step (both segments of split [1]): Jacobian assembled inside the Thomas sweep vs assemble-then-solve
+    s2 = torch.zeros_like(Y)
+
+    def fused_step():
+        for k in range(2):
+            eng.newton_solve_fused(Y, s2, SPLIT, LOCS, k, status=status)
+
+    def unfused_step():
+        for k in range(2):
+            eng.jacobian(Y, SPLIT, LOCS, J=J, r0=r, seg_lo=k, seg_hi=k + 1)
+            eng.solve(J, r, s, SPLIT, LOCS, k, k + 1, status=status, method="thomas")
+
+    ms_f, ms_u = timed(fused_step, 3), timed(unfused_step, 3)
+    # fused algorithmic bytes per cell-member: read the segment's U (8 s), write + read C' (8 s^2) and rhs' (8 s),
+    # write the step (8 s): s = 1 -> 48, s = 2 -> 128
+    fused_bytes = B * NX * (48 + 128)
+    out["ensemble_newton_linear_step"] = {"fused_ms": ms_f, "assemble_then_solve_ms": ms_u,
+                                          "bit_identical": bool(torch.equal(s, s2)),
+                                          "linear_steps_per_s": B / (ms_f * 1e-3),
+                                          "fused_GBps": fused_bytes / ms_f / 1e6, "fused_frac": fused_bytes / ms_f / 1e6 / peak}
     ens.steady_state(Y, split=SPLIT, split_locs=LOCS)       # warm the allocator (first call allocates ~2 GB)
     torch.cuda.synchronize()
     t0 = time.perf_counter()

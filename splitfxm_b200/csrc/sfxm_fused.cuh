@@ -50,8 +50,12 @@ __device__ __noinline__ void fused_row_general(const sfxm_problem_t &P, const Fu
   for (int j = 0; j < NV; ++j) r0l[j] = r0[j];
 }
 
+// Resident one-warp CTAs per SM the register allocation must allow.  Measured on the 65,536 x nx 250 ensemble
+// (gpurun_out/fused_time_variants.log): scalar segments run 0.64 -> 0.49 ms when capped at 128 registers (14 CTAs per SM:
+// all 2048 warps resident in one wave, the spills are cheaper than a second wave); 2x2 and 3x3 segments spill too much
+// under the cap and are left at 255 registers (8 CTAs per SM).
 #ifndef SFXM_FUSED_MIN_CTAS
-#define SFXM_FUSED_MIN_CTAS 1
+#define SFXM_FUSED_MIN_CTAS(S) ((S) == 1 ? 14 : 1)
 #endif
 
 // select element `idx` (a run-time value) of a small register array without indexing it dynamically
@@ -67,7 +71,7 @@ __device__ __forceinline__ double pick(const double (&v)[N], int idx) {
 // registers); the segment offset o is a run-time value that only enters addresses and selects.
 template <class Model, int SCHEME, int NV, int S>
 struct FusedSrc {
-  static constexpr int kMaxThreads = 32, kMinCtas = SFXM_FUSED_MIN_CTAS;   // one-warp CTAs (fused_launch_s)
+  static constexpr int kMaxThreads = 32, kMinCtas = SFXM_FUSED_MIN_CTAS(S);   // one-warp CTAs (fused_launch_s)
   using Args = FusedArgs;
   using M1 = typename Model::Scalar;
   const FusedArgs &a;
