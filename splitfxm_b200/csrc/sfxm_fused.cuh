@@ -71,7 +71,7 @@ __device__ __forceinline__ double pick(const double (&v)[N], int idx) {
 // registers); the segment offset o is a run-time value that only enters addresses and selects.
 template <class Model, int SCHEME, int NV, int S>
 struct FusedSrc {
-  static constexpr int kMaxThreads = 32, kMinCtas = SFXM_FUSED_MIN_CTAS(S);   // one-warp CTAs (fused_launch_s)
+  static constexpr int kMaxThreads = kThomasThreads, kMinCtas = SFXM_FUSED_MIN_CTAS(S);   // one-warp CTAs (fused_launch_s)
   using Args = FusedArgs;
   using M1 = typename Model::Scalar;
   const FusedArgs &a;
@@ -79,12 +79,14 @@ struct FusedSrc {
   double prm[Model::kParams];
   bool prm_ok;
   double reps;              // RN(1 / eps)
+  int64_t seq_next;         // the cell the forward ring expects next (-1: ring not primed)
   double Jseg[3][S][S];
   double rseg[S];
 
   __device__ __forceinline__ FusedSrc(const FusedArgs &args, const sfxm_problem_t &P, int64_t m) : a(args), o(first_var(P, args.mask)) {
     prm_ok = sane(a.eps, 120);
     reps = 1.0 / a.eps;
+    seq_next = -1;
 #pragma unroll
     for (int k = 0; k < Model::kParams; ++k) {
       prm[k] = __ldg(a.params + (a.pstride ? k * a.pstride + m : k));
@@ -99,19 +101,44 @@ struct FusedSrc {
     return f;
   }
 
-  // block row i needs cells i-1 .. i+1 of y; i-1 and i were touched by the previous rows, so the new data is cell i+1
   template <int SS>
-  __device__ __forceinline__ void prefetch(const sfxm_problem_t &P, int64_t i, int, int64_t m) const {
-    if (i + 1 >= P.nx) return;
-    if constexpr (Model::kDecoupled) {
+  __device__ __forceinline__ void prefetch(const sfxm_problem_t &, int64_t, int, int64_t) const {}   // see window()
+
+  // The state of cells i-1, i, i+1 (interior cell i) for the variables this source needs: the segment's own for
+  // decoupled models, all of them otherwise.  The sweep visits consecutive cells, so every cell is copied from HBM
+  // ONCE, kDF - 2 cells ahead of its first use, by cp.async into a per-thread ring in shared memory (slot = cell mod
+  // kDF); a jump in the cell sequence drains and re-primes the ring.
+  static constexpr int KV = Model::kDecoupled ? S : NV;
+  static constexpr int kDF = 8;
+  __device__ __forceinline__ const double *cell_ptr(const sfxm_problem_t &P, int64_t cell, int k, int64_t m) const {
+    const int j = Model::kDecoupled ? o + k : k;
+    return a.y + (P.var_base[j] + P.var_off[j] + cell * (int64_t)P.var_stride[j]) * P.batch + m;
+  }
+  __device__ __forceinline__ void window(const sfxm_problem_t &P, int64_t i, int64_t m, double (&w)[3][KV]) {
+    __shared__ double ring[kDF][KV][kThomasThreads];
+    const int tx = threadIdx.x;
+    auto issue = [&](int64_t cell) {        // one commit group per cell (empty beyond the mesh)
+      if (cell >= 0 && cell < P.nx) {
+        const int slot = (int)(cell & (kDF - 1));
 #pragma unroll
-      for (int cc = 0; cc < S; ++cc)
-        prefetch_l1(a.y + (P.var_base[o + cc] + P.var_off[o + cc] + (i + 1) * (int64_t)P.var_stride[o + cc]) * P.batch + m);
-    } else {
+        for (int k = 0; k < KV; ++k) cp_async8(&ring[slot][k][tx], cell_ptr(P, cell, k, m));
+      }
+      cp_async_commit();
+    };
+    if (i != seq_next) {
+      cp_async_wait<0>();                   // nothing of an earlier sequence may land after the re-prime
 #pragma unroll
-      for (int j = 0; j < NV; ++j)
-        prefetch_l1(a.y + (P.var_base[j] + P.var_off[j] + (i + 1) * (int64_t)P.var_stride[j]) * P.batch + m);
+      for (int k = -1; k <= kDF - 2; ++k) issue(i + k);
     }
+    cp_async_wait<kDF - 3>();               // cells <= i + 1 have landed
+#pragma unroll
+    for (int sl = 0; sl < 3; ++sl) {
+      const int slot = (int)((i - 1 + sl) & (kDF - 1));
+#pragma unroll
+      for (int k = 0; k < KV; ++k) w[sl][k] = ring[slot][k][tx];
+    }
+    issue(i + kDF - 1);                     // takes the slot of cell i - 1, read above
+    seq_next = i + 1;
   }
 
   __device__ __forceinline__ void prepare(const sfxm_problem_t &P, int64_t i, int64_t m) {
@@ -124,16 +151,15 @@ struct FusedSrc {
         // one scalar equation per variable (jac_column's decoupled branch): only the segment's own variables enter
         double us[S][3][1];
         int64_t off[S];
+        double w[3][KV];
+        window(P, i, m, w);
 #pragma unroll
         for (int cc = 0; cc < S; ++cc) {
-          const int64_t rs = (int64_t)P.var_stride[o + cc] * B;
-          off[cc] = (P.var_base[o + cc] + P.var_off[o + cc]) * B + m + i * rs;
-          const double *q = a.y + (off[cc] - rs);
+          off[cc] = (P.var_base[o + cc] + P.var_off[o + cc] + i * (int64_t)P.var_stride[o + cc]) * B + m;
 #pragma unroll
           for (int sl = 0; sl < 3; ++sl) {
-            us[cc][sl][0] = __ldg(q);
+            us[cc][sl][0] = w[sl][cc];
             ok = ok & sane(us[cc][sl][0], 120);
-            q += rs;
           }
         }
         if (ok) {
@@ -160,17 +186,12 @@ struct FusedSrc {
       } else {
         double u[3][NV];
         int64_t off[NV];
+        window(P, i, m, u);
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-          const int64_t rs = (int64_t)P.var_stride[j] * B;
-          off[j] = (P.var_base[j] + P.var_off[j]) * B + m + i * rs;
-          const double *q = a.y + (off[j] - rs);
+          off[j] = (P.var_base[j] + P.var_off[j] + i * (int64_t)P.var_stride[j]) * B + m;
 #pragma unroll
-          for (int sl = 0; sl < 3; ++sl) {
-            u[sl][j] = __ldg(q);
-            ok = ok & sane(u[sl][j], 120);
-            q += rs;
-          }
+          for (int sl = 0; sl < 3; ++sl) ok = ok & sane(u[sl][j], 120);
         }
         if (ok) {
           double r0[NV];
@@ -253,7 +274,7 @@ static int fused_launch_s(const FusedLaunch &L, int o, int cyclic) {
   double *workC = L.work;
   double *workR = L.work + P.nx * (int64_t)(NV * NV) * P.batch;
   // 32-thread CTAs: 65,536 members are 2048 warps = 13.8 per SM; small CTAs spread them evenly over the 148 SMs
-  const int threads = 32;
+  const int threads = kThomasThreads;
   const unsigned blocks = (unsigned)((P.batch + threads - 1) / threads);
   if (cyclic == 1)
     block_thomas_ll_kernel<Src, NV, S><<<blocks, threads, 0, L.st>>>(P, o, L.args, L.shift, L.active, L.s, workC, workR, L.status);

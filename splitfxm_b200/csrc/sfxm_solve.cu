@@ -58,7 +58,7 @@ static int launch_thomas(const sfxm_problem_t &P, int o, int cyclic, const doubl
                          cudaStream_t st) {
   double *workC = work;
   double *workR = work + P.nx * (int64_t)(NV * NV) * P.batch;
-  const int threads = P.batch >= 128 ? 128 : 32;
+  const int threads = kThomasThreads;   // one-warp CTAs: even spread over the SMs, thread-private cp.async rings
   const typename MemSrc<NV>::Args src{J, f};
   const unsigned blocks = (unsigned)((P.batch + threads - 1) / threads);
   if (cyclic == 1)   // lower-left corner only

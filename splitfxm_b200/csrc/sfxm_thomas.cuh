@@ -13,6 +13,22 @@ namespace sfxm {
 // the rows a later iteration needs are requested early: every iteration prefetches the rows kPrefetch<S> iterations
 // ahead into L1 (profile r1h: without it each iteration costs ~1500 cycles, one exposed HBM latency).
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// The back substitution re-reads the C' / rhs' rows the forward sweep wrote; its iterations are short (s^2 FMAs), so the
+// rows are fetched kRingDepth iterations ahead with cp.async into a per-thread ring in shared memory (thread-private
+// columns: no barrier needed, cp.async.wait_group orders the thread's own copies).  One-warp CTAs only.
+constexpr int kThomasThreads = 32;
+__device__ __forceinline__ void cp_async8(double *smem, const double *gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+template <int K>   // K doubles per row and thread
+struct RingDepth {
+  static constexpr int value = K <= 2 ? 8 : (K <= 12 ? 4 : 2);   // power of two; 32 threads x K x depth x 8 B <= 11 KB
+};
+
 template <int S>
 struct PrefetchDist {
   static constexpr int value = S == 1 ? 6 : (S == 2 ? 4 : 2);   // rows in flight x row size stays inside L1
@@ -73,7 +89,7 @@ __device__ __forceinline__ void load_block(const double *__restrict__ J, int64_t
 // Row source that reads an assembled banded Jacobian and residual from memory (sfxm_jacobian's layout).
 template <int NV>
 struct MemSrc {
-  static constexpr int kMaxThreads = 128, kMinCtas = 1;
+  static constexpr int kMaxThreads = kThomasThreads, kMinCtas = 1;
   struct Args {
     const double *J, *f;
   };
@@ -211,25 +227,41 @@ block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __gri
   for (int r = 0; r < S; ++r)
 #pragma unroll
     for (int c = 0; c < NR; ++c) Xlast[r][c] = X[r][c];
-  for (int64_t i = ne - 2; i >= 0; --i) {
-    double C[S][S], Rn[S][NR];
-    if (i >= PrefetchDist<S>::value) {
-      const int64_t ip = i - PrefetchDist<S>::value;
+  constexpr int KB = S * S + S * NR;
+  constexpr int DB = RingDepth<KB>::value;
+  __shared__ double ring[DB][KB][kThomasThreads];
+  const int tx = threadIdx.x;
+  auto issue = [&](int64_t row) {     // one commit group per call, empty past the first row: uniform group count
+    if (row >= 0) {
+      const int slot = (int)(row & (DB - 1));
 #pragma unroll
       for (int r = 0; r < S; ++r) {
 #pragma unroll
-        for (int c = 0; c < S; ++c) prefetch_l1(workC + (ip * (int64_t)(NV * NV) + (o + r) * NV + (o + c)) * B + m);
+        for (int c = 0; c < S; ++c)
+          cp_async8(&ring[slot][r * S + c][tx], workC + (row * (int64_t)(NV * NV) + (o + r) * NV + (o + c)) * B + m);
 #pragma unroll
-        for (int c = 0; c < NR; ++c) prefetch_l1(workR + ((ip * NV + (o + r)) * (int64_t)(1 + NV) + c) * B + m);
+        for (int c = 0; c < NR; ++c)
+          cp_async8(&ring[slot][S * S + r * NR + c][tx], workR + ((row * NV + (o + r)) * (int64_t)(1 + NV) + c) * B + m);
       }
     }
+    cp_async_commit();
+  };
 #pragma unroll
-    for (int r = 0; r < S; ++r) {
+  for (int k = 0; k < DB; ++k) issue(ne - 2 - k);
+  for (int64_t i = ne - 2; i >= 0; --i) {
+    double C[S][S], Rn[S][NR];
+    cp_async_wait<DB - 1>();          // the oldest group in flight (row i) has landed
+    {
+      const int slot = (int)(i & (DB - 1));
 #pragma unroll
-      for (int c = 0; c < S; ++c) C[r][c] = workC[(i * (int64_t)(NV * NV) + (o + r) * NV + (o + c)) * B + m];
+      for (int r = 0; r < S; ++r) {
 #pragma unroll
-      for (int c = 0; c < NR; ++c) Rn[r][c] = workR[((i * NV + (o + r)) * (int64_t)(1 + NV) + c) * B + m];
+        for (int c = 0; c < S; ++c) C[r][c] = ring[slot][r * S + c][tx];
+#pragma unroll
+        for (int c = 0; c < NR; ++c) Rn[r][c] = ring[slot][S * S + r * NR + c][tx];
+      }
     }
+    issue(i - DB);                    // refills the slot just read
 #pragma unroll
     for (int r = 0; r < S; ++r)
 #pragma unroll
@@ -412,24 +444,37 @@ block_thomas_ll_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __
   ok = gj_solve<S, 1>(Blast, X) && ok;
 #pragma unroll
   for (int r = 0; r < S; ++r) s_out[fidx(n - 1, r)] = X[r][0];
-  for (int64_t i = n - 2; i >= 0; --i) {
-    double Xn[S];
-    if (i >= PrefetchDist<S>::value) {
-      const int64_t ip = i - PrefetchDist<S>::value;
+  constexpr int KB = S * S + S;
+  constexpr int DB = RingDepth<KB>::value;
+  __shared__ double ring[DB][KB][kThomasThreads];
+  const int tx = threadIdx.x;
+  auto issue = [&](int64_t row) {
+    if (row >= 0) {
+      const int slot = (int)(row & (DB - 1));
 #pragma unroll
       for (int r = 0; r < S; ++r) {
-        prefetch_l1(workR + ((ip * NV + (o + r)) * (int64_t)(1 + NV)) * B + m);
+        cp_async8(&ring[slot][S * S + r][tx], workR + ((row * NV + (o + r)) * (int64_t)(1 + NV)) * B + m);
 #pragma unroll
-        for (int c = 0; c < S; ++c) prefetch_l1(workC + (ip * (int64_t)(NV * NV) + (o + r) * NV + (o + c)) * B + m);
+        for (int c = 0; c < S; ++c)
+          cp_async8(&ring[slot][r * S + c][tx], workC + (row * (int64_t)(NV * NV) + (o + r) * NV + (o + c)) * B + m);
       }
     }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int k = 0; k < DB; ++k) issue(n - 2 - k);
+  for (int64_t i = n - 2; i >= 0; --i) {
+    double Xn[S];
+    cp_async_wait<DB - 1>();
+    const int slot = (int)(i & (DB - 1));
 #pragma unroll
     for (int r = 0; r < S; ++r) {
-      double v = workR[((i * NV + (o + r)) * (int64_t)(1 + NV)) * B + m];
+      double v = ring[slot][S * S + r][tx];
 #pragma unroll
-      for (int c = 0; c < S; ++c) v -= workC[(i * (int64_t)(NV * NV) + (o + r) * NV + (o + c)) * B + m] * X[c][0];
+      for (int c = 0; c < S; ++c) v -= ring[slot][r * S + c][tx] * X[c][0];
       Xn[r] = v;
     }
+    issue(i - DB);
 #pragma unroll
     for (int r = 0; r < S; ++r) {
       X[r][0] = Xn[r];
