@@ -311,8 +311,9 @@ def run_gpu(args):
            "h2d_bytes_per_step": int(Y_host.numel() * 8), "d2h_bytes_per_step": int(Jh[0].numel() * 8),
            "steps": e2e_steps,
            "api": "EnsembleSimulation.jacobian_host(pinned host states -> pinned host Jacobians), 2 slots: the download "
-                  "of a step overlaps the upload + assembly of the next; same-segment entries only "
-                  f"({n_live} of {NV * NV} per block: the others do not exist in split mode)"}
+                  "of a step overlaps the upload + assembly of the next; only the entries the reference's sparse "
+                  f"matrix holds ({n_live} of {NV * NV} per block: same-segment entries, minus the exact zeros of the "
+                  "decoupled advection-diffusion equations)"}
     checksum = float(Jh[(e2e_steps - 1) % 2][:, 1, 0, :].sum())
     e2e["checksum_diag_u"] = checksum
     del Jh
@@ -487,7 +488,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--members", type=int, default=65536, help="ensemble members per GPU")
     ap.add_argument("--e2e-steps", type=int, default=6)
-    ap.add_argument("--cpu-sample", type=int, default=256)
+    ap.add_argument("--cpu-sample", type=int, default=10240, help="members the 1-core CPU baseline assembles (~10 s)")
     ap.add_argument("--ref-members", type=int, default=4096, help="members per step of the reference arm")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()

@@ -118,7 +118,9 @@ int sfxm_jacobian_segments(const sfxm_problem_t *prob, const double *x_int, cons
 
 /* Compact copy of a split Jacobian for the trip to the host: J_packed[((i*W + d)*L + e)*batch + m] holds the L
  * same-segment (r, c) entries of every block in row-major (r, c) order - the only entries Simulation.jacobian stores
- * in split mode (simulation.py:373-392).  *n_live_host receives L; with J == NULL the call only reports L. */
+ * in split mode (simulation.py:373-392).  For SFXM_MODEL_AD (one scalar equation per variable) only the r == c entries
+ * are kept: the others are exact zeros, which the reference's lil_matrix does not store either.  *n_live_host receives L;
+ * with J == NULL the call only reports L. */
 int sfxm_pack_jacobian(const sfxm_problem_t *prob, const double *J, double *J_packed, int32_t *n_live_host, void *stream);
 
 /* Solve, for every member and every variable segment, (J_seg + shift_m I) s = -f  with the block-tridiagonal

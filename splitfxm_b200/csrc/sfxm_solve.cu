@@ -134,9 +134,12 @@ extern "C" int sfxm_pack_jacobian(const sfxm_problem_t *prob, const double *J, d
   const sfxm_problem_t &P = *prob;
   PackMap map;
   map.L = 0;
+  // advection-diffusion: one scalar equation per variable, so the off-diagonal entries of a block are exact zeros -
+  // which the reference's lil_matrix never stores (simulation.py:357-392 assigns them, scipy drops zero assignments)
+  const bool decoupled = P.model == SFXM_MODEL_AD;
   for (int r = 0; r < P.nv; ++r)
     for (int c = 0; c < P.nv; ++c)
-      if (P.var_seg[r] == P.var_seg[c]) map.rc[map.L++] = r * P.nv + c;
+      if (P.var_seg[r] == P.var_seg[c] && (!decoupled || r == c)) map.rc[map.L++] = r * P.nv + c;
   *n_live_host = map.L;
   if (!J || !J_packed) return 0;     // query only
   const int64_t rows = P.nx * (P.nbl + P.nbr + 1);

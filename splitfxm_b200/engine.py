@@ -185,13 +185,17 @@ class Engine:
         return J
 
     def live_entries(self, split=False, split_locs=None):
-        """(r, c) pairs of a block that exist in this layout (same variable segment), row-major."""
+        """(r, c) pairs of a block that the reference's sparse matrix can hold in this layout, row-major: same
+        variable segment (simulation.py:373-392) and, for advection-diffusion, r == c (the other entries are exact
+        zeros, which lil_matrix drops)."""
         _, segs = self.problem(split, split_locs)
         seg_of = {}
         for k, (o, s) in enumerate(segs):
             for j in range(o, o + s):
                 seg_of[j] = k
-        return [(r, c) for r in range(self.nv) for c in range(self.nv) if seg_of[r] == seg_of[c]]
+        decoupled = self.model_id == _lib.MODEL_AD      # off-diagonal block entries are exact zeros (never stored)
+        return [(r, c) for r in range(self.nv) for c in range(self.nv)
+                if seg_of[r] == seg_of[c] and (r == c or not decoupled)]
 
     def pack_jacobian(self, J, split=False, split_locs=None, out=None):
         """-> [nx, W, L, batch] device tensor with the live entries only (sfxm_pack_jacobian)."""
