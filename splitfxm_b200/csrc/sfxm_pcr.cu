@@ -15,6 +15,7 @@
 // Traffic per pass and cell-member: 4 rows of (2 s^2 + s NR) doubles - HBM-bound streaming.
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 #include "../../include/sfxm_b200.h"
 #include "sfxm_host.h"
 #include "sfxm_pcr.cuh"
@@ -23,17 +24,12 @@ namespace sfxm {
 
 // J (banded, W = 3) + f -> normalised rows of the (condensed) system of ne = n or n-1 block rows
 template <int NV, int S, bool CYCLIC>
-__global__ void pcr_init_kernel(const __grid_constant__ sfxm_problem_t P, int o, const double *__restrict__ J,
-                                const double *__restrict__ f, const double *__restrict__ shift,
-                                double *__restrict__ w, int32_t *__restrict__ status) {
+__device__ __forceinline__ bool pcr_init_row(const sfxm_problem_t &P, int o, const double *__restrict__ J,
+                                             const double *__restrict__ f, double sh, int64_t i, int64_t m,
+                                             Row<S, CYCLIC ? 1 + S : 1> &row) {
   constexpr int NR = CYCLIC ? 1 + S : 1;
-  int64_t m, i;
-  pcr_coords(m, i);
   const int64_t B = P.batch, ne = CYCLIC ? P.nx - 1 : P.nx;
-  if (m >= B || i >= ne) return;
-  const double sh = shift ? shift[m] : 0.0;
   double Bd[S][S];
-  Row<S, NR> row;
   const double *p = J + (i * 3) * (int64_t)(NV * NV) * B + m;
 #pragma unroll
   for (int r = 0; r < S; ++r) {
@@ -49,8 +45,123 @@ __global__ void pcr_init_kernel(const __grid_constant__ sfxm_problem_t P, int o,
     const int64_t q = (P.var_base[o + r] + i * (int64_t)P.var_stride[o + r] + P.var_off[o + r]) * B + m;
     row.R[r][2 * S] = -__ldg(f + q);
   }
-  if (!gj_solve_pcr<S, 2 * S + NR>(Bd, row.R) && status) status[m] = 1;
+  return gj_solve_pcr<S, 2 * S + NR>(Bd, row.R);
+}
+
+template <int NV, int S, bool CYCLIC>
+__global__ void pcr_init_kernel(const __grid_constant__ sfxm_problem_t P, int o, const double *__restrict__ J,
+                                const double *__restrict__ f, const double *__restrict__ shift,
+                                double *__restrict__ w, int32_t *__restrict__ status) {
+  constexpr int NR = CYCLIC ? 1 + S : 1;
+  int64_t m, i;
+  pcr_coords(m, i);
+  const int64_t B = P.batch, ne = CYCLIC ? P.nx - 1 : P.nx;
+  if (m >= B || i >= ne) return;
+  Row<S, NR> row;
+  if (!pcr_init_row<NV, S, CYCLIC>(P, o, J, f, shift ? shift[m] : 0.0, i, m, row) && status) status[m] = 1;
   row.store(w, i, B, m);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small meshes: the whole reduction of one member in ONE launch, rows in shared memory.  The multi-launch path above
+// costs 2 + log2(n) launches per segment, which is all a Newton iteration on a few hundred cells consists of (launch-
+// bound: 0.13 ms per iteration at nx = 250).  One CTA per member, one thread per block row, the same row arithmetic
+// (pcr_init_row / pcr_combine), a barrier between reading the neighbours' rows and overwriting one's own.
+// ------------------------------------------------------------------------------------------------
+template <int NV, int S, bool CYCLIC>
+__global__ void __launch_bounds__(S <= 2 ? 1024 : 512)      // 64 / 128 registers: 3 x 3 rows spill badly at 64
+pcr_smem_kernel(const __grid_constant__ sfxm_problem_t P, int o, const double *__restrict__ J,
+                const double *__restrict__ f, const double *__restrict__ shift, const int32_t *__restrict__ active,
+                double *__restrict__ s_out, int32_t *__restrict__ status) {
+  constexpr int NR = CYCLIC ? 1 + S : 1;
+  constexpr int kRow = 2 * S * S + S * NR;
+  constexpr int kPitch = kRow | 1;
+  extern __shared__ double sm[];
+  const int64_t m = blockIdx.x, B = P.batch;
+  const int n = (int)P.nx, ne = CYCLIC ? n - 1 : n;
+  const int i = threadIdx.x;
+  const bool mine = i < ne;
+  const double sh = shift ? shift[m] : 0.0;
+  bool ok = true;
+  Row<S, NR> me;
+  if (mine) {
+    ok = pcr_init_row<NV, S, CYCLIC>(P, o, J, f, sh, i, m, me);
+    me.store_sm(sm, i, kPitch);
+  }
+  __syncthreads();
+  for (int h = 1; h < ne; h *= 2) {
+    double out[S][2 * S + NR];
+    if (mine) {
+      Row<S, NR> lo, hi;
+      const bool has_lo = i - h >= 0, has_hi = i + h < ne;
+      if (has_lo) lo.load_sm(sm, i - h, kPitch);
+      if (has_hi) hi.load_sm(sm, i + h, kPitch);
+      ok = pcr_combine<S, NR>(me, has_lo, lo, has_hi, hi, out) && ok;
+#pragma unroll
+      for (int r = 0; r < S; ++r)
+#pragma unroll
+        for (int c = 0; c < 2 * S + NR; ++c) me.R[r][c] = out[r][c];
+    }
+    __syncthreads();                       // every thread has read its neighbours' rows of this pass
+    if (mine) me.store_sm(sm, i, kPitch);
+    __syncthreads();
+  }
+  const bool write = !active || active[m];
+  auto q_of = [&](int64_t cell, int r) {
+    return (P.var_base[o + r] + cell * (int64_t)P.var_stride[o + r] + P.var_off[o + r]) * B + m;
+  };
+  if constexpr (!CYCLIC) {
+    if (mine && write) {
+#pragma unroll
+      for (int r = 0; r < S; ++r) s_out[q_of(i, r)] = me.R[r][2 * S];
+    }
+  } else {
+    // last block row: C_{n-1} x_0 + A_{n-1} x_{n-2} + B_{n-1} x_{n-1} = -f_{n-1},  x_i = q_i - Q_i x_{n-1}
+    double *xl = sm + (size_t)ne * kPitch;      // x_{n-1}, S doubles
+    if (i == 0) {
+      Row<S, NR> r0, rl;
+      r0.load_sm(sm, 0, kPitch);
+      rl.load_sm(sm, ne - 1, kPitch);
+      double A[S][S], Bd[S][S], C[S][S], rhs[S][1];
+      const double *p = J + ((int64_t)(n - 1) * 3) * (int64_t)(NV * NV) * B + m;
+#pragma unroll
+      for (int r = 0; r < S; ++r) {
+#pragma unroll
+        for (int c = 0; c < S; ++c) {
+          const int64_t e = (int64_t)((o + r) * NV + (o + c)) * B;
+          A[r][c] = __ldg(p + e);
+          Bd[r][c] = __ldg(p + (int64_t)(NV * NV) * B + e) + (r == c ? sh : 0.0);
+          C[r][c] = __ldg(p + (int64_t)(2 * NV * NV) * B + e);
+        }
+        rhs[r][0] = -__ldg(f + q_of(n - 1, r));
+      }
+#pragma unroll
+      for (int r = 0; r < S; ++r)
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+          rhs[r][0] -= C[r][k] * r0.R[k][2 * S] + A[r][k] * rl.R[k][2 * S];
+#pragma unroll
+          for (int c = 0; c < S; ++c) Bd[r][c] -= C[r][k] * r0.R[k][2 * S + 1 + c] + A[r][k] * rl.R[k][2 * S + 1 + c];
+        }
+      ok = gj_solve_pcr<S, 1>(Bd, rhs) && ok;
+#pragma unroll
+      for (int r = 0; r < S; ++r) {
+        xl[r] = rhs[r][0];
+        if (write) s_out[q_of(n - 1, r)] = rhs[r][0];
+      }
+    }
+    __syncthreads();
+    if (mine && write) {
+#pragma unroll
+      for (int r = 0; r < S; ++r) {
+        double xv = me.R[r][2 * S];
+#pragma unroll
+        for (int c = 0; c < S; ++c) xv -= me.R[r][2 * S + 1 + c] * xl[c];
+        s_out[q_of(i, r)] = xv;
+      }
+    }
+  }
+  if (!ok && status) status[m] = 1;
 }
 
 // non-cyclic: s = Dbar
@@ -142,12 +253,31 @@ __global__ void pcr_cyclic_fold_kernel(const __grid_constant__ sfxm_problem_t P,
   }
 }
 
+static bool smem_pcr_enabled() {     // SFXM_PCR_SMEM=0: always take the multi-launch path (tests compare the two)
+  const char *e = getenv("SFXM_PCR_SMEM");
+  return !(e && e[0] == '0');
+}
+
 template <int NV, int S, bool CYCLIC>
 static int pcr_solve_t(const sfxm_problem_t &P, int o, const double *J, const double *f, const double *shift,
                        const int32_t *active, double *s, double *work, int32_t *status, cudaStream_t st) {
   constexpr int NR = CYCLIC ? 1 + S : 1;
   constexpr int kRow = 2 * S * S + S * NR;
   const int64_t B = P.batch, ne = CYCLIC ? P.nx - 1 : P.nx;
+  // small meshes: one launch, rows in shared memory (one CTA per member)
+  const size_t smem = ((size_t)ne * (kRow | 1) + S) * sizeof(double);
+  if (ne <= (S <= 2 ? 1024 : 512) && smem <= 200 * 1024 && smem_pcr_enabled()) {
+    auto kern = pcr_smem_kernel<NV, S, CYCLIC>;
+    static bool configured = false;      // per instantiation
+    if (!configured) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        return set_error("sfxm_block_tridiag_solve_pcr: cannot raise the dynamic shared memory limit");
+      configured = true;
+    }
+    const int threads = (int)((ne + 31) / 32 * 32);
+    kern<<<(unsigned)B, threads, smem, st>>>(P, o, J, f, shift, active, s, status);
+    return check_launch("sfxm_block_tridiag_solve_pcr");
+  }
   double *w0 = work, *w1 = work + ne * kRow * B, *xlast = w1 + ne * kRow * B;
   dim3 b = pcr_block(B), g = pcr_grid(B, ne, b);
   if (g.y > 65535) return set_error("batch too large for the PCR solver (use the Thomas solver)");

@@ -60,6 +60,21 @@ struct Row {
 #pragma unroll
       for (int c = 0; c < 2 * S + NR; ++c) R[r][c] = __ldg(p + (int64_t)(r * (2 * S + NR) + c) * B);
   }
+  // shared-memory copy of the rows of ONE member: row i at sm + i * pitch (pitch odd: conflict-free row-per-thread access)
+  __device__ __forceinline__ void load_sm(const double *sm, int i, int pitch) {
+    const double *p = sm + i * pitch;
+#pragma unroll
+    for (int r = 0; r < S; ++r)
+#pragma unroll
+      for (int c = 0; c < 2 * S + NR; ++c) R[r][c] = p[r * (2 * S + NR) + c];
+  }
+  __device__ __forceinline__ void store_sm(double *sm, int i, int pitch) const {
+    double *p = sm + i * pitch;
+#pragma unroll
+    for (int r = 0; r < S; ++r)
+#pragma unroll
+      for (int c = 0; c < 2 * S + NR; ++c) p[r * (2 * S + NR) + c] = R[r][c];
+  }
   __device__ __forceinline__ void store(double *__restrict__ w, int64_t i, int64_t B, int64_t m) const {
     double *p = w + (i * kRow) * B + m;
 #pragma unroll
@@ -74,16 +89,11 @@ __device__ __forceinline__ void pcr_coords(int64_t &m, int64_t &i) {
   i = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
 }
 
+// one PCR pass for one row: [Abar | Cbar | Dbar] of row i from its own row and the rows h away (has_lo / has_hi: such a row exists)
 template <int S, int NR>
-__global__ void pcr_step_kernel(int64_t ne, int64_t B, int64_t h, const double *__restrict__ win,
-                                double *__restrict__ wout, int32_t *__restrict__ status) {
-  int64_t m, i;
-  pcr_coords(m, i);
-  if (m >= B || i >= ne) return;
-  Row<S, NR> me, nb;
-  me.load(win, i, B, m);
+__device__ __forceinline__ bool pcr_combine(const Row<S, NR> &me, bool has_lo, const Row<S, NR> &lo, bool has_hi,
+                                            const Row<S, NR> &hi, double (&out)[S][2 * S + NR]) {
   double Bd[S][S];
-  double out[S][2 * S + NR];
 #pragma unroll
   for (int r = 0; r < S; ++r) {
 #pragma unroll
@@ -95,8 +105,7 @@ __global__ void pcr_step_kernel(int64_t ne, int64_t B, int64_t h, const double *
 #pragma unroll
     for (int c = 0; c < NR; ++c) out[r][2 * S + c] = me.R[r][2 * S + c];
   }
-  if (i - h >= 0) {
-    nb.load(win, i - h, B, m);
+  if (has_lo) {
 #pragma unroll
     for (int r = 0; r < S; ++r)
 #pragma unroll
@@ -104,15 +113,14 @@ __global__ void pcr_step_kernel(int64_t ne, int64_t B, int64_t h, const double *
         const double a = me.R[r][k];                        // Abar_i
 #pragma unroll
         for (int c = 0; c < S; ++c) {
-          out[r][c] -= a * nb.R[k][c];                      // A' = -Abar_i Abar_{i-h}
-          Bd[r][c] -= a * nb.R[k][S + c];                   // B' -= Abar_i Cbar_{i-h}
+          out[r][c] -= a * lo.R[k][c];                     // A' = -Abar_i Abar_{i-h}
+          Bd[r][c] -= a * lo.R[k][S + c];                  // B' -= Abar_i Cbar_{i-h}
         }
 #pragma unroll
-        for (int c = 0; c < NR; ++c) out[r][2 * S + c] -= a * nb.R[k][2 * S + c];
+        for (int c = 0; c < NR; ++c) out[r][2 * S + c] -= a * lo.R[k][2 * S + c];
       }
   }
-  if (i + h < ne) {
-    nb.load(win, i + h, B, m);
+  if (has_hi) {
 #pragma unroll
     for (int r = 0; r < S; ++r)
 #pragma unroll
@@ -120,14 +128,29 @@ __global__ void pcr_step_kernel(int64_t ne, int64_t B, int64_t h, const double *
         const double g = me.R[r][S + k];                    // Cbar_i
 #pragma unroll
         for (int c = 0; c < S; ++c) {
-          out[r][S + c] -= g * nb.R[k][S + c];              // C' = -Cbar_i Cbar_{i+h}
-          Bd[r][c] -= g * nb.R[k][c];                       // B' -= Cbar_i Abar_{i+h}
+          out[r][S + c] -= g * hi.R[k][S + c];             // C' = -Cbar_i Cbar_{i+h}
+          Bd[r][c] -= g * hi.R[k][c];                      // B' -= Cbar_i Abar_{i+h}
         }
 #pragma unroll
-        for (int c = 0; c < NR; ++c) out[r][2 * S + c] -= g * nb.R[k][2 * S + c];
+        for (int c = 0; c < NR; ++c) out[r][2 * S + c] -= g * hi.R[k][2 * S + c];
       }
   }
-  if (!gj_solve_pcr<S, 2 * S + NR>(Bd, out) && status) status[m] = 1;
+  return gj_solve_pcr<S, 2 * S + NR>(Bd, out);
+}
+
+template <int S, int NR>
+__global__ void pcr_step_kernel(int64_t ne, int64_t B, int64_t h, const double *__restrict__ win,
+                                double *__restrict__ wout, int32_t *__restrict__ status) {
+  int64_t m, i;
+  pcr_coords(m, i);
+  if (m >= B || i >= ne) return;
+  Row<S, NR> me, lo, hi;
+  me.load(win, i, B, m);
+  const bool has_lo = i - h >= 0, has_hi = i + h < ne;
+  if (has_lo) lo.load(win, i - h, B, m);
+  if (has_hi) hi.load(win, i + h, B, m);
+  double out[S][2 * S + NR];
+  if (!pcr_combine<S, NR>(me, has_lo, lo, has_hi, hi, out) && status) status[m] = 1;
 #pragma unroll
   for (int r = 0; r < S; ++r)
 #pragma unroll

@@ -234,7 +234,8 @@ class Engine:
             nbytes = self.lib.sfxm_pcr_workspace_bytes(ctypes.byref(P))
             work = self._scratch("pcr", nbytes // 8)
             fn = self.lib.sfxm_block_tridiag_solve_pcr
-            _lib.count((seg_hi - seg_lo) * (2 + max(self.nx - 1, 1).bit_length()))
+            for k in range(seg_lo, seg_hi):
+                _lib.count(self._pcr_launches(P, segs[k]))
         _lib.check(fn(ctypes.byref(P), _lib.ptr(J), _lib.ptr(f), _lib.ptr(shift), _lib.ptr(active), int(seg_lo), int(seg_hi),
                       _lib.ptr(s), _lib.ptr(work), _lib.ptr(status), _lib.stream_ptr()))
         return s
@@ -257,6 +258,19 @@ class Engine:
                                                     _lib.ptr(work), _lib.ptr(status), _lib.stream_ptr()))
         _lib.count()
         return s
+
+    def _pcr_launches(self, P, seg):
+        """Kernel launches of one PCR segment solve: 1 when the rows fit in shared memory (csrc/sfxm_pcr.cu
+        pcr_smem_kernel), else init + ceil(log2 n) passes + write-back (+ 1 for the cyclic closure)."""
+        import os
+        o, S = seg
+        cyclic = any(P.bc_ltype[j] == _lib.BC_PERIODIC or P.bc_rtype[j] == _lib.BC_PERIODIC for j in range(o, o + S))
+        ne = self.nx - 1 if cyclic else self.nx
+        row = 2 * S * S + S * ((1 + S) if cyclic else 1)
+        smem = (ne * (row | 1) + S) * 8
+        if ne <= (1024 if S <= 2 else 512) and smem <= 200 * 1024 and os.environ.get("SFXM_PCR_SMEM", "1")[:1] != "0":
+            return 1
+        return 2 + max(ne - 1, 1).bit_length() + (1 if cyclic else 0)
 
     def sumsq(self, v, lo=0, hi=None, out=None):
         if hi is None:

@@ -274,3 +274,36 @@ def test_ensemble_newton_fused_equals_unfused():
         assert drv_a.fused and not drv_b.fused
         ita, itb = drv_a.run(ya), drv_b.run(yb)
         assert torch.equal(ita, itb) and torch.equal(ya, yb)
+
+
+@pytest.mark.parametrize("name,split,locs", [
+    ("ad_fvm_lf_nx40_mixedbc", False, None),
+    ("ad_fvm_lf_nonuniform", True, [1, 2]),
+    ("ad_fdm_central_nx250_split1", True, [1]),
+    ("sod_cons_nx100_t0p05", False, None),
+])
+def test_pcr_one_launch_shared_memory_equals_multi_launch(name, split, locs, monkeypatch):
+    """Small meshes take the one-launch PCR with the rows in shared memory; it runs the same row arithmetic as the
+    multi-launch passes, so the two agree bit for bit (batch 1 and a small ensemble)."""
+    import torch
+    from oracle import core
+    z = load(name)
+    s, d, m = product_simulation(z)
+    eng = s._engine()
+    y = eng.to_device(core.to_flat(core.to_block(z["x0"], m["nx"], len(m["comps"]), m["split"], m["locs"]), split, locs))
+    r = torch.empty_like(y)
+    J = eng.jacobian(y, split, locs, r0=r)
+    shift = torch.full((1,), -3.0, dtype=torch.float64, device=y.device)
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SFXM_PCR_SMEM", flag)
+        sol = torch.zeros_like(y)
+        status = torch.zeros(1, dtype=torch.int32, device=y.device)
+        from splitfxm_b200 import _lib
+        before = _lib.LAUNCHES[0]
+        eng.solve(J, r, sol, split, locs, shift=shift, status=status, method="pcr")
+        out[flag] = (sol, _lib.LAUNCHES[0] - before)
+        assert int(status[0]) == 0
+    assert torch.equal(out["0"][0], out["1"][0])
+    _, segs = eng.problem(split, locs)
+    assert out["1"][1] == len(segs) and out["0"][1] > 5 * len(segs)
