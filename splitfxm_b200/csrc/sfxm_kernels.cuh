@@ -563,6 +563,10 @@ jacobian_pair_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
   }
 }
 
+// (A per-variable variant for decoupled models - one warp per (cell, variable), two members per lane, 64-96 registers,
+// 20-32 one-warp CTAs per SM instead of 16 - was tried to get more resident warps: bit-identical, but 0.63-0.67 ms
+// against 0.57 ms on the bench shape at every register setting (the per-warp set-up - geometry row, parameters,
+// addresses, sanity check - is paid three times and more warps did not buy overlap); removed.)
 // (A strip variant - the warp walks several cells with the stencil as a sliding register window and prefetches the
 // next cell's slot before evaluating the current one - was tried to overlap the load, compute and store phases: the
 // loop body needs > 255 registers, spills, and runs at 0.77 ms against 0.57 ms for one cell per CTA; removed.)
