@@ -267,7 +267,9 @@ def run_gpu(args):
     # ---- roofline of the Jacobian kernel (this rank's launches) ------------------------------------
     # algorithmic bytes per launch: read U (nv*8 per cell-member) + x (8 per cell, shared by members), write the
     # same-segment entries of the band: split [1] -> segments of 1 and 2 variables -> (1 + 4) * W entries
-    seg_entries = sum(s * s for s in (LOCS[0], NV - LOCS[0]))
+    # (advection-diffusion is one scalar equation per variable: the off-diagonal same-segment entries are structural
+    # zeros, zero-filled once and never written - only the NV diagonal entries of each block are stored)
+    seg_entries = NV
     alg_bytes = B * NX * (NV * 8 + W * seg_entries * 8) + NX * 8
     kern_ms = float(np.mean(per_launch_ms))
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")

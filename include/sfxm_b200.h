@@ -104,7 +104,9 @@ int sfxm_fill_domain(const sfxm_problem_t *prob, const double *x_int, const doub
 
 /* Block-banded finite-difference Jacobian; all perturbations in one pass.  Replaces Simulation.jacobian
  * (simulation.py:270-394) incl. get_periodic_bcs / extend_band (bc.py:162-240).  Split mode writes
- * same-segment entries only (simulation.py:373-392); the others are left untouched (keep J zero-filled).
+ * same-segment entries only (simulation.py:373-392); the others are left untouched (keep J zero-filled).  The same holds
+ * for the off-diagonal block entries of SFXM_MODEL_AD (one scalar equation per variable): they are exact zeros in the
+ * reference too and are never written - J must be zero-filled once by its owner.
  * r0 (optional) receives the unperturbed residual in flat order. */
 int sfxm_jacobian(const sfxm_problem_t *prob, const double *x_int, const double *params, int64_t param_stride,
                   const double *geom, const double *y, double eps, double *J, double *r0, void *stream);

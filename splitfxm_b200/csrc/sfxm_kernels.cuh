@@ -297,6 +297,16 @@ __device__ __forceinline__ constexpr uint32_t column_bits(int c) {
   return b;
 }
 
+// Entries of a block that are ever written.  A decoupled model (one scalar equation per variable) has exact zeros off
+// the diagonal of every block - the reference computes them and its lil_matrix drops them (simulation.py:354-392) - so
+// they are structural: J buffers are zero-filled once by their owner (include/sfxm_b200.h) and these entries are never
+// touched.  That is 40 % of the stores of the bench shape, and the store path out of the SMs is what binds the assembly
+// kernel (profile r1g: l1tex->xbar write bytes at 74 % of peak with DRAM at 51 %).
+template <class Model>
+__device__ __forceinline__ constexpr bool stored_entry(int r, int c) {
+  return !Model::kDecoupled || r == c;
+}
+
 // One perturbed evaluation: column c of the stencil is `upc`, everything else is the base state.
 // Returns (r(u + eps e) - r0) / eps for every row (decoupled models: only row c can be non-zero).
 template <class Model, int SCHEME, int NV, int W, bool FAST>
@@ -362,7 +372,7 @@ __device__ __forceinline__ void jacobian_cell(const sfxm_problem_t &P, const dou
       for (int r = 0; r < NV; ++r)
 #pragma unroll
         for (int c = 0; c < NV; ++c) {
-          if (entry_mask & (1u << (r * NV + c))) *p = cols[c][r];
+          if (stored_entry<Model>(r, c) && (entry_mask & (1u << (r * NV + c)))) *p = cols[c][r];
           p += B;
         }
     }
@@ -408,7 +418,7 @@ __device__ __forceinline__ void jacobian_cell(const sfxm_problem_t &P, const dou
     for (int r = 0; r < NV; ++r)
 #pragma unroll
       for (int c = 0; c < NV; ++c) {
-        if (entry_mask & (1u << (r * NV + c))) *p = cols[c][r];
+        if (stored_entry<Model>(r, c) && (entry_mask & (1u << (r * NV + c)))) *p = cols[c][r];
         p += B;
       }
   }
@@ -557,7 +567,8 @@ jacobian_pair_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
     for (int r = 0; r < NV; ++r)
 #pragma unroll
       for (int c = 0; c < NV; ++c) {
-        if (entry_mask & (1u << (r * NV + c))) *reinterpret_cast<double2 *>(p) = make_double2(cols[0][c][r], cols[1][c][r]);
+        if (stored_entry<Model>(r, c) && (entry_mask & (1u << (r * NV + c))))
+          *reinterpret_cast<double2 *>(p) = make_double2(cols[0][c][r], cols[1][c][r]);
         p += B;
       }
   }
@@ -612,13 +623,13 @@ __device__ __forceinline__ void jacobian_scalar_cell(const sfxm_problem_t &P, co
                                                      const Geom<SCHEME, W> &geom, double eps, double r0,
                                                      double *__restrict__ p, int nv, uint32_t row_mask) {
   // p: entry (d = 0, r = j, c = 0) of this cell/member; row j of block d is at p + (d*nv*nv + c) * B.
-  // Writes the diagonal entry and the exact zeros of the other same-segment columns (row_mask bit c).
+  // Writes the diagonal entry (the off-diagonal entries of a decoupled model are structural zeros: never written,
+  // see stored_entry).
   const int64_t B = P.batch;
   const double reps = 1.0 / eps;
   auto emit = [&](int d, double val) {
     double *q = p + (int64_t)d * (nv * nv) * B;
-    for (int c = 0; c < nv; ++c)
-      if (row_mask & (1u << c)) q[(int64_t)c * B] = (c == j) ? val : 0.0;
+    if (row_mask & (1u << j)) q[(int64_t)j * B] = val;
   };
   if (interior) {
 #pragma unroll
