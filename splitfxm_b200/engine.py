@@ -259,13 +259,17 @@ class Engine:
         _lib.count()
         return s
 
-    def _pcr_launches(self, P, seg):
-        """Kernel launches of one PCR segment solve: 1 when the rows fit in shared memory (csrc/sfxm_pcr.cu
-        pcr_smem_kernel), else init + ceil(log2 n) passes + write-back (+ 1 for the cyclic closure)."""
+    def _pcr_launches(self, P, seg, n=None):
+        """Kernel launches of one PCR segment solve (csrc/sfxm_pcr.cu): 1 when the rows fit in shared memory
+        (pcr_smem_kernel); large meshes: chunk reduce + separator rows + fold around the solve of the nx / 256
+        separator system; otherwise init + ceil(log2 n) passes + write-back (+ 1 for the cyclic closure)."""
         import os
         o, S = seg
+        n = self.nx if n is None else n
+        if n >= 8 * 256 and os.environ.get("SFXM_PCR_CHUNKED", "1")[:1] != "0":
+            return 3 + self._pcr_launches(P, seg, (n + 255) // 256)
         cyclic = any(P.bc_ltype[j] == _lib.BC_PERIODIC or P.bc_rtype[j] == _lib.BC_PERIODIC for j in range(o, o + S))
-        ne = self.nx - 1 if cyclic else self.nx
+        ne = n - 1 if cyclic else n
         row = 2 * S * S + S * ((1 + S) if cyclic else 1)
         smem = (ne * (row | 1) + S) * 8
         if ne <= (1024 if S <= 2 else 512) and smem <= 200 * 1024 and os.environ.get("SFXM_PCR_SMEM", "1")[:1] != "0":
