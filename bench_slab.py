@@ -68,7 +68,7 @@ def newton_on_slabs(args, rank, world, dev):
 
     out = {}
     # -- parity on a small mesh
-    nx, split, locs = 3000, True, [1, 2]
+    nx, split, locs = 20000, True, [1, 2]        # slabs of >= 2048 cells up to 8 ranks: the nested-dissection path
     d, sim, slab = setup(nx)
     U0 = d.values(interior=True).copy()
     y = slab.eng.to_device(to_flat(U0[slab.lo:slab.hi], split, locs))

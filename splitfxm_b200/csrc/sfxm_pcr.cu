@@ -254,242 +254,15 @@ __global__ void pcr_cyclic_fold_kernel(const __grid_constant__ sfxm_problem_t P,
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// Large meshes: one level of nested dissection around the shared-memory PCR.  Plain PCR streams 4 rows per cell
-// through HBM ceil(log2 n) times (nx = 1e6: 20 passes, ~13 KB per cell for 264 algorithmic bytes).  Instead every
-// kL-th cell is a SEPARATOR; the kL - 1 cells between two separators form a chunk that one CTA reduces entirely in
-// shared memory, carrying 1 + 2 s right-hand sides [ -f | coupling to the left separator | to the right separator ]:
-//       x_i = q_i - V_i x_sepL - W_i x_sepR                          (chunk_reduce_kernel: J read once, rows written once)
-// Substituting the two cells next to a separator into its own block row gives a block-tridiagonal system of the
-// SAME form in the separator unknowns only (separator_kernel), cyclic exactly when the original is - it is written in
-// the banded layout of sfxm_jacobian and handed back to this solver (n / kL rows: shared memory or a few short
-// passes).  chunk_fold_kernel then evaluates the chunk cells.  O(n) traffic: ~75 doubles per cell for s = 3.
-// ------------------------------------------------------------------------------------------------
-constexpr int kChunkPeriod = 256;   // separators at cells 0, 256, 512, ...; chunks of <= 255 cells, one thread each
-
-// rows[((cell * S + r) * (1 + 2 S) + c) * B + m]: (q | V | W) of a chunk cell
-template <int NV, int S>
-__global__ void __launch_bounds__(kChunkPeriod)
-chunk_reduce_kernel(const __grid_constant__ sfxm_problem_t P, int o, const double *__restrict__ J,
-                    const double *__restrict__ f, const double *__restrict__ shift, double *__restrict__ rows,
-                    int32_t *__restrict__ status) {
-  constexpr int NR = 1 + 2 * S;
-  constexpr int NC = 2 * S + NR;
-  constexpr int kPitch = (S * NC) | 1;
-  extern __shared__ double sm[];
-  const int64_t k = blockIdx.x, m = blockIdx.y, B = P.batch, n = P.nx;
-  const int64_t first = k * kChunkPeriod + 1;                         // first chunk cell
-  const int nloc = (int)((n - first) < (kChunkPeriod - 1) ? (n - first) : (kChunkPeriod - 1));
-  if (nloc <= 0) return;
-  const int i = threadIdx.x;
-  const bool mine = i < nloc;
-  const int64_t cell = first + i;
-  const double sh = shift ? shift[m] : 0.0;
-  bool ok = true;
-  Row<S, NR> me;
-  if (mine) {
-    double Bd[S][S];
-    const double *p = J + (cell * 3) * (int64_t)(NV * NV) * B + m;
-#pragma unroll
-    for (int r = 0; r < S; ++r) {
-#pragma unroll
-      for (int c = 0; c < S; ++c) {
-        const int64_t e = (int64_t)((o + r) * NV + (o + c)) * B;
-        const double a = __ldg(p + e), b = __ldg(p + (int64_t)(NV * NV) * B + e), cc = __ldg(p + (int64_t)(2 * NV * NV) * B + e);
-        Bd[r][c] = b + (r == c ? sh : 0.0);
-        me.R[r][c] = (i == 0) ? 0.0 : a;
-        me.R[r][S + c] = (i == nloc - 1) ? 0.0 : cc;
-        me.R[r][2 * S + 1 + c] = (i == 0) ? a : 0.0;                  // coupling to the separator on the left
-        me.R[r][2 * S + 1 + S + c] = (i == nloc - 1) ? cc : 0.0;      // ... on the right (cell n-1: the wrap block)
-      }
-      const int64_t q = (P.var_base[o + r] + cell * (int64_t)P.var_stride[o + r] + P.var_off[o + r]) * B + m;
-      me.R[r][2 * S] = -__ldg(f + q);
-    }
-    ok = gj_solve_pcr<S, NC>(Bd, me.R);
-    me.store_sm(sm, i, kPitch);
-  }
-  __syncthreads();
-  for (int h = 1; h < nloc; h *= 2) {
-    double out[S][NC];
-    if (mine) {
-      Row<S, NR> lo, hi;
-      const bool has_lo = i - h >= 0, has_hi = i + h < nloc;
-      if (has_lo) lo.load_sm(sm, i - h, kPitch);
-      if (has_hi) hi.load_sm(sm, i + h, kPitch);
-      ok = pcr_combine<S, NR>(me, has_lo, lo, has_hi, hi, out) && ok;
-#pragma unroll
-      for (int r = 0; r < S; ++r)
-#pragma unroll
-        for (int c = 0; c < NC; ++c) me.R[r][c] = out[r][c];
-    }
-    __syncthreads();
-    if (mine) me.store_sm(sm, i, kPitch);
-    __syncthreads();
-  }
-  if (mine) {
-    double *w = rows + (cell * S) * (int64_t)NR * B + m;
-#pragma unroll
-    for (int r = 0; r < S; ++r)
-#pragma unroll
-      for (int c = 0; c < NR; ++c) w[(int64_t)(r * NR + c) * B] = me.R[r][2 * S + c];
-  }
-  if (!ok && status) status[m] = 1;
-}
-
-// block row of separator k in the reduced system, in the banded layout [(k * 3 + d) * NV * NV + r * NV + c] * B + m,
-// and fr = -(right-hand side) in the reduced flat layout (Pr)
-template <int NV, int S>
-__global__ void separator_kernel(const __grid_constant__ sfxm_problem_t P, const __grid_constant__ sfxm_problem_t Pr, int o,
-                                 const double *__restrict__ J, const double *__restrict__ f,
-                                 const double *__restrict__ shift, const double *__restrict__ rows,
-                                 double *__restrict__ Jr, double *__restrict__ fr) {
-  constexpr int NR = 1 + 2 * S;
-  const int64_t m = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
-  const int64_t k = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
-  const int64_t B = P.batch, n = P.nx, np = Pr.nx;
-  if (m >= B || k >= np) return;
-  const int64_t cell = k * kChunkPeriod;
-  const double sh = shift ? shift[m] : 0.0;
-  double A[S][S], Bd[S][S], C[S][S], Ar[S][S], Cr[S][S], rhs[S];
-  const double *p = J + (cell * 3) * (int64_t)(NV * NV) * B + m;
-#pragma unroll
-  for (int r = 0; r < S; ++r) {
-#pragma unroll
-    for (int c = 0; c < S; ++c) {
-      const int64_t e = (int64_t)((o + r) * NV + (o + c)) * B;
-      A[r][c] = __ldg(p + e);
-      Bd[r][c] = __ldg(p + (int64_t)(NV * NV) * B + e) + (r == c ? sh : 0.0);
-      C[r][c] = __ldg(p + (int64_t)(2 * NV * NV) * B + e);
-      Ar[r][c] = 0.0;
-      Cr[r][c] = 0.0;
-    }
-    rhs[r] = -__ldg(f + (P.var_base[o + r] + cell * (int64_t)P.var_stride[o + r] + P.var_off[o + r]) * B + m);
-  }
-  const int64_t left = (cell + n - 1) % n, right = (cell + 1) % n;
-  if (left % kChunkPeriod == 0) {            // the neighbour is itself a separator (last cell of the mesh)
-#pragma unroll
-    for (int r = 0; r < S; ++r)
-#pragma unroll
-      for (int c = 0; c < S; ++c) Ar[r][c] = A[r][c];
-  } else {                                   // x_left = q - V x_sep(k-1) - W x_sep(k)
-    const double *w = rows + (left * S) * (int64_t)NR * B + m;
-#pragma unroll
-    for (int r = 0; r < S; ++r)
-#pragma unroll
-      for (int t = 0; t < S; ++t) {
-        const double a = A[r][t];
-        rhs[r] -= a * w[(int64_t)(t * NR) * B];
-#pragma unroll
-        for (int c = 0; c < S; ++c) {
-          Ar[r][c] -= a * w[(int64_t)(t * NR + 1 + c) * B];
-          Bd[r][c] -= a * w[(int64_t)(t * NR + 1 + S + c) * B];
-        }
-      }
-  }
-  if (right % kChunkPeriod == 0) {
-#pragma unroll
-    for (int r = 0; r < S; ++r)
-#pragma unroll
-      for (int c = 0; c < S; ++c) Cr[r][c] = C[r][c];
-  } else {                                   // x_right = q - V x_sep(k) - W x_sep(k+1)
-    const double *w = rows + (right * S) * (int64_t)NR * B + m;
-#pragma unroll
-    for (int r = 0; r < S; ++r)
-#pragma unroll
-      for (int t = 0; t < S; ++t) {
-        const double g = C[r][t];
-        rhs[r] -= g * w[(int64_t)(t * NR) * B];
-#pragma unroll
-        for (int c = 0; c < S; ++c) {
-          Bd[r][c] -= g * w[(int64_t)(t * NR + 1 + c) * B];
-          Cr[r][c] -= g * w[(int64_t)(t * NR + 1 + S + c) * B];
-        }
-      }
-  }
-  double *q = Jr + (k * 3) * (int64_t)(NV * NV) * B + m;
-#pragma unroll
-  for (int r = 0; r < S; ++r) {
-#pragma unroll
-    for (int c = 0; c < S; ++c) {
-      const int64_t e = (int64_t)((o + r) * NV + (o + c)) * B;
-      q[e] = Ar[r][c];
-      q[(int64_t)(NV * NV) * B + e] = Bd[r][c];
-      q[(int64_t)(2 * NV * NV) * B + e] = Cr[r][c];
-    }
-    fr[(Pr.var_base[o + r] + k * (int64_t)Pr.var_stride[o + r] + Pr.var_off[o + r]) * B + m] = -rhs[r];
-  }
-}
-
-template <int S>
-__global__ void chunk_fold_kernel(const __grid_constant__ sfxm_problem_t P, const __grid_constant__ sfxm_problem_t Pr, int o,
-                                  const double *__restrict__ rows, const double *__restrict__ xr,
-                                  const int32_t *__restrict__ active, double *__restrict__ s_out) {
-  constexpr int NR = 1 + 2 * S;
-  int64_t m, i;
-  pcr_coords(m, i);
-  const int64_t B = P.batch, np = Pr.nx;
-  if (m >= B || i >= P.nx) return;
-  if (active && !active[m]) return;
-  const int64_t k = i / kChunkPeriod;
-  auto sep = [&](int64_t kk, int r) {
-    return __ldg(xr + (Pr.var_base[o + r] + kk * (int64_t)Pr.var_stride[o + r] + Pr.var_off[o + r]) * B + m);
-  };
-  double xl[S], xh[S];
-#pragma unroll
-  for (int r = 0; r < S; ++r) {
-    xl[r] = sep(k, r);
-    xh[r] = sep((k + 1) % np, r);
-  }
-  const bool is_sep = (i % kChunkPeriod) == 0;
-  const double *w = rows + (i * S) * (int64_t)NR * B + m;
-#pragma unroll
-  for (int r = 0; r < S; ++r) {
-    double xv = xl[r];
-    if (!is_sep) {
-      xv = w[(int64_t)(r * NR) * B];
-#pragma unroll
-      for (int c = 0; c < S; ++c) xv -= w[(int64_t)(r * NR + 1 + c) * B] * xl[c] + w[(int64_t)(r * NR + 1 + S + c) * B] * xh[c];
-    }
-    s_out[(P.var_base[o + r] + i * (int64_t)P.var_stride[o + r] + P.var_off[o + r]) * B + m] = xv;
-  }
-}
-
-static bool chunked_pcr_enabled() {    // SFXM_PCR_CHUNKED=0: plain multi-pass PCR for every size (tests compare the two)
-  const char *e = getenv("SFXM_PCR_CHUNKED");
-  return !(e && e[0] == '0');
-}
-
 template <int NV, int S>
 static int chunked_solve_t(const sfxm_problem_t &P, int o, int seg, const double *J, const double *f, const double *shift,
                            const int32_t *active, double *s, double *work, int32_t *status, cudaStream_t st) {
-  constexpr int NR = 1 + 2 * S;
-  const int64_t B = P.batch, n = P.nx;
-  const int64_t np = (n + kChunkPeriod - 1) / kChunkPeriod;
-  sfxm_problem_t Pr = P;                   // the separator system: same variables, segments and BC types, np "cells"
-  Pr.nx = np;
-  for (int j = 0; j < P.nv; ++j) Pr.var_base[j] = (P.var_base[j] / n) * np;      // var_base = (segment offset) * nx
-  double *rows = work;
-  double *Jr = rows + n * (int64_t)(S * NR) * B;
-  double *fr = Jr + np * 3 * (int64_t)(NV * NV) * B;
-  double *xr = fr + np * (int64_t)NV * B;
-  double *work_r = xr + np * (int64_t)NV * B;
-  constexpr size_t smem = (size_t)(kChunkPeriod - 1) * ((S * (2 * S + NR)) | 1) * sizeof(double);
-  auto kern = chunk_reduce_kernel<NV, S>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return set_error("sfxm_block_tridiag_solve_pcr: cannot raise the dynamic shared memory limit");
-    configured = true;
-  }
-  if (B > 65535) return set_error("batch too large for the PCR solver (use the Thomas solver)");
-  kern<<<dim3((unsigned)np, (unsigned)B), kChunkPeriod, smem, st>>>(P, o, J, f, shift, rows, status);
-  dim3 b = pcr_block(B);
-  separator_kernel<NV, S><<<pcr_grid(B, np, b), b, 0, st>>>(P, Pr, o, J, f, shift, rows, Jr, fr);
-  if (int e = check_launch("sfxm_block_tridiag_solve_pcr")) return e;
+  const ChunkLayout L = chunk_layout(P, S, false, work);
+  if (int e = chunk_reduce_launch<NV, S>(P, L, o, J, f, shift, status, st)) return e;
   // the separator system has the form of the original one: solve it with this very solver (the shift is already in it)
-  if (int e = sfxm_block_tridiag_solve_pcr(&Pr, Jr, fr, nullptr, nullptr, seg, seg + 1, xr, work_r, status, (void *)st)) return e;
-  chunk_fold_kernel<S><<<pcr_grid(B, n, b), b, 0, st>>>(P, Pr, o, rows, xr, active, s);
-  return check_launch("sfxm_block_tridiag_solve_pcr");
+  if (int e = sfxm_block_tridiag_solve_pcr(&L.Pr, L.Jr, L.fr, nullptr, nullptr, seg, seg + 1, L.xr, L.work_r, status, (void *)st))
+    return e;
+  return chunk_fold_launch<S>(P, L, o, active, s, st);
 }
 
 static bool smem_pcr_enabled() {     // SFXM_PCR_SMEM=0: always take the multi-launch path (tests compare the two)
@@ -538,7 +311,7 @@ template <int NV>
 static int pcr_nv(const sfxm_problem_t &P, int o, int seg, int S, bool cyc, const double *J, const double *f,
                   const double *shift, const int32_t *active, double *s, double *work, int32_t *status, cudaStream_t st) {
   // large meshes: one level of nested dissection (the separator system comes back here with nx / 256 rows)
-  if (P.nx >= 8 * kChunkPeriod && chunked_pcr_enabled()) {
+  if (chunked_applies(P)) {
 #define SFXM_CHUNK_CASE(SS)                                                                                         \
   if constexpr (NV >= SS) {                                                                                         \
     if (S == SS) return chunked_solve_t<NV, SS>(P, o, seg, J, f, shift, active, s, work, status, st);               \

@@ -154,6 +154,27 @@ static double *spike_final(double *work, int64_t n, int64_t row, int64_t B) {
   return (passes & 1) ? work + n * row * B : work;
 }
 
+// Large slabs: nested dissection as in sfxm_pcr.cu, with the slab's first AND last cell among the separators.  The
+// chunk reduction carries nothing extra: the coupling blocks to the neighbouring slabs sit in the wrap slots of cells 0
+// and n - 1, which are separators, so they turn up as the wrap slots of the separator system - a system of the same
+// form as the slab's own, np = n / 256 rows, that is handed back to sfxm_spike_reduce.  Its interface rows ARE the
+// slab's interface rows; sfxm_spike_fold folds the separator values, then the chunk cells.
+template <int NV, int S>
+static int spike_reduce_chunked(const sfxm_problem_t &P, int o, int seg, const double *J, const double *f,
+                                const double *shift, double *work, double *iface, int32_t *status, cudaStream_t st) {
+  const ChunkLayout L = chunk_layout(P, S, true, work);
+  if (int e = chunk_reduce_launch<NV, S>(P, L, o, J, f, shift, status, st)) return e;
+  return sfxm_spike_reduce(&L.Pr, L.Jr, L.fr, nullptr, seg, L.work_r, iface, status, (void *)st);
+}
+
+template <int S>
+static int spike_fold_chunked(const sfxm_problem_t &P, int o, int seg, double *work, const double *nbr,
+                              const int32_t *active, double *s, cudaStream_t st) {
+  const ChunkLayout L = chunk_layout(P, S, true, work);
+  if (int e = sfxm_spike_fold(&L.Pr, seg, L.work_r, nbr, nullptr, L.xr, (void *)st)) return e;
+  return chunk_fold_launch<S>(P, L, o, active, s, st);
+}
+
 template <int NV, int S>
 static int spike_reduce_t(const sfxm_problem_t &P, int o, const double *J, const double *f, const double *shift,
                           double *work, double *iface, int32_t *status, cudaStream_t st) {
@@ -215,7 +236,9 @@ extern "C" int sfxm_spike_reduce(const sfxm_problem_t *prob, const double *J, co
   if (!segment_of(P, seg, o, S)) return set_error("sfxm_spike_reduce: empty segment");
   cudaStream_t st = (cudaStream_t)stream;
 #define SFXM_SPIKE_CASE(NVV, SS)                                                                                    \
-  if (P.nv == NVV && S == SS) return spike_reduce_t<NVV, SS>(P, o, J, f, shift, work, iface, status, st);
+  if (P.nv == NVV && S == SS)                                                                                       \
+    return chunked_applies(P) ? spike_reduce_chunked<NVV, SS>(P, o, seg, J, f, shift, work, iface, status, st)     \
+                              : spike_reduce_t<NVV, SS>(P, o, J, f, shift, work, iface, status, st);
   SFXM_SPIKE_CASE(1, 1)
   SFXM_SPIKE_CASE(2, 1) SFXM_SPIKE_CASE(2, 2)
   SFXM_SPIKE_CASE(3, 1) SFXM_SPIKE_CASE(3, 2) SFXM_SPIKE_CASE(3, 3)
@@ -231,11 +254,12 @@ extern "C" int sfxm_spike_fold(const sfxm_problem_t *prob, int32_t seg, double *
   int o, S;
   if (!segment_of(P, seg, o, S)) return set_error("sfxm_spike_fold: empty segment");
   cudaStream_t st = (cudaStream_t)stream;
+  const bool chunked = chunked_applies(P);
   switch (S) {
-    case 1: return spike_fold_t<1>(P, o, work, nbr, active, s, st);
-    case 2: return spike_fold_t<2>(P, o, work, nbr, active, s, st);
-    case 3: return spike_fold_t<3>(P, o, work, nbr, active, s, st);
-    case 4: return spike_fold_t<4>(P, o, work, nbr, active, s, st);
+    case 1: return chunked ? spike_fold_chunked<1>(P, o, seg, work, nbr, active, s, st) : spike_fold_t<1>(P, o, work, nbr, active, s, st);
+    case 2: return chunked ? spike_fold_chunked<2>(P, o, seg, work, nbr, active, s, st) : spike_fold_t<2>(P, o, work, nbr, active, s, st);
+    case 3: return chunked ? spike_fold_chunked<3>(P, o, seg, work, nbr, active, s, st) : spike_fold_t<3>(P, o, work, nbr, active, s, st);
+    case 4: return chunked ? spike_fold_chunked<4>(P, o, seg, work, nbr, active, s, st) : spike_fold_t<4>(P, o, work, nbr, active, s, st);
   }
   return set_error("sfxm_spike_fold: bad segment size");
 }

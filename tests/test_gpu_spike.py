@@ -151,3 +151,48 @@ def test_dense_solve_kernel(N, B):
     ref = np.stack([np.linalg.solve(M[b], rhs[b]) for b in range(B)])
     assert int(status.sum()) == 0
     assert rel_err(z.cpu().numpy(), ref) < 1e-10 * max(1.0, max(np.linalg.cond(M[b]) for b in range(B)) * 1e-4)
+
+
+@pytest.mark.parametrize("G,nx", [(2, 4100), (3, 7000)])
+@pytest.mark.parametrize("bcs,split,locs", [(README_BCS, True, [1, 2]), (README_BCS, False, None), (WELL_POSED, True, [1])])
+def test_slab_solve_large_slabs_nested_dissection(bcs, split, locs, G, nx):
+    """Slabs of >= 2048 cells take the nested-dissection path (separators every 256 cells + both slab ends); the
+    gathered step must equal the single-mesh solve."""
+    import torch
+    import splitfxm_b200 as sf
+    from oracle import core
+    from splitfxm_b200.models.advection_diffusion import AdvectionDiffusion
+    from splitfxm_b200.spike import SlabNewtonEngine, ThreadGroup
+    comps = ["u", "v", "w"]
+    rng = np.random.default_rng(5)
+    U = rng.standard_normal((nx, 3))
+    scheme = sf.FVSchemes.LAX_FRIEDRICHS
+    d = sf.Domain.from_size(nx, 1, 1, comps)
+    d.interior_U()[:, :] = U
+    sim = sf.Simulation(d, AdvectionDiffusion(0.2, 0.01, "FVM"), {}, bcs, scheme)
+    e1 = sim._engine()
+    y1 = e1.to_device(core.to_flat(U, split, locs))
+    r1 = torch.empty_like(y1)
+    J1 = e1.jacobian(y1, split, locs, r0=r1)
+    shift1 = torch.full((1,), -float(nx) ** 2 * 0.05, dtype=torch.float64, device=y1.device)
+    s1 = torch.zeros_like(y1)
+    e1.solve(J1, r1, s1, split, locs, shift=shift1, method="pcr")
+    ref = core.to_block(s1.cpu().numpy()[:, 0], nx, 3, split, locs)
+    x_global = np.array(d.positions(interior=True))
+
+    def body(rank, comm):
+        slab = _thread_slab(x_global, comps, "ad", {"c": 0.2, "nu": 0.01}, bcs, scheme, "FVM", rank, G, comm)
+        assert slab.eng.nx >= 2048
+        eng = SlabNewtonEngine(slab, comm)
+        y = slab.eng.to_device(core.to_flat(U[slab.lo:slab.hi], split, locs))
+        r = torch.empty_like(y)
+        J = eng.jacobian(y, split, locs, r0=r)
+        shift = torch.full((1,), -float(nx) ** 2 * 0.05, dtype=torch.float64, device=y.device)
+        status = torch.zeros(1, dtype=torch.int32, device=y.device)
+        s = torch.zeros_like(y)
+        eng.solve(J, r, s, split, locs, shift=shift, status=status)
+        assert int(status[0]) == 0
+        return core.to_block(s.cpu().numpy()[:, 0], slab.hi - slab.lo, 3, split, locs)
+
+    got = np.concatenate(ThreadGroup(G).run(body))
+    assert rel_err(got, ref) < 1e-10
