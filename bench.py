@@ -425,12 +425,10 @@ def extras(torch, sf, ens, Y, dev, peak):
         ss = torch.zeros_like(y)
         st1 = torch.zeros(1, dtype=torch.int32, device=dev)
 
-        def newton_iteration():      # one Newton iteration of the device driver: J + f, solve (PCR), update, criterion norms
+        def newton_iteration():      # one Newton iteration of the device driver: J + f, solve (PCR), update + criterion norms
             e1.jacobian(y, SPLIT, LOCS, J=Jb, r0=rr)
             e1.solve(Jb, rr, ss, SPLIT, LOCS, status=st1)
-            e1.axpy(y, ss)
-            e1.sumsq(ss)
-            e1.sumsq(y)
+            e1.update_norms(y, ss)
         ms_n = timed(newton_iteration, 3)
         t0 = time.perf_counter()
         iters = sim.steady_state(split=SPLIT, split_locs=LOCS)       # public API, host buffers in and out

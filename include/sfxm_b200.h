@@ -186,6 +186,13 @@ int sfxm_dense_solve(const double *aug, int32_t n, int64_t batch, double *z, int
 int64_t sfxm_sumsq_workspace_bytes(int64_t n, int64_t batch);
 int sfxm_sumsq(const double *v, int64_t lo, int64_t hi, int64_t batch, double *out, double *work, void *stream);
 
+/* The Newton update and both norms of the convergence criterion in ONE pass over (y, s): if update != 0,
+ * y[q, m] += alpha[m] * s[q, m] for q in [lo, hi) and active members (alpha NULL = 1, active NULL = all); then
+ * out2[m] = sum s^2 and out2[batch + m] = sum y_new^2 over [lo, hi), accumulated in the order of sfxm_sumsq (same bits).
+ * work: 2 * sfxm_sumsq_workspace_bytes(hi - lo, batch). */
+int sfxm_update_norms(double *y, const double *s, const double *alpha, const int32_t *active, int32_t update, int64_t lo,
+                      int64_t hi, int64_t batch, double *out2, double *work, void *stream);
+
 /* y[q, m] += alpha[m] * s[q, m] for q in [lo, hi) and members with active[m] != 0. */
 int sfxm_axpy_masked(double *y, const double *s, const double *alpha, const int32_t *active, int64_t lo, int64_t hi,
                      int64_t batch, void *stream);

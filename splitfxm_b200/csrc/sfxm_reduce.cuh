@@ -58,6 +58,53 @@ static __global__ void reduce_final_kernel(const double *__restrict__ partial, i
   out[m] = acc;
 }
 
+// two sums per member from one pass: term(q, m) returns a double2; partial[(tile * 2 + w) * B + m], out2[w * B + m].
+// Same tiles and the same order of additions as reduce_partial_kernel, so each sum has the bits the one-sum kernel gives.
+template <class Term>
+__global__ void __launch_bounds__(kReduceThreads)
+reduce_partial2_kernel(Term term, int64_t lo, int64_t hi, int64_t B, double *__restrict__ partial) {
+  __shared__ double sh[2][kReduceThreads];
+  const int TM = blockDim.x, TR = blockDim.y;
+  const int64_t m = (int64_t)blockIdx.y * TM + threadIdx.x;
+  const int64_t q0 = lo + (int64_t)blockIdx.x * TR * kReduceRowsPerThread + threadIdx.y;
+  double a0 = 0.0, a1 = 0.0;
+  if (m < B) {
+#pragma unroll
+    for (int k = 0; k < kReduceRowsPerThread; ++k) {
+      const int64_t q = q0 + (int64_t)k * TR;
+      if (q < hi) {
+        const double2 t = term(q, m);
+        a0 += t.x;
+        a1 += t.y;
+      }
+    }
+  }
+  sh[0][threadIdx.y * TM + threadIdx.x] = a0;
+  sh[1][threadIdx.y * TM + threadIdx.x] = a1;
+  __syncthreads();
+  if (threadIdx.y == 0 && m < B) {
+    double t0 = sh[0][threadIdx.x], t1 = sh[1][threadIdx.x];
+    for (int r = 1; r < TR; ++r) {
+      t0 += sh[0][r * TM + threadIdx.x];
+      t1 += sh[1][r * TM + threadIdx.x];
+    }
+    partial[((int64_t)blockIdx.x * 2) * B + m] = t0;
+    partial[((int64_t)blockIdx.x * 2 + 1) * B + m] = t1;
+  }
+}
+
+// work must hold 2 * reduce_tiles(hi - lo, batch) * batch doubles; out2 holds 2 * batch
+template <class Term>
+static void reduce_rows2(Term term, int64_t lo, int64_t hi, int64_t batch, double *out2, double *work, cudaStream_t st) {
+  const int64_t ntiles = reduce_tiles(hi - lo, batch);
+  if (ntiles > 0) {
+    dim3 b = batch >= 32 ? dim3(32, kReduceThreads / 32) : dim3(1, kReduceThreads);
+    dim3 g((unsigned)ntiles, (unsigned)((batch + b.x - 1) / b.x));
+    reduce_partial2_kernel<Term><<<g, b, 0, st>>>(term, lo, hi, batch, work);
+  }
+  reduce_final_kernel<<<(unsigned)((2 * batch + 127) / 128), 128, 0, st>>>(work, ntiles, 2 * batch, out2);
+}
+
 // work must hold reduce_tiles(hi - lo, batch) * batch doubles
 template <class Term>
 static void reduce_rows(Term term, int64_t lo, int64_t hi, int64_t batch, double *out, double *work, cudaStream_t st) {

@@ -42,6 +42,25 @@ struct SquareTerm {   // the norms of the Newton convergence criterion
   }
 };
 
+// Newton update and the two norms of its convergence criterion in one pass over (y, s):
+//   y += alpha s for the active members (update != 0), then  sum s^2  and  sum y_new^2  per member
+struct UpdateNormsTerm {
+  double *y;
+  const double *s, *alpha;
+  const int32_t *active;
+  int64_t B;
+  int update;
+  __device__ __forceinline__ double2 operator()(int64_t q, int64_t m) const {
+    const double sv = __ldg(s + q * B + m);
+    double yv = y[q * B + m];
+    if (update && (!active || active[m])) {
+      yv = yv + (alpha ? alpha[m] : 1.0) * sv;
+      y[q * B + m] = yv;
+    }
+    return make_double2(sv * sv, yv * yv);
+  }
+};
+
 __global__ void axpy_masked_kernel(double *__restrict__ y, const double *__restrict__ s, const double *__restrict__ alpha,
                                    const int32_t *__restrict__ active, int64_t lo, int64_t hi, int64_t B) {
   const int64_t m = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
@@ -170,4 +189,12 @@ extern "C" int sfxm_axpy_masked(double *y, const double *s, const double *alpha,
   dim3 g((unsigned)((hi - lo + b.y - 1) / b.y), (unsigned)((batch + b.x - 1) / b.x));
   axpy_masked_kernel<<<g, b, 0, (cudaStream_t)stream>>>(y, s, alpha, active, lo, hi, batch);
   return check_launch("sfxm_axpy_masked");
+}
+
+extern "C" int sfxm_update_norms(double *y, const double *s, const double *alpha, const int32_t *active, int32_t update,
+                                 int64_t lo, int64_t hi, int64_t batch, double *out2, double *work, void *stream) {
+  if (!y || !s || !out2 || !work || hi < lo) return set_error("sfxm_update_norms: bad argument");
+  if (batch > 65535LL * 32) return set_error("sfxm_update_norms: batch too large");
+  reduce_rows2(UpdateNormsTerm{y, s, alpha, active, batch, update}, lo, hi, batch, out2, work, (cudaStream_t)stream);
+  return check_launch("sfxm_update_norms");
 }

@@ -288,6 +288,20 @@ class Engine:
         _lib.count(2)
         return out
 
+    def update_norms(self, y, s, active=None, lo=0, hi=None, update=True, alpha=None):
+        """y[lo:hi] += alpha * s[lo:hi] for the active members (if update), and the per-member sums of squares of s and
+        of the updated y over [lo, hi) - one pass, two launches (sfxm_update_norms).  -> (sum s^2, sum y^2)."""
+        if hi is None:
+            hi = self.n
+        out2 = torch.empty(2 * self.batch, dtype=torch.float64, device=self.device)
+        nbytes = 2 * self.lib.sfxm_sumsq_workspace_bytes(hi - lo, self.batch)
+        work = self._scratch("norms2", nbytes // 8)
+        _lib.check(self.lib.sfxm_update_norms(_lib.ptr(y), _lib.ptr(s), _lib.ptr(alpha), _lib.ptr(active), 1 if update else 0,
+                                              int(lo), int(hi), self.batch, _lib.ptr(out2), _lib.ptr(work),
+                                              _lib.stream_ptr()))
+        _lib.count(2)
+        return out2[:self.batch], out2[self.batch:]
+
     def axpy(self, y, s, alpha=None, active=None, lo=0, hi=None):
         if hi is None:
             hi = self.n

@@ -101,13 +101,13 @@ class NewtonDriver:
                 scale = lam if scale is None else scale * lam
             if scale is not None:
                 self.s[lo:hi] = torch.where(run[None, :], self.s[lo:hi] * scale[None, :], self.s[lo:hi])
-            eng.axpy(y, self.s, None, run32, lo, hi)
+            ss, yy = eng.update_norms(y, self.s, run32, lo, hi)       # y += s and both norms of the criterion, one pass
             if self.dt0 > 0:
                 eng.residual(y, self.rt, self.split, self.split_locs)
                 rn = torch.sqrt(eng.sumsq(self.rt, lo, hi))
                 grown = torch.where(rn > 0, torch.clamp(dt * rnorm / rn, max=self.dtmax), torch.full_like(dt, self.dtmax))
                 dt = torch.where(run, grown, dt)
-            c = torch.sqrt(eng.sumsq(self.s, lo, hi)) / (ABS_TOL + REL_TOL * torch.sqrt(eng.sumsq(y, lo, hi)))
+            c = torch.sqrt(ss) / (ABS_TOL + REL_TOL * torch.sqrt(yy))
             crit = torch.where(run, c, crit)
             it = it + run.to(torch.int64)
         return it
@@ -138,7 +138,8 @@ class NewtonDriver:
                 break
             self.split_newton(y, k0 + 1, maxiter, run)      # inner segments to convergence
             self.newton_segment(y, k0, 1, run)              # one step on this segment
-            c = torch.sqrt(eng.sumsq(self.s, lo, eng.n)) / (ABS_TOL + REL_TOL * torch.sqrt(eng.sumsq(y, lo, eng.n)))
+            ss, yy = eng.update_norms(y, self.s, None, lo, eng.n, update=False)
+            c = torch.sqrt(ss) / (ABS_TOL + REL_TOL * torch.sqrt(yy))
             crit = torch.where(run, c, crit)
             it = it + run.to(torch.int64)
         return it

@@ -254,6 +254,11 @@ class SlabNewtonEngine:
     def sumsq(self, v, lo=0, hi=None, out=None):
         return self.comm.all_reduce_sum(self.eng.sumsq(v, lo, hi, out))
 
+    def update_norms(self, y, s, active=None, lo=0, hi=None, update=True, alpha=None):
+        ss, yy = self.eng.update_norms(y, s, active, lo, hi, update, alpha)
+        both = self.comm.all_reduce_sum(torch.cat((ss, yy)))
+        return both[:self.eng.batch], both[self.eng.batch:]
+
     def axpy(self, y, s, alpha=None, active=None, lo=0, hi=None):
         return self.eng.axpy(y, s, alpha, active, lo, hi)
 

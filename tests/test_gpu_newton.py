@@ -357,3 +357,28 @@ def test_chunked_pcr_matches_plain_pcr(nx, bcs_kind, split, locs, monkeypatch):
         xn = np.roll(x, -(dslot - 1), axis=0)
         Ax += np.einsum("irc,ic->ir", Jh[:, dslot] * same[None], xn)
     assert np.max(np.abs(Ax + f)) <= 1e-9 * max(1.0, np.max(np.abs(f)))
+
+
+@pytest.mark.parametrize("B,n", [(1, 777), (5, 300), (96, 1201)])
+def test_update_norms_equals_axpy_then_sumsq(B, n):
+    """sfxm_update_norms = sfxm_axpy_masked + two sfxm_sumsq, bit for bit (same tiles, same order of additions)."""
+    import torch
+    from splitfxm_b200.engine import Engine
+    from splitfxm_b200 import _lib
+    eng = Engine(_lib.MODEL_AD, _lib.FD_CENTRAL, 3, 1, 1, np.linspace(0, 1, n // 3 if n % 3 == 0 else 100), 0.0, 1.0,
+                 np.array([0.2, 0.01]), batch=B)
+    eng.n = n                                           # only the vector kernels are used here
+    g = torch.Generator(device="cuda").manual_seed(B)
+    y = torch.randn((n, B), dtype=torch.float64, device="cuda", generator=g)
+    s = torch.randn((n, B), dtype=torch.float64, device="cuda", generator=g)
+    active = (torch.arange(B, device="cuda") % 3 != 1).to(torch.int32)
+    lo, hi = 17, n - 5
+    y_ref = y.clone()
+    eng.axpy(y_ref, s, None, active, lo, hi)
+    ss_ref, yy_ref = eng.sumsq(s, lo, hi).clone(), eng.sumsq(y_ref, lo, hi).clone()
+    y_new = y.clone()
+    ss, yy = eng.update_norms(y_new, s, active, lo, hi)
+    assert torch.equal(y_new, y_ref) and torch.equal(ss, ss_ref) and torch.equal(yy, yy_ref)
+    y_keep = y.clone()
+    ss2, yy2 = eng.update_norms(y_keep, s, None, lo, hi, update=False)
+    assert torch.equal(y_keep, y) and torch.equal(ss2, ss_ref) and torch.equal(yy2, eng.sumsq(y, lo, hi))
