@@ -495,7 +495,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--members", type=int, default=65536, help="ensemble members per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--cpu-sample", type=int, default=10240, help="members the 1-core CPU baseline assembles (~10 s)")
     ap.add_argument("--ref-members", type=int, default=4096, help="members per step of the reference arm")
     ap.add_argument("--no-extra", action="store_true")
