@@ -12,6 +12,7 @@
 #include <cstring>
 #include "sfxm_device.cuh"
 #include "sfxm_host.h"
+#include "sfxm_cpasync.cuh"
 
 #ifndef SFXM_PAIR_MIN_CTAS
 #define SFXM_PAIR_MIN_CTAS 16       // Jacobian pair kernel: 128 registers (20 / 24 CTAs spill and are slower)
@@ -166,6 +167,116 @@ residual_pair_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
         const double c1 = (W == 3 || P.nbl == 1) ? u[1][1][j] : u[1][W == 3 ? 1 : 2][j];
         const double2 yn = make_double2(c0 + dt * r[0][j], c1 + dt * r[1][j]);                                // simulation.py:459
         *reinterpret_cast<double2 *>(y_out + off[j]) = yn;
+        push_halo(P, i, j, m0, yn.x);
+        push_halo(P, i, j, m0 + 1, yn.y);
+      }
+    }
+  }
+}
+
+// 3-cell stencils: the same kernel with the state streamed ONCE.  residual_pair_kernel gathers the three cells of every
+// stencil (two of them L1 hits) and can only start a cell's loads when the previous cell is done, so a one-warp CTA has
+// one cell's rows in flight.  Here the warp keeps the stencil as a sliding register window; the rows of the cell that
+// enters the window are copied cp.async into a per-lane ring in shared memory kRingCells cells ahead of their use.
+#ifndef SFXM_RES_RING_CELLS
+#define SFXM_RES_RING_CELLS 4
+#endif
+template <class Model, int SCHEME, int NV, bool UPDATE>
+__global__ void __launch_bounds__(32, SFXM_RES_PAIR_MIN_CTAS)
+residual_ring_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restrict__ x_int,
+                     const double *__restrict__ params, int64_t param_stride, const double *__restrict__ y,
+                     double *__restrict__ r_out, double *__restrict__ y_out, double dt,
+                     const double *__restrict__ geom_tab, int strip) {
+  constexpr int W = 3, D = SFXM_RES_RING_CELLS;
+  __shared__ double2 ring[D][NV][32];
+  const int64_t i0 = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * strip;
+  const int64_t m0 = ((int64_t)blockIdx.x * 32 + threadIdx.x) * 2;
+  if (m0 >= P.batch || i0 >= P.nx) return;
+  const int64_t B = P.batch, nx = P.nx;
+  const int lane = threadIdx.x;
+  const int64_t i1 = i0 + strip < nx ? i0 + strip : nx;
+  double prm[2][Model::kParams];
+  bool prm_ok = true;
+#pragma unroll
+  for (int k = 0; k < Model::kParams; ++k) {
+    if (param_stride) {
+      const double2 t = __ldg(reinterpret_cast<const double2 *>(params + k * param_stride + m0));
+      prm[0][k] = t.x;
+      prm[1][k] = t.y;
+    } else {
+      prm[0][k] = prm[1][k] = __ldg(params + k);
+    }
+    prm_ok = prm_ok & sane(prm[0][k], 120) & sane(prm[1][k], 120);
+  }
+  int64_t base[NV], rs[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    rs[j] = (int64_t)P.var_stride[j] * B;
+    base[j] = (P.var_base[j] + P.var_off[j]) * B + m0;
+  }
+  auto issue = [&](int64_t cell) {           // one commit group per cell (empty beyond the mesh)
+    if (cell < nx) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        cp_async16(&ring[cell & (D - 1)][j][lane], reinterpret_cast<const double2 *>(y + base[j] + cell * rs[j]));
+    }
+    cp_async_commit();
+  };
+  // window: slot 1 = cell i - 1, slot 2 = cell i at loop entry (shifted down at the top of every iteration)
+  double u[2][W][NV];
+  bool ok_w[W];
+  {
+    const int64_t cm = i0 > 0 ? i0 - 1 : 0;
+    ok_w[0] = ok_w[1] = ok_w[2] = true;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const double2 a = __ldg(reinterpret_cast<const double2 *>(y + base[j] + cm * rs[j]));
+      const double2 b = __ldg(reinterpret_cast<const double2 *>(y + base[j] + i0 * rs[j]));
+      u[0][1][j] = a.x; u[1][1][j] = a.y;
+      u[0][2][j] = b.x; u[1][2][j] = b.y;
+      u[0][0][j] = u[1][0][j] = 0.0;
+      ok_w[1] = ok_w[1] & sane(a.x, 120) & sane(a.y, 120);
+      ok_w[2] = ok_w[2] & sane(b.x, 120) & sane(b.y, 120);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < D; ++k) issue(i0 + 1 + k);
+  for (int64_t i = i0; i < i1; ++i) {
+    ok_w[0] = ok_w[1];
+    ok_w[1] = ok_w[2];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      u[0][0][j] = u[0][1][j]; u[1][0][j] = u[1][1][j];
+      u[0][1][j] = u[0][2][j]; u[1][1][j] = u[1][2][j];
+    }
+    cp_async_wait<D - 1>();                  // the oldest group in flight (cell i + 1) has landed
+    if (i + 1 < nx) {
+      ok_w[2] = true;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const double2 t = ring[(i + 1) & (D - 1)][j][lane];
+        u[0][2][j] = t.x; u[1][2][j] = t.y;
+        ok_w[2] = ok_w[2] & sane(t.x, 120) & sane(t.y, 120);
+      }
+    }
+    issue(i + 1 + D);                        // refills the slot just read
+    const bool interior = (i >= 1) && (i + 1 < nx);
+    const Geom<SCHEME, W> geom(geom_tab, nx, i);
+    if (!(interior && prm_ok && ok_w[0] && ok_w[1] && ok_w[2] && geom.fast)) {
+      residual_member_noinline<Model, SCHEME, NV, W>(P, x_int, params, param_stride, y, r_out, y_out, dt, geom_tab, i, m0);
+      residual_member_noinline<Model, SCHEME, NV, W>(P, x_int, params, param_stride, y, r_out, y_out, dt, geom_tab, i, m0 + 1);
+      continue;
+    }
+    double r[2][NV];
+#pragma unroll
+    for (int v = 0; v < 2; ++v) cell_residual<Model, SCHEME, NV, W, true>(prm[v], u[v], geom, r[v]);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int64_t off = base[j] + i * rs[j];
+      if (r_out) *reinterpret_cast<double2 *>(r_out + off) = make_double2(r[0][j], r[1][j]);
+      if constexpr (UPDATE) {
+        const double2 yn = make_double2(u[0][1][j] + dt * r[0][j], u[1][1][j] + dt * r[1][j]);               // simulation.py:459
+        *reinterpret_cast<double2 *>(y_out + off) = yn;
         push_halo(P, i, j, m0, yn.x);
         push_halo(P, i, j, m0 + 1, yn.y);
       }
@@ -740,6 +851,23 @@ static bool pair_enabled() {
   }
   return v != 0;
 }
+static bool residual_ring_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SFXM_RES_RING");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+static int residual_ring_strip() {      // cells per one-warp CTA of residual_ring_kernel
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SFXM_RING_STRIP");
+    v = e ? atoi(e) : 32;
+    if (v < 1 || v > 65536) v = 32;
+  }
+  return v;
+}
 static int ensemble_strip() {
   static int v = -1;
   if (v < 0) {
@@ -807,6 +935,19 @@ static int launch_t(const Launch &L) {
     const int64_t gy = tiles < 65535 ? tiles : 65535;
     dim3 g((unsigned)((P.batch / 2 + 31) / 32), (unsigned)gy, (unsigned)((tiles + gy - 1) / gy));
     if (g.z > 65535) return set_error("mesh too large for one launch");
+    if constexpr (W == 3) {
+      if (residual_ring_enabled()) {
+        const int rstrip = residual_ring_strip();
+        const int64_t rtiles = (P.nx + rstrip - 1) / rstrip;
+        const int64_t rgy = rtiles < 65535 ? rtiles : 65535;
+        dim3 rg((unsigned)((P.batch / 2 + 31) / 32), (unsigned)rgy, (unsigned)((rtiles + rgy - 1) / rgy));
+        if (L.out1)
+          residual_ring_kernel<Model, SCHEME, NV, true><<<rg, dim3(32, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.out0, L.out1, L.scalar, L.geom, rstrip);
+        else
+          residual_ring_kernel<Model, SCHEME, NV, false><<<rg, dim3(32, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.out0, L.out1, L.scalar, L.geom, rstrip);
+        return check_launch("sfxm kernel launch");
+      }
+    }
     if (L.out1)
       residual_pair_kernel<Model, SCHEME, NV, W, true><<<g, dim3(32, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.out0, L.out1, L.scalar, L.geom, strip);
     else

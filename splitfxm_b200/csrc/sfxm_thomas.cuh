@@ -6,6 +6,7 @@
 #include <cstdint>
 #include "../../include/sfxm_b200.h"
 #include "sfxm_host.h"
+#include "sfxm_cpasync.cuh"
 
 namespace sfxm {
 
@@ -17,13 +18,6 @@ __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefe
 // rows are fetched kRingDepth iterations ahead with cp.async into a per-thread ring in shared memory (thread-private
 // columns: no barrier needed, cp.async.wait_group orders the thread's own copies).  One-warp CTAs only.
 constexpr int kThomasThreads = 32;
-__device__ __forceinline__ void cp_async8(double *smem, const double *gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 template <int K>   // K doubles per row and thread
 struct RingDepth {
   static constexpr int value = K <= 2 ? 8 : (K <= 12 ? 4 : 2);   // power of two; 32 threads x K x depth x 8 B <= 11 KB
