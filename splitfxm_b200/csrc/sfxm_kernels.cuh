@@ -685,131 +685,10 @@ jacobian_pair_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
   }
 }
 
-// The same block rows for 3-cell stencils with the state streamed once: one warp walks `strip` cells, the stencil is a
-// sliding register window and the rows of the entering cell arrive by cp.async through a per-lane shared-memory ring
-// (as in residual_ring_kernel), so no CTA starts with an exposed HBM round trip and every state row is loaded once.
-template <class Model, int SCHEME, int NV, bool RESTRICT>
-__global__ void __launch_bounds__(32, SFXM_PAIR_MIN_CTAS)
-jacobian_ring_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restrict__ x_int,
-                     const double *__restrict__ params, int64_t param_stride, const double *__restrict__ y,
-                     double eps, double *__restrict__ J, double *__restrict__ r0_out, uint32_t entry_mask,
-                     const double *__restrict__ geom_tab, int strip) {
-  constexpr int W = 3, D = SFXM_RES_RING_CELLS;
-  __shared__ double2 ring[D][NV][32];
-  const int64_t i0 = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * strip;
-  const int64_t m0 = ((int64_t)blockIdx.x * 32 + threadIdx.x) * 2;
-  if (m0 >= P.batch || i0 >= P.nx) return;
-  const int64_t B = P.batch, nx = P.nx;
-  const int lane = threadIdx.x;
-  const int64_t i1 = i0 + strip < nx ? i0 + strip : nx;
-  double prm[2][Model::kParams];
-  bool prm_ok = sane(eps, 120);
-#pragma unroll
-  for (int k = 0; k < Model::kParams; ++k) {
-    if (param_stride) {
-      const double2 t = __ldg(reinterpret_cast<const double2 *>(params + k * param_stride + m0));
-      prm[0][k] = t.x;
-      prm[1][k] = t.y;
-    } else {
-      prm[0][k] = prm[1][k] = __ldg(params + k);
-    }
-    prm_ok = prm_ok & sane(prm[0][k], 120) & sane(prm[1][k], 120);
-  }
-  const double reps = 1.0 / eps;
-  int64_t base[NV], rs[NV];
-#pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    rs[j] = (int64_t)P.var_stride[j] * B;
-    base[j] = (P.var_base[j] + P.var_off[j]) * B + m0;
-  }
-  auto issue = [&](int64_t cell) {
-    if (cell < nx) {
-#pragma unroll
-      for (int j = 0; j < NV; ++j)
-        cp_async16(&ring[cell & (D - 1)][j][lane], reinterpret_cast<const double2 *>(y + base[j] + cell * rs[j]));
-    }
-    cp_async_commit();
-  };
-  double u[2][W][NV];
-  bool ok_w[W];
-  {
-    const int64_t cm = i0 > 0 ? i0 - 1 : 0;
-    ok_w[0] = ok_w[1] = ok_w[2] = true;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const double2 a = __ldg(reinterpret_cast<const double2 *>(y + base[j] + cm * rs[j]));
-      const double2 b = __ldg(reinterpret_cast<const double2 *>(y + base[j] + i0 * rs[j]));
-      u[0][1][j] = a.x; u[1][1][j] = a.y;
-      u[0][2][j] = b.x; u[1][2][j] = b.y;
-      u[0][0][j] = u[1][0][j] = 0.0;
-      ok_w[1] = ok_w[1] & sane(a.x, 120) & sane(a.y, 120);
-      ok_w[2] = ok_w[2] & sane(b.x, 120) & sane(b.y, 120);
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < D; ++k) issue(i0 + 1 + k);
-  for (int64_t i = i0; i < i1; ++i) {
-    ok_w[0] = ok_w[1];
-    ok_w[1] = ok_w[2];
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      u[0][0][j] = u[0][1][j]; u[1][0][j] = u[1][1][j];
-      u[0][1][j] = u[0][2][j]; u[1][1][j] = u[1][2][j];
-    }
-    cp_async_wait<D - 1>();
-    if (i + 1 < nx) {
-      ok_w[2] = true;
-#pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const double2 t = ring[(i + 1) & (D - 1)][j][lane];
-        u[0][2][j] = t.x; u[1][2][j] = t.y;
-        ok_w[2] = ok_w[2] & sane(t.x, 120) & sane(t.y, 120);
-      }
-    }
-    issue(i + 1 + D);
-    const bool interior = (i >= 1) && (i + 1 < nx);
-    const Geom<SCHEME, W> geom(geom_tab, nx, i);
-    if (!(interior && prm_ok && ok_w[0] && ok_w[1] && ok_w[2] && geom.fast)) {
-      jacobian_member_noinline<Model, SCHEME, NV, W>(P, x_int, params, param_stride, y, eps, J, r0_out, entry_mask, geom_tab, i, m0);
-      jacobian_member_noinline<Model, SCHEME, NV, W>(P, x_int, params, param_stride, y, eps, J, r0_out, entry_mask, geom_tab, i, m0 + 1);
-      continue;
-    }
-    double r0[2][NV];
-#pragma unroll
-    for (int v = 0; v < 2; ++v) cell_residual<Model, SCHEME, NV, W, true>(prm[v], u[v], geom, r0[v]);   // simulation.py:320
-    if (r0_out) {
-#pragma unroll
-      for (int j = 0; j < NV; ++j) *reinterpret_cast<double2 *>(r0_out + base[j] + i * rs[j]) = make_double2(r0[0][j], r0[1][j]);
-    }
-    double *p = J + (i * W) * (int64_t)(NV * NV) * B + m0;
-#pragma unroll
-    for (int d = 0; d < W; ++d) {
-      double cols[2][NV][NV];   // [member][c][r]
-#pragma unroll
-      for (int v = 0; v < 2; ++v)
-#pragma unroll
-        for (int c = 0; c < NV; ++c) {
-          if constexpr (RESTRICT) {
-            if (!(entry_mask & column_bits<NV>(c))) continue;
-          }
-          double upc[W];
-#pragma unroll
-          for (int sl = 0; sl < W; ++sl) upc[sl] = u[v][sl][c];
-          upc[d] = u[v][d][c] + eps;                          // simulation.py:337
-          jac_column<Model, SCHEME, NV, W, true>(prm[v], u[v], upc, c, geom, r0[v], eps, reps, cols[v][c]);
-        }
-#pragma unroll
-      for (int r = 0; r < NV; ++r)
-#pragma unroll
-        for (int c = 0; c < NV; ++c) {
-          if (stored_entry<Model>(r, c) && (entry_mask & (1u << (r * NV + c))))
-            *reinterpret_cast<double2 *>(p) = make_double2(cols[0][c][r], cols[1][c][r]);
-          p += B;
-        }
-    }
-  }
-}
-
+// (The ring / sliding-window structure of residual_ring_kernel was tried here too - one warp walking 4-32 cells, the
+// entering cell's rows prefetched by cp.async: the loop around the unrolled perturbations spills 500-800 bytes at 128
+// registers (276 at 168) and runs at 0.73-0.77 ms against 0.50 ms for one cell per CTA; removed.  The assembly kernel is
+// bound by its FP64 instruction stream, not by load latency.)
 // (A per-variable variant for decoupled models - one warp per (cell, variable), two members per lane, 64-96 registers,
 // 20-32 one-warp CTAs per SM instead of 16 - was tried to get more resident warps: bit-identical, but 0.63-0.67 ms
 // against 0.57 ms on the bench shape at every register setting (the per-warp set-up - geometry row, parameters,
@@ -993,15 +872,6 @@ static int residual_ring_strip() {      // cells per one-warp CTA of residual_ri
   }
   return v;
 }
-static int jacobian_ring_strip() {      // cells per one-warp CTA of jacobian_ring_kernel; 0 = one cell per CTA (jacobian_pair_kernel)
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("SFXM_JAC_RING_STRIP");
-    v = e ? atoi(e) : 0;
-    if (v < 0 || v > 65536) v = 0;
-  }
-  return v;
-}
 static int ensemble_strip() {
   static int v = -1;
   if (v < 0) {
@@ -1100,19 +970,6 @@ static int launch_t(const Launch &L) {
     const int64_t gy = P.nx < 65535 ? P.nx : 65535;
     dim3 g((unsigned)((P.batch / 2 + 31) / 32), (unsigned)gy, (unsigned)((P.nx + gy - 1) / gy));
     if (g.z > 65535) return set_error("mesh too large for one launch");
-    if constexpr (W == 3) {
-      const int jstrip = jacobian_ring_strip();
-      if (jstrip > 0) {
-        const int64_t rtiles = (P.nx + jstrip - 1) / jstrip;
-        const int64_t rgy = rtiles < 65535 ? rtiles : 65535;
-        dim3 rg((unsigned)((P.batch / 2 + 31) / 32), (unsigned)rgy, (unsigned)((rtiles + rgy - 1) / rgy));
-        if (restricted)
-          jacobian_ring_kernel<Model, SCHEME, NV, true><<<rg, dim3(32, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.scalar, L.out0, L.out1, mask, L.geom, jstrip);
-        else
-          jacobian_ring_kernel<Model, SCHEME, NV, false><<<rg, dim3(32, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.scalar, L.out0, L.out1, mask, L.geom, jstrip);
-        return check_launch("sfxm kernel launch");
-      }
-    }
     if (restricted)
       jacobian_pair_kernel<Model, SCHEME, NV, W, true><<<g, dim3(32, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.scalar, L.out0, L.out1, mask, L.geom);
     else
