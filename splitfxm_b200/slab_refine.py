@@ -38,6 +38,40 @@ def _neighbour_rows(comm, rows, lo, n_loc, n_global):
     return (got[comm.rank - 1] if has_l else empty), (got[comm.rank + 1] if has_r else empty)
 
 
+def rebalance_rows(comm, mine, sizes):
+    """Even out consecutive per-rank row blocks.  Rank r holds `mine` = rows [offs[r], offs[r + 1]) of a global array
+    (offs = cumulative `sizes`); afterwards it holds the rows of `slab_bounds(total, world, r)`.  Only the overlaps of the
+    old and the new ranges travel, point to point.  Device-agnostic (the CPU tests run it over gloo).
+    Returns (rows of the new slab, its first global row, total)."""
+    offs = np.concatenate(([0], np.cumsum(sizes)))
+    total = int(offs[-1])
+    me, world = comm.rank, comm.world
+    my_lo, my_hi = int(offs[me]), int(offs[me + 1])
+    tlo, thi = slab_bounds(total, world, me)
+    send, recv = {}, {}
+    for r in range(world):
+        if r == me:
+            continue
+        rlo, rhi = slab_bounds(total, world, r)
+        a, b = max(my_lo, rlo), min(my_hi, rhi)              # what I hold of rank r's new slab
+        if b > a:
+            send[r] = mine[a - my_lo:b - my_lo].contiguous()
+        a, b = max(int(offs[r]), tlo), min(int(offs[r + 1]), thi)      # what rank r holds of mine
+        if b > a:
+            recv[r] = (b - a,) + tuple(mine.shape[1:])
+    got = comm.exchange(send, recv, mine)
+    parts = []
+    for r in range(world):                                   # old ranges are in rank order, so are the pieces
+        if r == me:
+            a, b = max(my_lo, tlo), min(my_hi, thi)
+            if b > a:
+                parts.append(mine[a - my_lo:b - my_lo])
+        elif r in got:
+            parts.append(got[r])
+    out = torch.cat(parts, dim=0) if parts else mine[:0]
+    return out, tlo, total
+
+
 class SlabRefiner(Refiner):
     def refine_slab(self, x_loc, U_loc, lo, n_global, comm, rebalance=True, report=True):
         """x_loc [n_loc], U_loc [n_loc, nv]: device tensors with this rank's cells [lo, lo + n_loc) of a mesh of
@@ -97,28 +131,7 @@ class SlabRefiner(Refiner):
             return x_new, U_new, int(offs[comm.rank]), total
         # 4. rebalance: contiguous ranges of the new global order move to the ranks that own them now
         mine = torch.cat((x_new.view(-1, 1), U_new), dim=1).contiguous()
-        my_lo, my_hi = int(offs[comm.rank]), int(offs[comm.rank + 1])
-        send, recv = {}, {}
-        for r in range(comm.world):
-            tlo, thi = slab_bounds(total, comm.world, r)
-            a, b = max(my_lo, tlo), min(my_hi, thi)          # what I hold of rank r's new slab
-            if b > a and r != comm.rank:
-                send[r] = mine[a - my_lo:b - my_lo].contiguous()
-        tlo, thi = slab_bounds(total, comm.world, comm.rank)
-        for r in range(comm.world):
-            a, b = max(int(offs[r]), tlo), min(int(offs[r + 1]), thi)
-            if b > a and r != comm.rank:
-                recv[r] = (b - a, 1 + nv)
-        got = comm.exchange(send, recv, mine)
-        parts = []
-        for r in range(comm.world):
-            if r == comm.rank:
-                a, b = max(my_lo, tlo), min(my_hi, thi)
-                if b > a:
-                    parts.append(mine[a - my_lo:b - my_lo])
-            elif r in got:
-                parts.append(got[r])
-        out = torch.cat(parts, dim=0) if parts else mine[:0]
+        out, tlo, total = rebalance_rows(comm, mine, sizes)
         return out[:, 0].contiguous(), out[:, 1:].contiguous(), tlo, total
 
     def _report(self, comm, work, ne, own_lo, own_hi, lo, n_global, dev):

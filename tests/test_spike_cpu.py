@@ -161,3 +161,74 @@ def test_interface_solve_gloo_world2(periodic):
         lo, hi, x, nrm, low, flag = out[rank]
         assert np.max(np.abs(x - ref[lo:hi])) < 1e-11
         assert abs(nrm - float((ref ** 2).sum())) < 1e-9 and low == 0.0 and flag
+
+
+# ---- re-balancing of the slabs after a refinement pass (splitfxm_b200/slab_refine.py rebalance_rows) ----
+@pytest.mark.parametrize("sizes", [[10, 30, 10, 10], [0, 7, 0, 33], [5, 5, 5, 5], [40, 0, 0, 0], [1, 2, 3], [13]])
+def test_rebalance_rows_thread_ranks(sizes):
+    from splitfxm_b200.distributed import slab_bounds
+    from splitfxm_b200.slab_refine import rebalance_rows
+    from splitfxm_b200.spike import ThreadGroup
+    G, total = len(sizes), sum(sizes)
+    offs = np.concatenate(([0], np.cumsum(sizes)))
+    glob = np.stack([np.arange(total, dtype=np.float64), 100.0 + np.arange(total)], axis=1)
+
+    def body(rank, comm):
+        mine = torch.from_numpy(glob[offs[rank]:offs[rank + 1]].copy())
+        out, tlo, tot = rebalance_rows(comm, mine, sizes)
+        return out.numpy(), tlo, tot
+
+    res = ThreadGroup(G).run(body)
+    for rank, (out, tlo, tot) in enumerate(res):
+        lo, hi = slab_bounds(total, G, rank)
+        assert tot == total and tlo == lo
+        assert np.array_equal(out, glob[lo:hi])              # the right rows, in order, nothing lost or duplicated
+
+
+def _rebalance_gloo_worker(rank, world, port, sizes, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from splitfxm_b200.slab_refine import rebalance_rows
+    from splitfxm_b200.spike import DistComm
+    offs = np.concatenate(([0], np.cumsum(sizes)))
+    total = int(offs[-1])
+    glob = np.stack([np.arange(total, dtype=np.float64), -np.arange(total, dtype=np.float64)], axis=1)
+    mine = torch.from_numpy(glob[offs[rank]:offs[rank + 1]].copy())
+    rows, tlo, tot = rebalance_rows(DistComm(), mine, sizes)
+    out[rank] = (rows.numpy().copy(), tlo, tot)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("sizes", [[3, 17], [20, 0], [9, 9]])
+def test_rebalance_rows_gloo_world2(sizes):
+    from splitfxm_b200.distributed import slab_bounds
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_rebalance_gloo_worker, args=(2, _free_port(), sizes, out), nprocs=2, join=True)
+    total = sum(sizes)
+    for rank in range(2):
+        rows, tlo, tot = out[rank]
+        lo, hi = slab_bounds(total, 2, rank)
+        assert (tlo, tot) == (lo, total)
+        assert np.array_equal(rows[:, 0], np.arange(lo, hi, dtype=np.float64))
+        assert np.array_equal(rows[:, 1], -np.arange(lo, hi, dtype=np.float64))
+
+
+def test_refinement_overlap_rows_thread_ranks():
+    """The six overlap cells a slab copies from each neighbour before marking (slab_refine._neighbour_rows)."""
+    from splitfxm_b200.distributed import slab_bounds
+    from splitfxm_b200.slab_refine import OVERLAP, _neighbour_rows
+    from splitfxm_b200.spike import ThreadGroup
+    G, n = 3, 40
+    glob = np.stack([np.arange(n, dtype=np.float64), 2.0 * np.arange(n)], axis=1)
+
+    def body(rank, comm):
+        lo, hi = slab_bounds(n, G, rank)
+        fl, fr = _neighbour_rows(comm, torch.from_numpy(glob[lo:hi].copy()), lo, hi - lo, n)
+        return lo, hi, fl.numpy(), fr.numpy()
+
+    for lo, hi, fl, fr in ThreadGroup(G).run(body):
+        assert np.array_equal(fl, glob[max(lo - OVERLAP, 0):lo] if lo > 0 else glob[:0])
+        assert np.array_equal(fr, glob[hi:hi + OVERLAP] if hi < n else glob[:0])
