@@ -113,8 +113,6 @@ def newton_on_slabs(args, rank, world, dev):
 def amr_on_slabs(rank, world, dev, n=1_000_000):
     """Refiner on a slab-decomposed mesh: three fronts on n cells, pruning on; the gathered result
     must equal the single-GPU Refiner's mesh bit for bit.  Reported, never raised on one rank only."""
-    import contextlib
-    import io
     import torch
     import torch.distributed as dist
     from splitfxm_b200.distributed import slab_bounds

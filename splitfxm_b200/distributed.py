@@ -9,8 +9,6 @@ variables wrap rank 0 <-> G-1): ``nb * nv`` doubles per side, i.e. latency-bound
 boundary conditions are applied by the kernels on the ranks that own a domain end, exactly as on one GPU, so
 the slab residuals concatenated are bit-identical to the single-mesh residual.
 """
-import ctypes
-
 import numpy as np
 import torch
 
