@@ -22,7 +22,7 @@ from .newton import NewtonDriver
 from .ode import RK45Stepper, euler
 from .refine import Refiner
 from .schemes import FDSchemes, FVSchemes, _scheme_ids, stencil_sizes
-from .simhelper import array_list_reshape, create_bound_events, report_bounds
+from .simhelper import DeviceBounds, array_list_reshape, create_bound_events, report_bounds
 from .system import System
 
 JAC_REQUIRED = ["Radau", "BDF"]
@@ -192,15 +192,17 @@ class Simulation:
         if method == "Euler":
             on_step = None
             if bounds is not None:
+                checker = DeviceBounds(ext_bounds, eng.device)       # compared on the device, offenders only come back
+
                 def on_step(yd, t):
-                    report_bounds(yd.cpu().numpy().reshape(-1), ext_bounds, t)
+                    checker.report(yd, t)
             y, ghost_state, _ = euler(eng, y, t_diff, max_step, split, split_locs, on_step)
         elif method == "RK45":
             stepper = RK45Stepper(eng, split, split_locs, 1e-3, 1e-6, max_step)
             y = stepper.integrate(y, t_diff)
             ghost_state = stepper.last_rhs_state
             if bounds is not None:
-                report_bounds(y.cpu().numpy().reshape(-1), ext_bounds, t_diff)
+                DeviceBounds(ext_bounds, eng.device).report(y, t_diff)
         else:
             # Any other scipy method (RK23, DOP853, LSODA, Radau, BDF ...): scipy.integrate.solve_ivp drives, exactly as
             # in the reference (simulation.py:466-469), with the right-hand side and - for the implicit methods - the
