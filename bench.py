@@ -40,6 +40,8 @@ BCS = {"u": {"left": {"dirichlet": 0.0}, "right": {"dirichlet": 0.0}},
 SPLIT, LOCS = True, [1]
 METRIC = "jacobian_assemblies_per_s"
 UNIT = "assemblies/s (nx=250, nv=3, FDM CENTRAL, split [1])"
+NEWTON_METRIC = "newton_solves_per_s"
+NEWTON_UNIT = "steady states/s (Split-Newton to convergence, nx=250, nv=3, FDM CENTRAL, split [1])"
 
 
 def member_params(first, count, total):
@@ -78,8 +80,18 @@ def member_states(y0, first, count):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: oracle port
+# CPU arms: the unmodified reference (baseline/_ref) when it is installed, else the oracle port
 # ------------------------------------------------------------------------------------------------
+def bench_config(members_per_gpu, world):
+    """`config` of the JSON line - the same object on the GPU arm and on the reference arm."""
+    total = members_per_gpu * world
+    return {"workload": f"configs[1] sparse-Jacobian benchmark shape (nx={NX}, nv={NV}, FDM CENTRAL, nb 1/1, split {LOCS}) "
+                        f"for an ensemble of {members_per_gpu} members per GPU (configs[3] sweep over c, nu; {total} members "
+                        "in total); Newton leg: Split-Newton steady state of every member of the same ensemble",
+            "members_per_gpu": members_per_gpu, "parallelism": f"ensemble-sharded x{world}, no collective",
+            "l2": "inputs+outputs per launch (1.6 GB moved) exceed the 126 MB L2"}
+
+
 def _cpu_assemble(args):
     first, count, total = args
     from oracle import core
@@ -94,43 +106,104 @@ def _cpu_assemble(args):
     return acc
 
 
-def cpu_baseline(sample, total):
+def reference_available():
+    from baseline import reference_env
+    return reference_env.available()
+
+
+def cpu_baseline(sample, newton_sample, total):
+    """Reported baseline on ONE host core, bounded sample of the same ensemble: the unmodified reference
+    (`kind: reference`, baseline/_ref, in a spawned process) or, if it is not installed, the oracle port."""
+    cores_box = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if reference_available():
+        from baseline.ref_worker import RefPool
+        n_j = max(sample // 160, 8)                 # the reference is ~150x slower than the port: 64 assemblies ~ 11 s
+        pool = RefPool(1, n_j, total)
+        try:
+            dt, _ = pool.step("assemble")
+        finally:
+            pool.close()
+        out = {"value": n_j / dt, "unit": UNIT, "cores": 1, "kind": "reference",
+               "sample": f"{n_j} members of the same ensemble, unmodified reference Simulation.jacobian(x0, True, [1]) "
+                         f"(simulation.py:270-394, baseline/_ref), {dt:.2f} s on 1 of {cores_box} host cores"}
+        if newton_sample > 0:
+            pool = RefPool(1, newton_sample, total)
+            try:
+                dtn, res = pool.step("steady")
+            finally:
+                pool.close()
+            its = res[0][1]
+            out["newton"] = {"value": newton_sample / dtn, "unit": NEWTON_UNIT, "cores": 1, "kind": "reference",
+                             "iterations_min_max": [min(its), max(its)],
+                             "sample": f"{newton_sample} members, reference Simulation.steady_state(split=True, split_locs=[1]) "
+                                       f"over the oracle/newton.py stand-in for the absent splitnewton, {dtn:.2f} s on 1 core"}
+        return out
     t0 = time.perf_counter()
     _cpu_assemble((0, sample, total))
     dt = time.perf_counter() - t0
     return {"value": sample / dt, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"{sample} members of the same ensemble, oracle/core.py Problem.jacobian_banded (NumPy colour "
-                      f"passes), {dt:.2f} s on 1 core; the reference itself (per-cell Python loops, simulation.py:"
-                      "270-394) took 0.16 s per assembly in the build container (BASELINE.md)"}
+                      f"passes), {dt:.2f} s on 1 core (baseline/_ref not installed)"}
 
 
 def run_reference(args):
-    """Reference arm: the CPU algorithm on all host cores, bounded sample per step."""
+    """Reference arm: the reference's own CPU implementation on all host cores, bounded sample per step.  Under
+    torchrun only rank 0 works."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    per_proc = max(args.ref_members // cores, 1)
-    sample = per_proc * cores
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     total = args.members * args.gpus
-    jobs = [(i * per_proc, per_proc, total) for i in range(cores)]
-    with mp.get_context("fork").Pool(cores) as pool:
-        for _ in range(args.warmup):
-            pool.map(_cpu_assemble, jobs)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            pool.map(_cpu_assemble, jobs)
-        dt = time.perf_counter() - t0
+    cfg = bench_config(args.members, args.gpus)
+    newton = None
+    if reference_available():
+        from baseline.ref_worker import RefPool
+        kind, per_proc = "reference", max(args.ref_members_per_core, 1)
+        sample = per_proc * cores
+        pool = RefPool(cores, per_proc, total)
+        try:
+            for _ in range(args.warmup):
+                pool.step("assemble")
+            dt = 0.0
+            for _ in range(args.steps):
+                dt += pool.step("assemble")[0]
+            n_steps = max(1, min(args.steps, args.newton_steps))
+            pool.step("steady")
+            dtn, its = 0.0, []
+            for _ in range(n_steps):
+                t, res = pool.step("steady")
+                dtn += t
+                its = [i for r in res for i in r[1]]
+        finally:
+            pool.close()
+        what = (f"{sample} members per step ({per_proc} per process over {cores} processes), unmodified reference "
+                "Simulation.jacobian (baseline/_ref)")
+        newton = {"metric": NEWTON_METRIC, "value": sample * n_steps / dtn, "unit": NEWTON_UNIT, "steps": n_steps,
+                  "ms_per_step": 1e3 * dtn / n_steps, "iterations_min_max": [min(its), max(its)],
+                  "sample": f"{sample} members per step, reference Simulation.steady_state(split=True, split_locs=[1]) over "
+                            "the oracle/newton.py stand-in for the absent third-party splitnewton (parity unpinned)"}
+    else:
+        import multiprocessing as mp
+        kind = "port"
+        per_proc = max(args.ref_members // cores, 1)
+        sample = per_proc * cores
+        jobs = [(i * per_proc, per_proc, total) for i in range(cores)]
+        with mp.get_context("fork").Pool(cores) as pool:
+            for _ in range(args.warmup):
+                pool.map(_cpu_assemble, jobs)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                pool.map(_cpu_assemble, jobs)
+            dt = time.perf_counter() - t0
+        what = f"{sample} members per step over {cores} processes (oracle/core.py; baseline/_ref not installed)"
     value = sample * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"Jacobian assembly nx={NX} nv={NV} FDM CENTRAL split {LOCS}, "
-                                   f"{sample} members per step (bounded sample of the {total}-member ensemble)"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sample} members per step over {cores} processes (oracle/core.py)"},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": what},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "newton": newton}
     print(json.dumps(line), flush=True)
 
 
@@ -265,14 +338,13 @@ def run_gpu(args):
     value = total * args.steps / (elapsed_ms * 1e-3)
 
     # ---- roofline of the Jacobian kernel (this rank's launches) ------------------------------------
-    # algorithmic bytes per launch: read U (nv*8 per cell-member) + x (8 per cell, shared by members), write the
-    # same-segment entries of the band: split [1] -> segments of 1 and 2 variables -> (1 + 4) * W entries
-    # = SURVEY.md 8(d)'s per-unit figure (24 + W * sum s_k^2 * 8 = 144 B per cell-member), which is what `achieved`
-    # is defined on.  Advection-diffusion is one scalar equation per variable, so two of the five same-segment entries
-    # of a block are exact zeros: structural - zero-filled once by the buffer's owner, never re-written - and the kernel
-    # actually moves 24 + W * NV * 8 = 96 B per cell-member (`bytes_moved_per_launch`, `frac_of_bytes_moved`).
+    # `frac` is on the bytes the kernel actually moves: read U (nv*8 per cell-member) + x (8 per cell, shared by the
+    # members), write W*nv entries per cell-member.  Advection-diffusion is one scalar equation per variable, so the
+    # off-diagonal same-segment entries of a block are exact zeros: structural - zero-filled once by the buffer's owner,
+    # never re-written - 24 + W*NV*8 = 96 B per cell-member; ncu dram__bytes (`traffic`) = 1.01x that.  SURVEY 8(d)'s
+    # per-unit figure counts all same-segment entries (24 + W * sum s_k^2 * 8 = 144 B): kept as `survey_8d_*`.
     seg_entries = sum(s * s for s in (LOCS[0], NV - LOCS[0]))
-    alg_bytes = B * NX * (NV * 8 + W * seg_entries * 8) + NX * 8
+    survey_bytes = B * NX * (NV * 8 + W * seg_entries * 8) + NX * 8
     moved_bytes = B * NX * (NV * 8 + W * NV * 8) + NX * 8
     kern_ms = float(np.mean(per_launch_ms))
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -280,19 +352,28 @@ def run_gpu(args):
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-    traffic = None
+    achieved = moved_bytes / (kern_ms * 1e-3) / 1e9
+    traffic, fp64_instr = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("jacobian_kernel_dram_bytes_per_launch")
+        tj = json.load(open(tpath))
+        traffic = tj.get("jacobian_kernel_dram_bytes_per_launch")
+        fp64_instr = tj.get("jacobian_kernel_fp64_instr_per_cell_member")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "jacobian_pair_kernel<ModelAD<3>, FD_CENTRAL, 3, 3, false>",
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms, "peak_source": peak_src,
-                "bytes_moved_per_launch": moved_bytes, "frac_of_bytes_moved": moved_bytes / (kern_ms * 1e-3) / 1e9 / peak,
-                "note": "achieved = SURVEY 8(d) algorithmic bytes (all same-segment entries of the band) / kernel time; the "
-                        "kernel never re-writes the structural zeros of the decoupled model, so it moves a third fewer "
-                        "bytes than that (traffic = ncu DRAM bytes) and is bound by the FP64 pipe (63 % busy, ncu r1j): "
-                        "345 exact-arithmetic FP64 instructions per cell-member = 0.31 ms floor"}
+                "traffic": traffic, "kernel": JAC_KERNEL,
+                "algorithmic_bytes_per_launch": moved_bytes, "kernel_ms": kern_ms, "peak_source": peak_src,
+                "survey_8d_bytes_per_launch": survey_bytes, "survey_8d_frac": survey_bytes / (kern_ms * 1e-3) / 1e9 / peak,
+                "note": "frac = bytes actually moved / kernel time / measured HBM peak"}
+    if fp64_instr:
+        # FP64 pipe: 64 lanes per SM per clock x 148 SMs at the sampled SM clock
+        rate = 148 * 64 * 1.965e9
+        roofline["fp64_pipe_frac"] = fp64_instr * B * NX / rate / (kern_ms * 1e-3)
+        roofline["fp64_instr_per_cell_member"] = fp64_instr
+        roofline["note"] += ("; fp64_pipe_frac = FP64-pipe instructions (ncu) x cell-members / (148 SMs x 64 lanes x "
+                             "1.965 GHz) / kernel time - the exact-arithmetic divisions make this the nearer bound")
+
+    # ---- Newton leg: Split-Newton steady state of every member, on every rank ----------------------
+    newton = newton_leg(args, torch, dist, ens, Y_host, dev, world, total, barrier, peak)
 
     # ---- end to end through the public API with host buffers --------------------------------------
     # Every step uploads its states from pinned host memory and downloads its Jacobians (the same-segment entries -
@@ -328,6 +409,13 @@ def run_gpu(args):
     e2e["checksum_diag_u"] = checksum
     del Jh
 
+    # ---- one large mesh, slab-decomposed over the ranks (BASELINE config 5): every rank, N > 1 only ----
+    slab = None
+    if world > 1 and not args.no_slab:
+        del ens._slots
+        torch.cuda.empty_cache()
+        slab = slab_leg(args, torch, dist, sf, dev, rank, world, peak)
+
     # ---- extras: Newton iterations on the same ensemble, single-mesh sweep -------------------------
     extra = {}
     if rank == 0 and not args.no_extra:
@@ -337,19 +425,175 @@ def run_gpu(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": value / (1.0 / 0.6), "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"configs[1] sparse-Jacobian benchmark shape (nx={NX}, nv={NV}, FDM CENTRAL, "
-                                       f"nb 1/1, split {LOCS}) for an ensemble of {B} members per GPU "
-                                       f"(configs[3] sweep over c, nu; {total} members in total)",
-                           "members_per_gpu": B, "parallelism": f"ensemble-sharded x{world}, no collective",
-                           "l2": "inputs+outputs per launch (%.1f GB) exceed the 126 MB L2" % (alg_bytes / 1e9),
-                           "vs_baseline_note": "BASELINE.md published sparse Jacobian ~0.6 s per assembly at N=250 "
-                                               "(README.md:100-105, hardware unstated)"},
-                "gpu_launches": launches, "roofline": roofline, "e2e": e2e,
-                "cpu_baseline": cpu_baseline(args.cpu_sample, total),
+                "config": bench_config(B, world),
+                "vs_baseline_note": "BASELINE.md published sparse Jacobian ~0.6 s per assembly at N=250 (README.md:100-105, "
+                                    "hardware unstated)",
+                "gpu_launches": launches, "roofline": roofline, "e2e": e2e, "newton": newton, "slab": slab,
+                "cpu_baseline": cpu_baseline(args.cpu_sample, args.cpu_newton_sample, total),
                 "clocks": sampler.summary() if sampler else None, "extra": extra}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+JAC_KERNEL = "jacobian_pair_kernel<ModelAD<3>, FD_CENTRAL, 3, 3, false>"
+
+
+def newton_leg(args, torch, dist, ens, Y_host, dev, world, total, barrier, peak):
+    """BASELINE metric, second half: Newton solves/s = Split-Newton steady states of the ensemble per second.
+    `value`: states resident in HBM; `e2e`: EnsembleSimulation.steady_state_host, pinned host states in, pinned host
+    steady states + iteration counts out, copies inside the timed region.  Runs on every rank; max over ranks."""
+    from splitfxm_b200 import _lib
+    eng = ens.eng
+    B = eng.batch
+    Y = Y_host.to(dev)
+    steps = max(1, min(args.steps, args.newton_steps))
+    ens.steady_state(Y, split=SPLIT, split_locs=LOCS)             # warm the allocator (first call allocates ~2 GB)
+    barrier()
+    _lib.LAUNCHES[0] = 0
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        Yf, its = ens.steady_state(Y, split=SPLIT, split_locs=LOCS)
+    t1.record()
+    barrier()
+    launches = _lib.LAUNCHES[0]
+    t = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / steps
+    res = float(torch.max(torch.abs(eng.residual(Yf, None, SPLIT, LOCS))))
+    it_lo, it_hi = int(its.min()), int(its.max())
+    out_host = torch.empty((eng.n, B), dtype=torch.float64).pin_memory()
+    its_host = torch.empty(B, dtype=torch.int64).pin_memory()
+    ens.steady_state_host(Y_host, out_host, its_host, SPLIT, LOCS)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ens.steady_state_host(Y_host, out_host, its_host, SPLIT, LOCS)
+    e1.record()
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    ms_e = float(te[0]) / steps
+    # linear-solve sweeps actually run: per outer iteration the inner segment is solved to convergence, then one step
+    # on the outer segment; fused algorithmic bytes per cell-member per sweep: s = 1 -> 48, s = 2 -> 128
+    return {"metric": NEWTON_METRIC, "value": total / (ms * 1e-3), "unit": NEWTON_UNIT, "steps": steps, "ms_per_step": ms,
+            "gpu_launches": launches, "iterations_min_max": [it_lo, it_hi], "max_abs_residual": res,
+            "e2e": {"value": total / (ms_e * 1e-3), "unit": NEWTON_UNIT, "ms_per_step": ms_e,
+                    "h2d_bytes_per_step": int(Y_host.numel() * 8), "d2h_bytes_per_step": int(out_host.numel() * 8 + B * 8),
+                    "api": "EnsembleSimulation.steady_state_host(pinned host states -> pinned host steady states + "
+                           "iteration counts)", "checksum": float(out_host[:, 0].sum())}}
+
+
+def slab_leg(args, torch, dist, sf, dev, rank, world, peak):
+    """BASELINE config 5 under the driver: ONE conservative Sod mesh (Euler1DConservative, FVM Lax-Friedrichs, neumann
+    ends), nx = --slab-nx cells in total, slab-decomposed over the ranks; explicit Euler steps with the halo exchange
+    (nb * nv doubles per side) fused into the update kernel as peer stores over NVLink, and the NCCL send/recv variant
+    beside it.  Then Newton on a slab-decomposed advection-diffusion mesh (partitioned block solve, one small
+    all-gather per solve), weak scaling: 1e6 cells per rank.  Nothing raises on one rank only."""
+    from splitfxm_b200.distributed import SlabSimulation
+    out = {}
+    comps = ["rho", "rhou", "E"]
+    bcs = {n: {"left": {"neumann": 0.0}, "right": {"neumann": 0.0}} for n in comps}
+
+    def tmax(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    try:
+        nx = args.slab_nx
+        x = np.linspace(0.0, 1.0, nx)
+        slab = SlabSimulation(x, comps, "euler_cons", {"gamma": 1.4}, bcs, sf.FVSchemes.LAX_FRIEDRICHS, "FVM", rank, world,
+                              device=dev)
+        xs = x[slab.lo:slab.hi]
+        left = xs < 0.5
+        U0 = np.stack([np.where(left, 1.0, 0.125), np.zeros_like(xs), np.where(left, 2.5, 0.25)], axis=1)
+        y = slab.eng.to_device(U0.reshape(-1))
+        dt = 0.4 * (x[1] - x[0]) / 2.2
+        steps = args.slab_steps
+        slab.enable_peer_halos()
+        y, _ = slab.evolve_euler_fused(y, 20 * dt * 0.999999, dt)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        y, nst = slab.evolve_euler_fused(y, steps * dt * 0.999999, dt)
+        t1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = tmax(t0.elapsed_time(t1)) / max(nst, 1)
+        other = torch.empty_like(y)
+        for _ in range(5):
+            slab.exchange(y)
+            slab.eng.euler_step(y, other, dt)
+            y, other = other, y
+        dist.barrier()
+        torch.cuda.synchronize()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record()
+        for _ in range(max(steps // 4, 1)):
+            slab.exchange(y)
+            slab.eng.euler_step(y, other, dt)
+            y, other = other, y
+        n1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms_nccl = tmax(n0.elapsed_time(n1)) / max(steps // 4, 1)
+        fin = torch.tensor([1.0 if bool(torch.isfinite(y).all()) else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(fin, op=dist.ReduceOp.MIN)
+        gbps = (nx / world) * 56 / (ms * 1e-3) / 1e9
+        out["euler_sod"] = {"workload": f"conservative Sod, nx={nx}, explicit Euler (max_step = 0.4 dx / 2.2), slabs x{world}",
+                            "scaling": "strong", "steps": int(nst), "ms_per_step_fused_peer_halo": ms,
+                            "ms_per_step_nccl_halo": ms_nccl, "cell_updates_per_s": nx / (ms * 1e-3),
+                            "GBps_per_gpu": gbps, "frac_of_hbm_peak_per_gpu": gbps / peak,
+                            "bytes_per_cell_step": 56, "finite": bool(fin[0] > 0),
+                            "collective": "none per step (peer stores + flag words over NVLink); NCCL variant: "
+                                          "batch_isend_irecv of nb*nv doubles per side"}
+        del slab, y, other
+        torch.cuda.empty_cache()
+    except Exception as exc:                     # reported, never raised on one rank only
+        out["euler_sod"] = {"error": repr(exc)}
+    try:
+        from splitfxm_b200.spike import DistComm
+        ad_comps = ["u", "v", "w"]
+        ad_bcs = {"u": {"left": {"dirichlet": 1.0}, "right": {"dirichlet": 0.0}},
+                  "v": {"left": {"dirichlet": 3}, "right": {"dirichlet": 4}},
+                  "w": {"left": {"dirichlet": 2}, "right": {"neumann": 0.0}}}
+        nxn = args.slab_newton_nx * world
+        xg = np.linspace(0.0, 1.0, nxn)
+        slab = SlabSimulation(xg, ad_comps, "ad", {"c": 0.2, "nu": 0.05}, ad_bcs, sf.FVSchemes.LAX_FRIEDRICHS, "FVM", rank,
+                              world, device=dev)
+        xs = xg[slab.lo:slab.hi]
+        U0 = np.stack([np.exp(-200 * (xs - 0.25) ** 2), np.where(xs > 0.5, 2.0, 0.0) * (xs - 0.5), (np.abs(xs - 0.5) < 0.25) * 1.0],
+                      axis=1)
+        y0 = slab.eng.to_device(U0.reshape(-1))
+        comm = DistComm()
+        for timed in (False, True):
+            y = y0.clone()
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            its = slab.steady_state(y, False, None, comm=comm)
+            t1.record()
+            torch.cuda.synchronize()
+        ms = tmax(t0.elapsed_time(t1))
+        rn = comm.all_reduce_sum(slab.eng.sumsq(slab.residual(y)))
+        out["newton_ad"] = {"workload": f"advection-diffusion FVM LF, nx={nxn} ({args.slab_newton_nx} cells per rank), unsplit "
+                                        "Newton on slabs (partitioned block solve)", "scaling": "weak",
+                            "iterations": int(its[0]), "ms_total": ms, "ms_per_newton_iteration": ms / max(int(its[0]), 1),
+                            "newton_iterations_per_s": max(int(its[0]), 1) / (ms * 1e-3),
+                            "residual_l2_after": float(torch.sqrt(rn)[0]),
+                            "collective": "one all-gather of 2s(1+2s) doubles per rank per solve + all-reduced norms"}
+        del slab, y, y0
+        torch.cuda.empty_cache()
+    except Exception as exc:
+        out["newton_ad"] = {"error": repr(exc)}
+    return out
 
 
 def extras(torch, sf, ens, Y, dev, peak):
@@ -378,6 +622,14 @@ def extras(torch, sf, ens, Y, dev, peak):
     status = torch.zeros(B, dtype=torch.int32, device=dev)
     ms_res = timed(lambda: eng.residual(Y, r, SPLIT, LOCS), 5)
     ms_solve = timed(lambda: eng.solve(J, r, s, SPLIT, LOCS, status=status), 3)
+    def roof(kernel, nbytes, ms, what):
+        return {"kernel": kernel, "bound": "hbm", "achieved": nbytes / ms / 1e6, "peak": peak, "unit": "GB/s",
+                "frac": nbytes / ms / 1e6 / peak, "algorithmic_bytes_per_launch": int(nbytes), "kernel_ms": ms, "bytes": what}
+
+    rooflines = []
+    out["rooflines"] = rooflines
+    rooflines.append(roof("residual_ring_kernel<ModelAD<3>, FD_CENTRAL> (ensemble residual)", B * NX * 48 + NX * 8, ms_res,
+                          "read U 24 + write r 24 per cell-member"))
     out["ensemble_residual"] = {"ms": ms_res, "GBps": B * NX * 48 / ms_res / 1e6, "frac": B * NX * 48 / ms_res / 1e6 / peak}
     solve_bytes = B * NX * ((1 + 4) * W * 8 + 24 + 24)
     out["ensemble_block_tridiag_solve"] = {"ms": ms_solve, "GBps": solve_bytes / ms_solve / 1e6,
@@ -399,19 +651,14 @@ def extras(torch, sf, ens, Y, dev, peak):
     # fused algorithmic bytes per cell-member: read the segment's U (8 s), write + read C' (8 s^2) and rhs' (8 s),
     # write the step (8 s): s = 1 -> 48, s = 2 -> 128
     fused_bytes = B * NX * (48 + 128)
+    rooflines.append(roof("block_thomas_kernel<MemSrc> (ensemble block-tridiagonal solve, both segments)", solve_bytes, ms_solve,
+                          "read J_seg 120 + f 24, write s 24 per cell-member"))
+    rooflines.append(roof("block_thomas_kernel<FusedSrc> x2 (Newton linear step, Jacobian inside the sweep)", fused_bytes, ms_f,
+                          "s=1: 48, s=2: 128 per cell-member (U, C', rhs', step)"))
     out["ensemble_newton_linear_step"] = {"fused_ms": ms_f, "assemble_then_solve_ms": ms_u,
                                           "bit_identical": bool(torch.equal(s, s2)),
                                           "linear_steps_per_s": B / (ms_f * 1e-3),
                                           "fused_GBps": fused_bytes / ms_f / 1e6, "fused_frac": fused_bytes / ms_f / 1e6 / peak}
-    ens.steady_state(Y, split=SPLIT, split_locs=LOCS)       # warm the allocator (first call allocates ~2 GB)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    Yf, its = ens.steady_state(Y, split=SPLIT, split_locs=LOCS)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    res = float(torch.max(torch.abs(eng.residual(Yf, None, SPLIT, LOCS))))
-    out["ensemble_split_newton"] = {"members": B, "seconds": dt, "steady_states_per_s": B / dt,
-                                    "iterations_min_max": [int(its.min()), int(its.max())], "max_abs_residual": res}
     sweep = []
     for nx in (250, 1000, 10000, 100000, 1000000):
         d = sf.Domain.from_size(nx, 1, 1, COMPS)
@@ -433,6 +680,12 @@ def extras(torch, sf, ens, Y, dev, peak):
         t0 = time.perf_counter()
         iters = sim.steady_state(split=SPLIT, split_locs=LOCS)       # public API, host buffers in and out
         t_ss = time.perf_counter() - t0
+        if nx == 1000000:
+            rooflines.append(roof("jacobian_scalar_kernel (one mesh, nx=1e6)", nx * (24 + 8 + 15 * 8), ms_j,
+                                  "read U 24 + x 8, write 15 same-segment band entries per cell"))
+            rooflines.append(roof("residual_scalar_kernel (one mesh, nx=1e6)", nx * 56, ms_r, "read U 24 + x 8, write r 24"))
+            rooflines.append(roof("Newton iteration, one mesh nx=1e6 (Jacobian + nested-dissection PCR + update/norms)",
+                                  nx * 640, ms_n, "SURVEY 8(d): 640 B per cell per Newton iteration"))
         sweep.append({"nx": nx, "jacobian_ms": ms_j, "jacobian_assemblies_per_s": 1e3 / ms_j,
                       "jacobian_GBps": nx * (24 + 8 + 15 * 8) / ms_j / 1e6, "residual_ms": ms_r,
                       "residual_GBps": nx * 56 / ms_r / 1e6, "newton_iteration_ms": ms_n,
@@ -472,6 +725,9 @@ def extras(torch, sf, ens, Y, dev, peak):
         with contextlib.redirect_stdout(io.StringIO()):
             r.refine(d)
         t_api = time.perf_counter() - t0
+        if nx == 1000000:
+            rooflines.append(roof("AMR pass (sfxm_refine_mark + sfxm_refine_apply), nx=1e6", nx * 96, ms_amr,
+                                  "SURVEY 8(d): ~96 B per cell over both passes"))
         out.setdefault("amr", []).append({"nx": nx, "device_pass_ms": ms_amr, "GBps": nx * 96 / ms_amr / 1e6,
                                           "cells_after": int(counts[0]), "refine_api_s": t_api})
     d = sf.Domain.from_size(100000, 1, 1, comps)
@@ -496,8 +752,17 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--members", type=int, default=65536, help="ensemble members per GPU")
     ap.add_argument("--e2e-steps", type=int, default=12)
-    ap.add_argument("--cpu-sample", type=int, default=10240, help="members the 1-core CPU baseline assembles (~10 s)")
-    ap.add_argument("--ref-members", type=int, default=4096, help="members per step of the reference arm")
+    ap.add_argument("--cpu-sample", type=int, default=10240,
+                    help="members the 1-core oracle-port baseline assembles (~10 s); the reference itself gets 1/160 of it")
+    ap.add_argument("--cpu-newton-sample", type=int, default=8, help="steady states of the 1-core reference baseline")
+    ap.add_argument("--ref-members", type=int, default=4096, help="members per step of the reference arm (oracle port)")
+    ap.add_argument("--ref-members-per-core", type=int, default=1,
+                    help="members per step and host core of the reference arm (unmodified reference, ~0.2 s each)")
+    ap.add_argument("--newton-steps", type=int, default=5, help="timed steady-state passes of the Newton leg")
+    ap.add_argument("--slab-nx", type=int, default=10_000_000)
+    ap.add_argument("--slab-steps", type=int, default=200)
+    ap.add_argument("--slab-newton-nx", type=int, default=1_000_000, help="cells per rank of the slab Newton leg")
+    ap.add_argument("--no-slab", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -103,6 +103,27 @@ class EnsembleSimulation:
         its = drv.run(y, maxiter)
         return y, its
 
+    def steady_state_host(self, Y_host, out_host, its_host, split=False, split_locs=None, dt0=0.0, dtmax=1.0,
+                          armijo=False, bounds=None, maxiter=math.inf):
+        """Host buffers in, host buffers out: Y_host [n, batch] (pinned) is uploaded, every member is Newton-solved on
+        the device, and the final states / iteration counts are downloaded into out_host [n, batch] / its_host [batch]
+        (pinned).  Synchronous: returns when the results are in host memory."""
+        eng = self.eng
+        if not hasattr(self, "_ss_state"):
+            self._ss_state = torch.empty((eng.n, eng.batch), dtype=torch.float64, device=eng.device)
+        y = self._ss_state
+        y.copy_(Y_host, non_blocking=True)
+        key = (bool(split), tuple(split_locs) if split_locs else None, float(dt0), float(dtmax), bool(armijo), bounds is None)
+        drv = getattr(self, "_ss_driver", None)
+        if drv is None or self._ss_key != key or bounds is not None:
+            drv = NewtonDriver(eng, split, split_locs, dt0, dtmax, armijo, bounds)
+            self._ss_driver, self._ss_key = drv, key
+        its = drv.run(y, maxiter)
+        out_host.copy_(y, non_blocking=True)
+        its_host.copy_(its, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_host, its_host
+
     def evolve_euler(self, Y, t_diff, max_step, split=False, split_locs=None):
         y, _, _ = euler(self.eng, self._state(Y).clone(), t_diff, max_step, split, split_locs)
         return y

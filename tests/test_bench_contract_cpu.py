@@ -12,7 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0", "--ref-members", "32"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+                          "--warmup", "0", "--ref-members", "32", "--newton-steps", "1"], capture_output=True, text=True,
+                         timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip().startswith("{")]
     assert len(lines) == 1
@@ -24,8 +25,23 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["steps"] == 1 and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert "workload" in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    sys.path.insert(0, ROOT)
+    from baseline import reference_env
+    # the unmodified reference (baseline/_ref, git-ignored, installed by __graft_entry__.build()) when present, else the port
+    assert cb["kind"] == ("reference" if reference_env.available() else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    if cb["kind"] == "reference":
+        nw = d["newton"]
+        assert nw["metric"] == "newton_solves_per_s" and nw["value"] > 0 and nw["iterations_min_max"][0] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_both_arms_share_one_config():
+    """The driver compares the two arms on `config`: one function builds it for both."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.bench_config(65536, 8) == bench.bench_config(65536, 8)
+    assert "members_per_gpu" in bench.bench_config(128, 2) and "workload" in bench.bench_config(128, 2)
 
 
 def test_reference_arm_other_ranks_exit_quietly():
