@@ -51,7 +51,9 @@ def bound_step(x, s, bounds, bound_fac=BOUND_FAC):
 
 
 def newton(f, J, x0, maxiter=np.inf, sparse=False, dt0=0.0, dtmax=1.0, armijo=False, bounds=None,
-           bound_fac=BOUND_FAC):
+           bound_fac=BOUND_FAC, trace=None):
+    """trace (tests only): a list that receives one dict per iteration - n (unknowns of this solve), alpha (Armijo
+    factor), lam (bound damping), dt (pseudo time step used), crit."""
     if dt0 < 0 or dtmax < 0:
         raise ValueError("Must specify positive dt0 and dtmax")
     x = np.array(x0, dtype=np.float64)
@@ -66,12 +68,12 @@ def newton(f, J, x0, maxiter=np.inf, sparse=False, dt0=0.0, dtmax=1.0, armijo=Fa
     while crit >= 1 and it < maxiter:
         r = np.asarray(f(x), dtype=np.float64)
         A = J(x)
+        dt_used, alpha = dt, 1.0
         if dt0 > 0:
             A = A - (1.0 / dt) * (identity(n, format="csr") if issparse(A) else np.eye(n))
         s = _solve(A, -r, sparse)
         rnorm = np.linalg.norm(r)
         if armijo:
-            alpha = 1.0
             for _ in range(ARMIJO_MAX_HALVINGS):
                 if np.linalg.norm(f(x + alpha * s)) <= (1.0 - ARMIJO_C * alpha) * rnorm:
                     break
@@ -86,15 +88,17 @@ def newton(f, J, x0, maxiter=np.inf, sparse=False, dt0=0.0, dtmax=1.0, armijo=Fa
             dt = min(dt * rnorm / rn, dtmax) if rn > 0 else dtmax
         crit = criterion(x, s)
         it += 1
+        if trace is not None:
+            trace.append(dict(n=n, alpha=alpha, lam=float(lam), dt=dt_used, crit=float(crit)))
     return x, s, it
 
 
 def split_newton(f, J, x0, locs, maxiter=np.inf, sparse=False, dt0=0.0, dtmax=1.0, armijo=False, bounds=None,
-                 bound_fac=BOUND_FAC):
+                 bound_fac=BOUND_FAC, trace=None):
     """locs ascending, in flat-vector units (simulation.py:520: num_points * split_loc)."""
     x0 = np.array(x0, dtype=np.float64)
     if len(locs) == 0:
-        return newton(f, J, x0, maxiter, sparse, dt0, dtmax, armijo, bounds, bound_fac)
+        return newton(f, J, x0, maxiter, sparse, dt0, dtmax, armijo, bounds, bound_fac, trace)
     loc = int(locs[0])
     xa, xb = x0[:loc].copy(), x0[loc:].copy()
     ba = bb = None
@@ -110,13 +114,13 @@ def split_newton(f, J, x0, locs, maxiter=np.inf, sparse=False, dt0=0.0, dtmax=1.
         def fb(y): return np.asarray(f(np.concatenate([xa, y])))[loc:]
         def Jb(y): return J(np.concatenate([xa, y]))[loc:, loc:]
         if rest:
-            xb, sb, _ = split_newton(fb, Jb, xb, rest, maxiter, sparse, dt0, dtmax, armijo, bb, bound_fac)
+            xb, sb, _ = split_newton(fb, Jb, xb, rest, maxiter, sparse, dt0, dtmax, armijo, bb, bound_fac, trace)
         else:
-            xb, sb, _ = newton(fb, Jb, xb, maxiter, sparse, dt0, dtmax, armijo, bb, bound_fac)
+            xb, sb, _ = newton(fb, Jb, xb, maxiter, sparse, dt0, dtmax, armijo, bb, bound_fac, trace)
         # one Newton step on the outer part with the inner part frozen
         def fa(y): return np.asarray(f(np.concatenate([y, xb])))[:loc]
         def Ja(y): return J(np.concatenate([y, xb]))[:loc, :loc]
-        xa, sa, _ = newton(fa, Ja, xa, 1, sparse, dt0, dtmax, armijo, ba, bound_fac)
+        xa, sa, _ = newton(fa, Ja, xa, 1, sparse, dt0, dtmax, armijo, ba, bound_fac, trace)
         x = np.concatenate([xa, xb])
         s = np.concatenate([sa, sb])
         crit = criterion(x, s)

@@ -26,6 +26,18 @@ def slab_bounds(nx, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def slab_neighbours(rank, world, any_per_left, any_per_right):
+    """(left, right) neighbour ranks of a slab, None where there is no neighbour.  Interior faces always have one; the
+    domain ends wrap (rank 0 <-> G-1) when some variable is periodic on EITHER side - one symmetric condition, so that
+    both end ranks post matching messages when a variable is periodic on one side only (bc.py:50-65 allows
+    {'left': 'periodic', 'right': 'outflow'}).  The extra message is harmless: the ghost type of a non-periodic variable
+    stays non-HALO and never reads the buffer."""
+    wrap = bool(any_per_left or any_per_right)
+    left = (rank - 1) if rank > 0 else ((world - 1) if wrap else None)
+    right = (rank + 1) if rank < world - 1 else (0 if wrap else None)
+    return left, right
+
+
 class HaloTransport:
     """Moves the packed boundary cells between neighbouring ranks.  send_left goes to the left neighbour and
     lands in ITS recv_right; send_right goes to the right neighbour's recv_left.  `left`/`right` are neighbour
@@ -80,7 +92,7 @@ class SlabSimulation:
 
     def __init__(self, x_global, comps, model, params, bcs, scheme, method, rank, world, xmin=0.0, xmax=1.0,
                  nbl=1, nbr=1, device=None, transport=None, batch=1):
-        from .ensemble import _MODELS
+        from .ensemble import resolve_model
         if (method == "FVM") != isinstance(scheme, FVSchemes):
             raise SFXM("Scheme family does not match the numerical method")
         if stencil_sizes.get(scheme) != nbl + nbr + 1:
@@ -91,8 +103,8 @@ class SlabSimulation:
         self.lo, self.hi = slab_bounds(nxg, world, rank)
         self.nv, self.nbl, self.nbr = len(comps), nbl, nbr
         self.comps = list(comps)
-        model_id, names = _MODELS[model]
-        table = np.array([float(params[k]) for k in names])
+        model_id, cols = resolve_model(model, params)
+        table = np.array([float(c) for c in cols])
         self.eng = Engine(model_id, _scheme_ids[scheme], self.nv, nbl, nbr, x_global[self.lo:self.hi], xmin, xmax, table,
                           batch=batch, device=device)
         dev = self.eng.device
@@ -109,9 +121,7 @@ class SlabSimulation:
             parsed[self.comps.index(name)] = (_parse_side(bc["left"]), _parse_side(bc["right"]))
         any_per_left = any(p[0][0] == _lib.BC_PERIODIC for p in parsed.values())
         any_per_right = any(p[1][0] == _lib.BC_PERIODIC for p in parsed.values())
-        # neighbours: interior faces always; domain ends only when some variable is periodic there
-        self.left = (rank - 1) if not first else ((world - 1) if any_per_left else None)
-        self.right = (rank + 1) if not last else (0 if any_per_right else None)
+        self.left, self.right = slab_neighbours(rank, world, any_per_left, any_per_right)
         order = [self.comps.index(n) for n in bcs.keys()]      # application order decides the ghost positions
         nx_loc = self.hi - self.lo
 

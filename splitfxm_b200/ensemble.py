@@ -23,19 +23,35 @@ _MODELS = {"ad": (_lib.MODEL_AD, ("c", "nu")), "euler_prim": (_lib.MODEL_EULER_P
            "euler_cons": (_lib.MODEL_EULER_CONS, ("gamma",))}
 
 
+def resolve_model(model, params):
+    """-> (model_id, [one scalar or array[batch] per device parameter]).  model: a built-in name ('ad' | 'euler_prim' |
+    'euler_cons', params: dict name -> value) or a DeviceModel, e.g. from custom.compile_model (params: None for the
+    DeviceModel's own values, or a sequence / dict with one entry per parameter of the functor, in its order)."""
+    if hasattr(model, "model_id"):
+        if params is None:
+            return model.model_id, list(model.params)
+        cols = list(params.values()) if isinstance(params, dict) else list(params)
+        if len(cols) != len(model.params):
+            raise SFXM("one value (or array over the members) per parameter of the device model is needed")
+        return model.model_id, cols
+    if model not in _MODELS:
+        raise SFXM("unknown device model " + str(model))
+    model_id, names = _MODELS[model]
+    return model_id, [params[k] for k in names]
+
+
 class EnsembleSimulation:
     def __init__(self, d, model, params, bcs, scheme, method="FVM", device=None):
-        """d: Domain (mesh, ghosts, components); model: 'ad' | 'euler_prim' | 'euler_cons'; params: dict name ->
-        scalar or array[batch]; bcs: reference-style dict shared by all members."""
-        if model not in _MODELS:
-            raise SFXM("unknown device model " + str(model))
+        """d: Domain (mesh, ghosts, components); model: 'ad' | 'euler_prim' | 'euler_cons' or a DeviceModel (custom
+        models, custom.compile_model); params: dict name -> scalar or array[batch] (see resolve_model); bcs:
+        reference-style dict shared by all members."""
+        model_id, cols = resolve_model(model, params)
         if (method == "FVM") != isinstance(scheme, FVSchemes):
             raise SFXM("Scheme family does not match the numerical method")
         nbl, nbr = d.nb(btype.LEFT), d.nb(btype.RIGHT)
         if stencil_sizes.get(scheme) != nbl + nbr + 1:
             raise SFXM("Stencil size does not match boundary conditions")
-        model_id, names = _MODELS[model]
-        cols = [np.atleast_1d(np.asarray(params[k], dtype=np.float64)) for k in names]
+        cols = [np.atleast_1d(np.asarray(c, dtype=np.float64)) for c in cols]
         batch = max(c.shape[0] for c in cols)
         table = np.stack([np.broadcast_to(c, (batch,)) for c in cols])
         self._d, self._bcs = d, bcs

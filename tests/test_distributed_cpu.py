@@ -59,6 +59,41 @@ def test_halo_transport_world2(periodic):
             assert rr[0, 0] == 10.0 * rnb              # right halo = right neighbour's FIRST cell
 
 
+def _one_sided_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from splitfxm_b200.distributed import HaloTransport, slab_neighbours
+    # a variable periodic on the LEFT only: rank 0 needs rank G-1's last cells; rank G-1 must post the matching send
+    left, right = slab_neighbours(rank, world, True, False)
+    tr = HaloTransport(rank, world, left, right)
+    send_left = torch.tensor([[10.0 * rank]])
+    send_right = torch.tensor([[10.0 * rank + 9]])
+    recv_left = torch.full((1, 1), float("nan"))
+    recv_right = torch.full((1, 1), float("nan"))
+    tr.exchange(send_left, send_right, recv_left, recv_right)
+    out[rank] = (left, right, float(recv_left[0, 0]), float(recv_right[0, 0]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_one_sided_periodic_wrap_completes(world):
+    """with per-side wrap decisions rank 0 waited for a message rank G-1 never sent."""
+    from splitfxm_b200.distributed import slab_neighbours
+    assert slab_neighbours(0, 4, False, False) == (None, 1) and slab_neighbours(3, 4, False, False) == (2, None)
+    assert slab_neighbours(0, 4, True, False) == (3, 1) and slab_neighbours(3, 4, True, False) == (2, 0)
+    assert slab_neighbours(0, 4, False, True) == (3, 1) and slab_neighbours(3, 4, False, True) == (2, 0)
+    assert slab_neighbours(0, 1, False, True) == (0, 0)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_one_sided_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    left, right, rl, rr = out[0]
+    assert left == world - 1 and rl == 10.0 * (world - 1) + 9       # rank 0's left ghosts = last cell of rank G-1
+    left, right, rl, rr = out[world - 1]
+    assert right == 0 and rr == 0.0
+
+
 def test_slab_bounds_cover_mesh():
     from splitfxm_b200.distributed import slab_bounds
     for nx, world in ((10, 3), (1000, 8), (10_000_000, 8), (17, 1)):

@@ -4,45 +4,7 @@ residual/Jacobian machinery evaluating the same model in NumPy (oracle/core.py w
 import numpy as np
 import pytest
 
-BURGERS = """
-struct UserModel {                       // u_t + (u^2/2)_x = nu u_xx, every variable independently
-  static constexpr int kParams = 1;
-  static constexpr bool kDiagonalDFDU = true, kHasDiffusion = true, kDecoupled = false;
-  using Scalar = UserModel;
-  __device__ static void F(const double* p, const double (&u)[NV], double (&f)[NV]) {
-    for (int j = 0; j < NV; ++j) f[j] = 0.5 * (u[j] * u[j]);
-  }
-  __device__ static void D(const double* p, const double (&u)[NV], double (&d)[NV]) {
-    for (int j = 0; j < NV; ++j) d[j] = p[0] * u[j];
-  }
-  __device__ static double sigma(const double* p, const double (&u)[NV]) {
-    double s = 0.0;
-    for (int j = 0; j < NV; ++j) s = fmax(s, fabs(u[j]));
-    return s;
-  }
-  __device__ static double eig(const double* p, const double (&u)[NV], int j) { return u[j]; }
-};
-"""
-
-
-class OracleBurgers:
-    name = "burgers"
-    diagonal_dfdu = True
-
-    def __init__(self, nu):
-        self.nu = nu
-
-    def F(self, U):
-        return 0.5 * (U * U)
-
-    def D(self, U):
-        return self.nu * U
-
-    def sigma(self, U):
-        return np.max(np.abs(U), axis=-1)
-
-    def eig_diag(self, U):
-        return U
+from nonlinear_cases import BURGERS_SRC as BURGERS, OracleBurgers  # noqa: E402
 
 
 def test_plugin_compiles_on_cpu():

@@ -194,3 +194,44 @@ def test_host_round_trip_of_packed_jacobians():
         for e, (r, c) in enumerate(live):
             assert np.array_equal(outs[k].numpy()[:, :, e, :], full[:, :, r, c, :])
         assert not full[:, :, 1, 2, :].any() and not full[:, :, 2, 1, :].any()      # what was left out is all zero
+
+
+@pytest.mark.parametrize("B", [128, 127])
+def test_bench_configuration_matches_oracle(B):
+    """The BENCHED kernel configuration itself, against the oracle member by member: bench.BCS (dirichlet u), 3
+    variables, FDM CENTRAL, split [1], the bench's own member parameters and states.  B = 128 runs
+    jacobian_pair_kernel / residual_ring_kernel (two members per lane - what bench.py times), B = 127 the per-member
+    kernels.  Values and zero pattern of the block-banded Jacobian and the residual are bit-equal."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    import splitfxm_b200 as sf
+    from oracle import core
+    from splitfxm_b200.ensemble import EnsembleSimulation
+    x, y0 = bench.initial_state()
+    xo, y0o = bench.initial_state_oracle()
+    assert np.array_equal(x, xo) and np.array_equal(y0, y0o)            # both arms start from the same vector
+    total = 65536
+    first = 4096 - 5                                                    # a slice that straddles a row of the (c, nu) grid
+    c, nu = bench.member_params(first, B, total)
+    Y = bench.member_states(y0, first, B)
+    d = sf.Domain.from_size(bench.NX, 1, 1, bench.COMPS)
+    ens = EnsembleSimulation(d, "ad", {"c": c, "nu": nu}, bench.BCS, sf.FDSchemes.CENTRAL, method="FDM")
+    J = ens.jacobian(Y, bench.SPLIT, bench.LOCS).cpu().numpy()          # [nx, W, nv, nv, B]
+    R = ens.residual(Y, bench.SPLIT, bench.LOCS).cpu().numpy()
+    for k in range(B):
+        P = core.Problem(core.AdvectionDiffusion(c[k], nu[k]), "FDM", "CENTRAL", x, 1, 1, bench.BCS, bench.COMPS)
+        Ub = core.to_block(Y[:, k], bench.NX, bench.NV, bench.SPLIT, bench.LOCS)
+        Jb = P.jacobian_banded(Ub)
+        assert np.array_equal(J[..., k], Jb), k
+        assert np.array_equal(R[:, k], P.residual(Y[:, k], bench.SPLIT, bench.LOCS)), k
+    # and the host round trip bench.py's e2e leg times returns exactly the live entries of those Jacobians
+    import torch
+    if B % 2 == 0:
+        live = ens.eng.live_entries(bench.SPLIT, bench.LOCS)
+        out = torch.empty((bench.NX, bench.W, len(live), B), dtype=torch.float64).pin_memory()
+        ens.jacobian_host(torch.from_numpy(Y).pin_memory(), out, bench.SPLIT, bench.LOCS)
+        ens.sync_host()
+        for e, (r, cc) in enumerate(live):
+            assert np.array_equal(out.numpy()[:, :, e, :], J[:, :, r, cc, :])

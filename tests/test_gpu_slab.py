@@ -36,7 +36,7 @@ def _gather(tr, vecs, split, locs):
 
 
 @pytest.mark.parametrize("G", [2, 3])
-@pytest.mark.parametrize("case", ["ad_fvm_readme", "ad_fdm_rbias", "sod_cons"])
+@pytest.mark.parametrize("case", ["ad_fvm_readme", "ad_fdm_rbias", "sod_cons", "ad_one_sided_periodic"])
 def test_slabs_reproduce_single_mesh(case, G):
     import splitfxm_b200 as sf
     from splitfxm_b200.models.advection_diffusion import AdvectionDiffusion
@@ -47,6 +47,13 @@ def test_slabs_reproduce_single_mesh(case, G):
         comps, bcs, nbl, nbr = ["u", "v", "w"], README_BCS, 1, 1
         model, mname, params, scheme, method = AdvectionDiffusion(0.2, 0.001, "FVM"), "ad", {"c": 0.2, "nu": 0.001}, sf.FVSchemes.LAX_FRIEDRICHS, "FVM"
         split, locs = True, [1, 2]
+        U = rng.standard_normal((nx, 3))
+    elif case == "ad_one_sided_periodic":          # bc.py allows periodic on one side only
+        comps, nbl, nbr = ["u", "v", "w"], 1, 1
+        bcs = {"u": {"left": "periodic", "right": "outflow"}, "v": {"left": {"dirichlet": 3}, "right": {"neumann": 0.5}},
+               "w": {"left": "outflow", "right": {"dirichlet": 1.0}}}
+        model, mname, params, scheme, method = AdvectionDiffusion(0.2, 0.01, "FVM"), "ad", {"c": 0.2, "nu": 0.01}, sf.FVSchemes.LAX_FRIEDRICHS, "FVM"
+        split, locs = True, [1]
         U = rng.standard_normal((nx, 3))
     elif case == "ad_fdm_rbias":
         comps, bcs, nbl, nbr = ["u", "v", "w"], README_BCS, 1, 2

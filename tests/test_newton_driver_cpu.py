@@ -33,13 +33,13 @@ class OracleEngine:
     """The Engine interface NewtonDriver uses, batch 1, on CPU tensors; rows [row_lo, row_hi) of every flat vector are
     this rank's (the whole vector when there is one rank)."""
 
-    def __init__(self, P, split, locs, comm=None):
+    def __init__(self, P, split, locs, comm=None, nx=NX, nv=3):
         from splitfxm_b200.engine import split_segments
         self.P, self.split, self.locs = P, split, locs
-        self.nx, self.nv, self.batch = NX, 3, 1
-        self.n = NX * 3
+        self.nx, self.nv, self.batch = nx, nv, 1
+        self.n = nx * nv
         self.device = torch.device("cpu")
-        self.segs = split_segments(3, split, locs)
+        self.segs = split_segments(nv, split, locs)
         self.comm = comm
         if comm is not None:                       # norms are summed over the ranks; every rank holds the whole state
             self.reduce_min = lambda t: comm.all_reduce_min(t)
@@ -129,11 +129,11 @@ def _extend_bounds(bounds, split, locs):
             for b in bounds]
 
 
-def _driver_run(eng, x0, split, locs, kw):
+def _driver_run(eng, x0, split, locs, kw, ext_bounds=None):
     from splitfxm_b200.newton import NewtonDriver
     dkw = dict(kw)
     bounds = dkw.pop("bounds", None)
-    ext = _extend_bounds(bounds, split, locs) if bounds is not None else None
+    ext = ext_bounds if ext_bounds is not None else (_extend_bounds(bounds, split, locs) if bounds is not None else None)
     y = torch.from_numpy(x0.copy()).reshape(-1, 1)
     drv = NewtonDriver(eng, split, locs, dkw.get("dt0", 0.0), dkw.get("dtmax", 1.0), dkw.get("armijo", False), ext)
     assert not drv.fused
@@ -146,6 +146,26 @@ def test_driver_follows_the_specification(split, locs, kw):
     P, U = _problem()
     x0, xf, it_ref = _reference_run(P, U, split, locs, kw)
     it, x = _driver_run(OracleEngine(P, split, locs), x0, split, locs, kw)
+    assert it == it_ref
+    assert np.max(np.abs(x - xf)) <= 1e-10 * max(1.0, np.max(np.abs(xf)))
+
+
+def _nonlinear_names():
+    from nonlinear_cases import CASES as NL
+    return sorted(NL)
+
+
+@pytest.mark.parametrize("name", _nonlinear_names())
+def test_driver_follows_the_specification_on_nonlinear_problems(name):
+    """Burgers (viscous shock, custom model) and the Euler duct: >= 4 iterations with active Armijo back-tracking,
+    bound clipping and pseudo-transient growth (tests/test_newton_nonlinear_oracle.py asserts those branches are taken);
+    the device driver's control logic must reproduce the specification's iteration count and iterate."""
+    from nonlinear_cases import extend_bounds, oracle_case, oracle_solve
+    P, U0, c = oracle_case(name)
+    nx, nv = U0.shape
+    x0, xf, it_ref, _ = oracle_solve(name)
+    ext = extend_bounds(c["kw"]["bounds"], nx, nv, c["split"], c["locs"]) if "bounds" in c["kw"] else None
+    it, x = _driver_run(OracleEngine(P, c["split"], c["locs"], nx=nx, nv=nv), x0, c["split"], c["locs"], c["kw"], ext)
     assert it == it_ref
     assert np.max(np.abs(x - xf)) <= 1e-10 * max(1.0, np.max(np.abs(xf)))
 
