@@ -230,6 +230,11 @@ int sfxm_refine_flags(const void *work, int64_t n, uint8_t *loc_out, uint8_t *ke
                       int32_t *comp_out, void *stream);
 int sfxm_refine_apply(const double *x, const double *U, int64_t n, int32_t nv, const void *work, double *x_out,
                       double *U_out, void *stream);
+/* Explicit flags instead of sfxm_refine_mark - Refiner.perform_changes(d, loc, keep), refine.py:239-282:
+ * keep_in[t] = 0 deletes cell t, loc_in[t] = 1 inserts the midpoint after cell t (device byte arrays [n]); fills the
+ * workspace (scans, counts_dev as for sfxm_refine_mark) so that sfxm_refine_apply builds the new mesh. */
+int sfxm_refine_set_flags(const uint8_t *loc_in, const uint8_t *keep_in, int64_t n, void *work, int64_t *counts_dev,
+                          void *stream);
 
 /* The same refinement on a WINDOW of a slab-decomposed mesh (AMR over several GPUs).  x[ne], U[ne * nv] hold
  * the global cells g0 .. g0 + ne - 1 of a mesh of ng cells; [own_lo, own_hi) (window indices) are this rank's cells, the
@@ -285,6 +290,14 @@ int sfxm_fv_fluxes(int32_t scheme, int32_t nv, const double *F, const double *u,
 int sfxm_fv_diffusion_fluxes(int32_t nv, const double *D, const double *x, double *Dw, double *De, void *stream);
 int sfxm_fd_derivative(int32_t scheme, int32_t order, int32_t nv, const double *F, const double *x, double *out,
                        void *stream);
+/* One cell's residual from the stencil VALUES - the arithmetic of FVTransportEquation.residuals
+ * (equations/fv_transport.py:49-58: rhs = (S - (1/dx)(Fe - Fw)) + (1/dx)(DFe - DFw)) and FDTransportEquation.residuals
+ * (equations/fd_transport.py:46-50: rhs = (S - Dx(F)) + D2x(D)) in ONE launch.  F, D, u: [slots][nv]; x: [slots];
+ * S: [nv]; sigma / eig as for sfxm_fv_fluxes. */
+int sfxm_fv_cell_residual(int32_t scheme, int32_t nv, const double *F, const double *D, const double *u, const double *x,
+                          const double *S, double sigma, const double *eig, double *out, void *stream);
+int sfxm_fd_cell_residual(int32_t scheme, int32_t nv, const double *F, const double *D, const double *x, const double *S,
+                          double *out, void *stream);
 
 /* Device self-test: counts (into *mismatch_dev, a device uint64 the caller zeroes) operands for which the
  * five-FMA division by a known reciprocal used in the stencil kernels differs from the IEEE quotient.

@@ -79,6 +79,7 @@ SIGNATURES = {
     "sfxm_refine_mark": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_f64, c_f64, c_f64, c_f64, c_f64, c_f64, c_vp, c_vp, c_vp]),
     "sfxm_refine_flags": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_refine_apply": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_refine_set_flags": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "sfxm_refine_window_stats": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "sfxm_refine_window_mark": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, c_i64, c_i64, c_f64, c_f64, c_f64,
                                                c_f64, c_f64, c_f64, c_vp, c_vp, c_vp, c_vp]),
@@ -93,6 +94,8 @@ SIGNATURES = {
     "sfxm_fv_fluxes": (ctypes.c_int, [c_i32, c_i32, c_vp, c_vp, c_f64, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_fv_diffusion_fluxes": (ctypes.c_int, [c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_fd_derivative": (ctypes.c_int, [c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_fv_cell_residual": (ctypes.c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_f64, c_vp, c_vp, c_vp]),
+    "sfxm_fd_cell_residual": (ctypes.c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_selftest_div": (ctypes.c_int, [c_i64, ctypes.c_uint64, c_i32, c_vp, c_vp]),
 }
 
@@ -131,6 +134,7 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+AMR_MARK_LAUNCHES = 10   # kernels sfxm_refine_mark issues (csrc/sfxm_amr.cu)
 LAUNCHES = [0]   # number of kernel launches issued through the C ABI (bench.py reports it)
 
 

@@ -116,20 +116,26 @@ def describe_bcs(prob, bcs: dict, d: Domain):
     variables, so the rule of the LAST variable in that order decides what is stored (bc.py:56-151)."""
     nv = d.num_components()
     nbl, nbr = d.nb(btype.LEFT), d.nb(btype.RIGHT)
-    x, U = d._x, d._U
-    n = x.shape[0]
+    covered = {d.component_index(name) for name in bcs}
+    need_ghosts = len(covered) < nv        # a variable without a BC keeps the ghost cells the Domain holds
+    if need_ghosts:
+        x, U = d._host()                   # read-only host copy (refreshed from the device if stale)
+        n = x.shape[0]
     for j in range(nv):
         prob.bc_ltype[j] = _lib.BC_KEEP
         prob.bc_rtype[j] = _lib.BC_KEEP
         for g in range(min(nbl, _lib.MAX_NB)):
-            prob.bc_lval[j][g] = float(U[nbl - 1 - g, j])
+            prob.bc_lval[j][g] = float(U[nbl - 1 - g, j]) if need_ghosts else 0.0
         for g in range(min(nbr, _lib.MAX_NB)):
-            prob.bc_rval[j][g] = float(U[n - nbr + g, j])
+            prob.bc_rval[j][g] = float(U[n - nbr + g, j]) if need_ghosts else 0.0
     prob.gx_left = prob.gx_right = _lib.GX_KEEP
-    for g in range(min(nbl, _lib.MAX_NB)):
-        prob.gx_keep_left[g] = float(x[nbl - 1 - g])
-    for g in range(min(nbr, _lib.MAX_NB)):
-        prob.gx_keep_right[g] = float(x[n - nbr + g])
+    if not bcs:                            # no BC at all: the ghost positions stay what they are
+        x = d._host()[0]
+        n = x.shape[0]
+        for g in range(min(nbl, _lib.MAX_NB)):
+            prob.gx_keep_left[g] = float(x[nbl - 1 - g])
+        for g in range(min(nbr, _lib.MAX_NB)):
+            prob.gx_keep_right[g] = float(x[n - nbr + g])
     for name, bc in bcs.items():
         j = d.component_index(name)
         _check_dirs(bc)

@@ -347,6 +347,20 @@ static int amr_apply_t(const double *z, const double *U, const Window &wd, const
   return check_launch("sfxm_refine_apply");
 }
 
+// explicit flags (Refiner.perform_changes(d, loc, keep), refine.py:239-282): keep_in[t] = 0 deletes cell t, loc_in[t] = 1
+// inserts the midpoint after cell t
+__global__ void amr_set_flags_kernel(const uint8_t *__restrict__ loc_in, const uint8_t *__restrict__ keep_in, int64_t n,
+                                     uint8_t *__restrict__ loc, uint8_t *__restrict__ keepf, int64_t *__restrict__ kept_cnt,
+                                     int64_t *__restrict__ ins_cnt) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint8_t k = keep_in[t] ? 1 : 0, l = loc_in[t] ? 1 : 0;
+  loc[t] = l;
+  keepf[t] = k;
+  kept_cnt[t] = k;
+  ins_cnt[t] = (l && t + 1 < n) ? 1 : 0;
+}
+
 #define SFXM_NV_SWITCH(nv, CALL)                                   \
   switch (nv) {                                                    \
     case 1: { constexpr int NVV = 1; e = CALL; } break;            \
@@ -379,6 +393,28 @@ extern "C" int sfxm_refine_mark(const double *x, const double *U, int64_t n, int
   SFXM_NV_SWITCH(nv, (amr_mark_t<NVV>(x, U, wd, cr, stats, wk, nullptr, st)));
   if (e) return e;
   return amr_finalize_t(wd, -1, wk, counts_dev, st);
+}
+
+extern "C" int sfxm_refine_set_flags(const uint8_t *loc_in, const uint8_t *keep_in, int64_t n, void *work,
+                                     int64_t *counts_dev, void *stream) {
+  if (!loc_in || !keep_in || !work || !counts_dev) return set_error("sfxm_refine_set_flags: null argument");
+  if (n < 2 || n > 2147483647LL) return set_error("sfxm_refine_set_flags: bad mesh size");
+  const AmrWork w = amr_layout(n);
+  const Window wd{n, 0, n, 0, n};
+  cudaStream_t st = (cudaStream_t)stream;
+  char *wk = (char *)work;
+  amr_set_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(loc_in, keep_in, n, (uint8_t *)(wk + w.off_loc),
+                                                                  (uint8_t *)(wk + w.off_keepf), (int64_t *)(wk + w.off_kcnt),
+                                                                  (int64_t *)(wk + w.off_icnt));
+  size_t cb = (size_t)w.cub_bytes;
+  cub::DeviceScan::ExclusiveSum((void *)(wk + w.off_cub), cb, (const int64_t *)(wk + w.off_kcnt), (int64_t *)(wk + w.off_kbef),
+                                (int)n, st);
+  cb = (size_t)w.cub_bytes;
+  cub::DeviceScan::ExclusiveSum((void *)(wk + w.off_cub), cb, (const int64_t *)(wk + w.off_icnt), (int64_t *)(wk + w.off_ibef),
+                                (int)n, st);
+  amr_count_kernel<<<1, 1, 0, st>>>((const int64_t *)(wk + w.off_kbef), (const int64_t *)(wk + w.off_ibef),
+                                    (const int64_t *)(wk + w.off_kcnt), (const int64_t *)(wk + w.off_icnt), wd, counts_dev);
+  return check_launch("sfxm_refine_set_flags");
 }
 
 extern "C" int sfxm_refine_flags(const void *work, int64_t n, uint8_t *loc_out, uint8_t *keep_out, uint8_t *gridpt_out,

@@ -67,9 +67,79 @@ __global__ void fd_derivative_kernel(int scheme, int order, int nv, const double
   }
 }
 
+// One cell's finite-volume residual from the stencil VALUES (fv_transport.py:49-58): the fluxes above, then
+// rhs = (S - (1/dx)(Fe - Fw)) + (1/dx)(DFe - DFw) with dx = 0.5 (dxw + dxe).  F, D, u: [3][nv]; x: [3]; S: [nv].
+__global__ void fv_cell_residual_kernel(int scheme, int nv, const double *__restrict__ F, const double *__restrict__ D,
+                                        const double *__restrict__ u, const double *__restrict__ x,
+                                        const double *__restrict__ S, double sigma, const double *__restrict__ eig,
+                                        double *__restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nv) return;
+  const double Fl = F[j], Fc = F[nv + j], Fr = F[2 * nv + j];
+  double Fw, Fe;
+  if (scheme == SFXM_FV_LAX_FRIEDRICHS) {
+    const double hs = 0.5 * sigma;
+    Fw = 0.5 * (Fl + Fc) - hs * (u[nv + j] - u[j]);
+    Fe = 0.5 * (Fc + Fr) - hs * (u[2 * nv + j] - u[nv + j]);
+  } else if (scheme == SFXM_FV_CENTRAL) {
+    Fw = 0.5 * (Fl + Fc);
+    Fe = 0.5 * (Fc + Fr);
+  } else {
+    const bool pos = eig[j] > 0.0;
+    Fw = pos ? Fl : Fc;
+    Fe = pos ? Fc : Fr;
+  }
+  const double dxw = x[1] - x[0], dxe = x[2] - x[1];
+  const double DFw = (D[nv + j] - D[j]) / (0.5 * dxw);
+  const double DFe = (D[2 * nv + j] - D[nv + j]) / (0.5 * dxe);
+  const double dx = 0.5 * (dxw + dxe);
+  const double inv = 1.0 / dx;
+  out[j] = (S[j] - inv * (Fe - Fw)) + inv * (DFe - DFw);
+}
+
+// One cell's finite-difference residual (fd_transport.py:46-50): rhs = (S - Dx(F)) + D2x(D).  F, D: [W][nv]; x: [W].
+__global__ void fd_cell_residual_kernel(int scheme, int nv, const double *__restrict__ F, const double *__restrict__ D,
+                                        const double *__restrict__ x, const double *__restrict__ S,
+                                        double *__restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nv) return;
+  double d1, d2;
+  if (scheme == SFXM_FD_CENTRAL) {
+    d1 = (F[2 * nv + j] - F[j]) / (x[2] - x[0]);
+    const double dxw = x[1] - x[0], dxe = x[2] - x[1];
+    const double Dw = (D[nv + j] - D[j]) / dxw;
+    const double De = (D[2 * nv + j] - D[nv + j]) / dxe;
+    d2 = (De - Dw) / ((dxw + dxe) / 2.0);
+  } else {
+    const double h = x[1] - x[0];
+    d1 = (((-F[j] - F[nv + j]) + F[2 * nv + j]) + F[3 * nv + j]) / (4.0 * h);
+    d2 = (((D[j] - D[nv + j]) - D[2 * nv + j]) + D[3 * nv + j]) / (2.0 * (h * h));
+  }
+  out[j] = (S[j] - d1) + d2;
+}
+
 }  // namespace sfxm
 
 using namespace sfxm;
+
+extern "C" int sfxm_fv_cell_residual(int32_t scheme, int32_t nv, const double *F, const double *D, const double *u,
+                                     const double *x, const double *S, double sigma, const double *eig, double *out,
+                                     void *stream) {
+  if (nv < 1 || !F || !D || !u || !x || !S || !out) return set_error("sfxm_fv_cell_residual: bad argument");
+  if (scheme != SFXM_FV_LAX_FRIEDRICHS && scheme != SFXM_FV_CENTRAL && scheme != SFXM_FV_UPWIND)
+    return set_error("Unsupported scheme");
+  if (scheme == SFXM_FV_UPWIND && !eig) return set_error("dFdU is required for determining upwind direction.");
+  fv_cell_residual_kernel<<<(nv + 63) / 64, 64, 0, (cudaStream_t)stream>>>(scheme, nv, F, D, u, x, S, sigma, eig, out);
+  return check_launch("sfxm_fv_cell_residual");
+}
+
+extern "C" int sfxm_fd_cell_residual(int32_t scheme, int32_t nv, const double *F, const double *D, const double *x,
+                                     const double *S, double *out, void *stream) {
+  if (nv < 1 || !F || !D || !x || !S || !out) return set_error("sfxm_fd_cell_residual: bad argument");
+  if (scheme != SFXM_FD_CENTRAL && scheme != SFXM_FD_RIGHT_BIAS) return set_error("Unsupported scheme");
+  fd_cell_residual_kernel<<<(nv + 63) / 64, 64, 0, (cudaStream_t)stream>>>(scheme, nv, F, D, x, S, out);
+  return check_launch("sfxm_fd_cell_residual");
+}
 
 extern "C" int sfxm_fv_fluxes(int32_t scheme, int32_t nv, const double *F, const double *u, double sigma,
                               const double *eig, double *Fw, double *Fe, void *stream) {

@@ -56,17 +56,26 @@ class Engine:
 
     # -- configuration -------------------------------------------------------------------------------
     def set_mesh(self, x_int):
-        x_int = np.ascontiguousarray(x_int, dtype=np.float64)
-        self.nx = int(x_int.shape[0])
+        """x_int: interior positions, a host array or a CUDA tensor (used in place when contiguous FP64)."""
+        if isinstance(x_int, torch.Tensor):
+            xt = x_int.to(device=self.device, dtype=torch.float64).contiguous()
+        else:
+            xt = torch.from_numpy(np.ascontiguousarray(x_int, dtype=np.float64)).to(self.device)
+        self.nx = int(xt.shape[0])
         self.n = self.nx * self.nv
-        self.x_int = torch.from_numpy(x_int).to(self.device)
+        self.x_int = xt
         self._probs = {}
         self._work = {}
         self._geom = None
+        self._flat_idx = {}
 
     def set_params(self, params):
         """params: [n_params] (shared) or [n_params, batch] (per member)."""
         p = np.ascontiguousarray(params, dtype=np.float64)
+        last = getattr(self, "_params_host", None)
+        if last is not None and last.shape == p.shape and np.array_equal(last, p):
+            return
+        self._params_host = p.copy()
         if p.ndim == 1:
             self.param_stride = 0
         elif p.ndim == 2 and p.shape[1] == self.batch:
@@ -110,6 +119,39 @@ class Engine:
             _lib.check(self.lib.sfxm_geometry(ctypes.byref(P), _lib.ptr(self.x_int), _lib.ptr(self._geom), _lib.stream_ptr()))
             _lib.count()
         return P, segs
+
+    # -- flat vector <-> [nx, nv] block, on the device (simulation.py:107-148, domain.py:276-312) -------
+    def _flat_index(self, split, split_locs):
+        key = (bool(split), tuple(sorted(set(split_locs))) if (split and split_locs is not None) else None)
+        hit = self._flat_idx.get(key)
+        if hit is None:
+            segs = split_segments(self.nv, split, split_locs)
+            if len(segs) == 1:
+                hit = False                  # unsplit: the flat vector IS the row-major block
+            else:
+                p = torch.arange(self.nx, dtype=torch.int64, device=self.device)[:, None]
+                cols = []
+                for (o, s) in segs:
+                    for j in range(o, o + s):
+                        cols.append(o * self.nx + p * s + (j - o))
+                hit = torch.cat(cols, dim=1).reshape(-1)
+            self._flat_idx[key] = hit
+        return hit
+
+    def block_to_flat(self, Ub, split=False, split_locs=None):
+        """[nx, nv] device block -> flat state [n, 1] in the (split-major) vector order; batch 1."""
+        idx = self._flat_index(split, split_locs)
+        if idx is False:
+            return Ub.reshape(self.n, 1).clone()
+        y = torch.empty((self.n, 1), dtype=torch.float64, device=self.device)
+        y[idx, 0] = Ub.reshape(-1)
+        return y
+
+    def flat_to_block(self, y, split=False, split_locs=None):
+        idx = self._flat_index(split, split_locs)
+        if idx is False:
+            return y.reshape(self.nx, self.nv)
+        return y.reshape(-1)[idx].reshape(self.nx, self.nv)
 
     # -- memory ----------------------------------------------------------------------------------------
     def empty_state(self):

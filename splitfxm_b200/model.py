@@ -7,10 +7,19 @@ fallback: Simulation raises SFXM for it."""
 
 
 class DeviceModel:
+    """params: a list of numbers, or a callable returning one - evaluated at every solver call, so that a model whose
+    attributes are changed after construction (``model.c = 0.3``) is seen with its current values, as in the reference,
+    whose F / D read ``self.c`` at call time (models/advection_diffusion.py:28-31)."""
+
     def __init__(self, model_id, params, method):
         self.model_id = int(model_id)
-        self.params = [float(p) for p in params]
+        self._params = params
         self.method = method
+
+    @property
+    def params(self):
+        p = self._params() if callable(self._params) else self._params
+        return [float(v) for v in p]
 
 
 class Model:

@@ -18,7 +18,7 @@ class AdvectionDiffusion(Model):
         if method not in ("FDM", "FVM"):
             raise SFXM("Invalid numerical method specified")
         self.c, self.nu = c, nu
-        self._device = DeviceModel(_lib.MODEL_AD, [c, nu], method)
+        self._device = DeviceModel(_lib.MODEL_AD, lambda: [self.c, self.nu], method)
         if method == "FVM":
             self._equation = FVTransportEquation(self.flux, self.diffused, self.source, self.flux_jacobian)
         else:

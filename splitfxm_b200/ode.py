@@ -54,7 +54,7 @@ class RK45Stepper:
     over all slabs of a decomposed mesh (default: identity); n_global: number of unknowns of the whole mesh."""
 
     def __init__(self, eng, split=False, split_locs=None, rtol=1e-3, atol=1e-6, max_step=np.inf, rhs=None, reduce=None,
-                 n_global=None):
+                 n_global=None, on_step=None):
         if eng.batch != 1:
             raise SFXM("adaptive RK45 drives one mesh; ensembles use Euler stepping or per-member Simulations")
         if max_step <= 0:
@@ -73,6 +73,7 @@ class RK45Stepper:
         self.nfev = 0
         self.last_rhs_state = None     # state of the last RHS evaluation (the reference's ghosts belong to it)
         self._rhs = rhs
+        self._on_step = on_step        # on_step(y, t): called at t = 0 and after every accepted step (scipy's event sites)
         self._reduce = reduce if reduce is not None else (lambda v: v)
         self._n_global = int(n_global) if n_global is not None else eng.n
 
@@ -128,6 +129,8 @@ class RK45Stepper:
             raise ValueError("t_diff must be positive")
         y = y.clone()
         y_new = torch.empty_like(y)
+        if self._on_step is not None:
+            self._on_step(y, 0.0)
         self.f(y, self.K[0])
         h_abs = self.select_initial_step(y, t_bound)
         t = 0.0
@@ -181,6 +184,8 @@ class RK45Stepper:
                 _lib.count()
             t = t_new
             y, y_new = y_new, y
+            if self._on_step is not None:
+                self._on_step(y, t)
             self.last_rhs_state = y
             self.K[0].copy_(self.K[6])      # FSAL: f_new becomes f of the next step
         return result

@@ -40,29 +40,23 @@ class Refiner:
         self._npmax = npmax
 
     # ------------------------------------------------------------------------------------------------
-    def refine_arrays(self, x, U, want_flags=True):
-        """Device refinement of one mesh given as host arrays x[n], U[n, nv] -> (x_new, U_new, flags).
-
-        flags = dict(loc, keep, gridpt, comp) as NumPy arrays (for the report), or None."""
+    def _refine_device(self, xd, Ud, want_flags=True):
+        """Device refinement of one mesh: xd [n], Ud [n, nv] CUDA tensors -> (x_new, U_new, flags) on the device.
+        The only host round trip is the new mesh size (the allocation needs it); flags = dict(loc, keep, gridpt, comp):
+        device byte/int arrays for the report, or None."""
         import torch
-        if not torch.cuda.is_available():
-            raise SFXM("splitfxm_b200 needs a CUDA device (there is no CPU fallback)")
         lib = _lib.load()
-        x = np.ascontiguousarray(x, dtype=np.float64)
-        U = np.ascontiguousarray(U, dtype=np.float64)
-        n, nv = U.shape
+        n, nv = Ud.shape
         if n > self._npmax:
             raise SFXM("Exceeded maximum number of points")        # refine.py:124-125
-        dev = torch.device("cuda", torch.cuda.current_device())
-        xd = torch.from_numpy(x).to(dev)
-        Ud = torch.from_numpy(U).to(dev)
+        dev = xd.device
         work = torch.empty(lib.sfxm_refine_workspace_bytes(n), dtype=torch.uint8, device=dev)
         counts = torch.zeros(3, dtype=torch.int64, device=dev)
         st = _lib.stream_ptr()
         _lib.check(lib.sfxm_refine_mark(xd.data_ptr(), Ud.data_ptr(), n, nv, float(self._ratio), float(self._slope),
                                         float(self._curve), float(self._prune), float(self._min_range),
                                         float(self._min_grid), work.data_ptr(), counts.data_ptr(), st))
-        _lib.count(10)
+        _lib.count(_lib.AMR_MARK_LAUNCHES)
         n_new = int(counts[0])          # the one read-back the new allocation needs
         x_new = torch.empty(n_new, dtype=torch.float64, device=dev)
         U_new = torch.empty((n_new, nv), dtype=torch.float64, device=dev)
@@ -77,41 +71,118 @@ class Refiner:
             comp = torch.empty(_lib.MAX_NV, dtype=torch.int32, device=dev)
             _lib.check(lib.sfxm_refine_flags(work.data_ptr(), n, loc.data_ptr(), keep.data_ptr(), gridpt.data_ptr(),
                                              comp.data_ptr(), st))
-            flags = dict(loc=loc.cpu().numpy(), keep=keep.cpu().numpy(), gridpt=gridpt.cpu().numpy(),
-                         comp=comp.cpu().numpy())
+            flags = dict(loc=loc, keep=keep, gridpt=gridpt, comp=comp)
+        return x_new, U_new, flags
+
+    def refine_arrays(self, x, U, want_flags=True):
+        """Host arrays in, host arrays out (x[n], U[n, nv]) -> (x_new, U_new, flags as NumPy arrays or None)."""
+        import torch
+        if not torch.cuda.is_available():
+            raise SFXM("splitfxm_b200 needs a CUDA device (there is no CPU fallback)")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        xd = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
+        Ud = torch.from_numpy(np.ascontiguousarray(U, dtype=np.float64)).to(dev)
+        x_new, U_new, flags = self._refine_device(xd, Ud, want_flags)
+        if flags is not None:
+            flags = {k: v.cpu().numpy() for k, v in flags.items()}
         return x_new.cpu().numpy(), U_new.cpu().numpy(), flags
 
-    def refine(self, d):
-        """Refine the Domain's interior in place (refine.py:90-237, 239-282)."""
-        nbl, nbr = d.nb(btype.LEFT), d.nb(btype.RIGHT)
-        x_new, U_new, flags = self.refine_arrays(d.interior_x(), d.interior_U())
-        names = [d.component_name(i) for i in range(d.num_components())]
-        self.show_changes(flags, names)
-        n_old = d._x.shape[0]
-        d._x = np.concatenate([d._x[:nbl], x_new, d._x[n_old - nbr:]])
-        d._U = np.concatenate([d._U[:nbl], U_new, d._U[n_old - nbr:]])
-        d._nx = x_new.shape[0]
-        d._domain = None       # cell views are rebuilt on demand
+    @staticmethod
+    def _dicts_from_flags(flags, names):
+        """The reference's `loc`, `c`, `keep` dictionaries (refine.py:103-118) from the device flags; only the indices
+        of the marked cells cross to the host.  Keys are in ascending order (the reference's are in the order its loops
+        first touch them), `keep` lists the deletions only."""
+        import torch
+        n = flags["loc"].shape[0]
+        loc_idx = torch.nonzero(flags["loc"][:n - 1]).reshape(-1).cpu().tolist()
+        del_idx = torch.nonzero(flags["keep"] == 0).reshape(-1).cpu().tolist()
+        pt_idx = torch.nonzero(flags["gridpt"]).reshape(-1).cpu().tolist()
+        comp = flags["comp"].cpu().tolist()
+        loc = {int(i): 1 for i in loc_idx}
+        c = {names[i]: 1 for i in range(len(names)) if comp[i]}
+        c.update({f"point {int(j)}": 1 for j in pt_idx})
+        keep = {int(i): -1 for i in del_idx}
+        return loc, c, keep
 
-    def show_changes(self, flags, names):
-        """The reference's stdout report (refine.py:284-312); indices are listed in ascending order."""
+    def refine(self, d):
+        """Refine the Domain's interior in place (refine.py:90-237, 239-282).  Works on the Domain's device copy and
+        leaves the new mesh there: nothing but the new size and the indices for the report crosses PCIe."""
+        import torch
+        if not torch.cuda.is_available():
+            raise SFXM("splitfxm_b200 needs a CUDA device (there is no CPU fallback)")
+        nbl, nbr, nx = d.nb(btype.LEFT), d.nb(btype.RIGHT), d._nx
+        dx, dU = d._device()
+        x_new, U_new, flags = self._refine_device(dx[nbl:nbl + nx], dU[nbl:nbl + nx])
+        names = [d.component_name(i) for i in range(d.num_components())]
+        self.show_changes(*self._dicts_from_flags(flags, names))
+        n_old = dx.shape[0]
+        d._adopt_device(torch.cat([dx[:nbl], x_new, dx[n_old - nbr:]]), torch.cat([dU[:nbl], U_new, dU[n_old - nbr:]]),
+                        nx=x_new.shape[0], mesh_changed=True)
+
+    def perform_changes(self, d, loc, keep):
+        """Apply explicit changes (refine.py:239-282): a midpoint cell after every index in `loc`, every cell whose
+        `keep` entry is -1 deleted.  The reference deletes while enumerating the list (refine.py:273-275), so of two
+        ADJACENT marked cells it skips the second; reproduced (refine() never marks adjacent cells)."""
+        import torch
+        if not torch.cuda.is_available():
+            raise SFXM("splitfxm_b200 needs a CUDA device (there is no CPU fallback)")
+        lib = _lib.load()
+        nbl, nbr, nx = d.nb(btype.LEFT), d.nb(btype.RIGHT), d._nx
+        marked = np.zeros(nx, dtype=bool)
+        for i, v in keep.items():
+            if 0 <= i < nx and v == -1:
+                marked[i] = True
+        # offset of every marked cell inside its run of marked cells: even offsets are deleted, odd ones skipped
+        idx = np.arange(nx)
+        run_start = np.maximum.accumulate(np.where(marked & ~np.r_[False, marked[:-1]], idx, -1))
+        delete = marked & (((idx - run_start) & 1) == 0)
+        ins = np.zeros(nx, dtype=np.uint8)
+        for i in loc.keys():
+            if not 0 <= i < nx - 1:
+                raise IndexError("list index out of range")            # cells[i + 1] in the reference
+            ins[i] = 1
+        dx, dU = d._device()
+        dev = dx.device
+        xi, Ui = dx[nbl:nbl + nx], dU[nbl:nbl + nx]
+        nv = Ui.shape[1]
+        work = torch.empty(lib.sfxm_refine_workspace_bytes(nx), dtype=torch.uint8, device=dev)
+        counts = torch.zeros(3, dtype=torch.int64, device=dev)
+        loc_d = torch.from_numpy(ins).to(dev)
+        keep_d = torch.from_numpy((~delete).astype(np.uint8)).to(dev)
+        st = _lib.stream_ptr()
+        _lib.check(lib.sfxm_refine_set_flags(loc_d.data_ptr(), keep_d.data_ptr(), nx, work.data_ptr(), counts.data_ptr(), st))
+        _lib.count(4)
+        n_new = int(counts[0])
+        x_new = torch.empty(n_new, dtype=torch.float64, device=dev)
+        U_new = torch.empty((n_new, nv), dtype=torch.float64, device=dev)
+        _lib.check(lib.sfxm_refine_apply(xi.data_ptr(), Ui.data_ptr(), nx, nv, work.data_ptr(), x_new.data_ptr(),
+                                         U_new.data_ptr(), st))
+        _lib.count()
+        n_old = dx.shape[0]
+        d._adopt_device(torch.cat([dx[:nbl], x_new, dx[n_old - nbr:]]), torch.cat([dU[:nbl], U_new, dU[n_old - nbr:]]),
+                        nx=n_new, mesh_changed=True)
+
+    def show_changes(self, loc, c, keep):
+        """The reference's stdout report (refine.py:284-312), same signature: `loc` {index: 1}, `c` {name: 1},
+        `keep` {index: +-1}; printed in the dictionaries' own order."""
         print("#" * 78)
-        loc = np.nonzero(flags["loc"][:-1])[0]
-        if loc.size != 0:
+        if len(loc) != 0:
             print("Refining grid...")
             print("New points inserted after grid points ")
-            print(" ".join(str(int(i)) for i in loc), end=" ")
+            for i in loc.keys():
+                print(i, end=" ")
             print("    to resolve ", end="")
-            why = [names[i] for i in range(len(names)) if flags["comp"][i]]
-            why += [f"point {int(j)}" for j in np.nonzero(flags["gridpt"])[0]]
-            print(" ".join(why), end=" ")
+            for name in c.keys():
+                print(name, end=" ")
             print("")
         else:
             print("No new points needed")
-        deleted = np.nonzero(flags["keep"] == 0)[0]
-        if deleted.size != 0:
+        num_deleted = list(keep.values()).count(-1)
+        if num_deleted != 0:
             print("Deleted points at ")
-            print(" ".join(str(int(i)) for i in deleted), end=" ")
+            for i in keep.keys():
+                if keep[i] == -1:
+                    print(i, end=" ")
             print("")
         else:
             print("No new points deleted")

@@ -63,11 +63,12 @@ class Simulation:
         if stencil_sizes.get(self._s._scheme) != boundary_cells + 1:
             raise SFXM("Stencil size does not match boundary conditions")
         self._eng = None
-        self._eng_key = None
+        self._eng_key = self._eng_rev = self._bc_sig = None
 
     # -- device engine -----------------------------------------------------------------------------------
     def _engine(self):
-        """Engine for the Domain's current mesh (rebuilt when the mesh size changed, e.g. after AMR)."""
+        """Engine for the Domain's current mesh.  The Domain's device copy is the engine's input: nothing is uploaded
+        unless host code touched the Domain since the last call (domain.py: _device)."""
         d, m = self._d, self._s._model
         dev = getattr(m, "_device", None)
         if dev is None:
@@ -78,32 +79,48 @@ class Simulation:
             raise SFXM("Scheme family does not match the model's numerical method")
         if scheme not in _scheme_ids:
             raise SFXM("Unsupported scheme")
-        x_int = d.interior_x()
-        key = (x_int.shape[0], d.num_components(), d.nb(btype.LEFT), d.nb(btype.RIGHT), _scheme_ids[scheme], dev.model_id)
+        if not torch.cuda.is_available():
+            raise SFXM("splitfxm_b200 needs a CUDA device (there is no CPU fallback)")
+        nbl, nbr, nx = d.nb(btype.LEFT), d.nb(btype.RIGHT), d._nx
+        dx, _ = d._device()
+        key = (nx, d.num_components(), nbl, nbr, _scheme_ids[scheme], dev.model_id)
         if self._eng is None or self._eng_key != key:
-            self._eng = Engine(dev.model_id, _scheme_ids[scheme], d.num_components(), d.nb(btype.LEFT), d.nb(btype.RIGHT),
-                               x_int, d.xmin(), d.xmax(), dev.params, batch=1)
-            self._eng_key = key
+            self._eng = Engine(dev.model_id, _scheme_ids[scheme], d.num_components(), nbl, nbr, dx[nbl:nbl + nx],
+                               d.xmin(), d.xmax(), dev.params, batch=1)
+            self._eng_key, self._eng_rev, self._bc_sig = key, d._mesh_rev, None
         else:
-            self._eng.set_mesh(x_int)
+            if self._eng_rev != d._mesh_rev:
+                self._eng.set_mesh(dx[nbl:nbl + nx])
+                self._eng_rev, self._bc_sig = d._mesh_rev, None
             self._eng.set_params(dev.params)
-        self._eng.set_bcs(lambda P: describe_bcs(P, self._bcs, d))
+        # the BC descriptor is rebuilt when the bcs dict changed, and always when some variable has no BC (its ghost
+        # cells are whatever the Domain holds at the time of the call)
+        sig = repr(self._bcs) if len(self._bcs) == d.num_components() else None
+        if sig is None or sig != self._bc_sig:
+            self._eng.set_bcs(lambda P: describe_bcs(P, self._bcs, d))
+            self._bc_sig = sig
         return self._eng
 
+    def _state(self, eng, split, split_locs):
+        """The Domain's interior as the flat device vector [n, 1] (listify_interior, domain.py:276-312) - no host copy."""
+        d = self._d
+        nbl = d.nb(btype.LEFT)
+        _, dU = d._device()
+        return eng.block_to_flat(dU[nbl:nbl + d._nx], split, split_locs)
+
     def _store(self, eng, y, split, split_locs, ghost_state=None):
-        """Device state -> Domain: initialize_from_list + apply_BC (simulation.py:171-175).
+        """Device state -> Domain: initialize_from_list + apply_BC (simulation.py:171-175), on the device.
 
         ``ghost_state``: the state of the last right-hand-side evaluation.  The reference's evolve() ends with
         initialize_from_list (simulation.py:472), which rewrites the interior only, so the ghost cells it leaves
         behind are those of the last RHS call - reproduced here."""
+        d = self._d
         x_all, U_all = eng.fill_domain(y if ghost_state is None else ghost_state, split, split_locs)
-        self._d._x[:] = x_all.cpu().numpy()
-        self._d._U[:, :] = U_all.cpu().numpy().reshape(self._d._U.shape)
+        U_all = U_all.reshape(x_all.shape[0], eng.nv)
         if ghost_state is not None:
-            from .engine import flat_index_table
-            _, segs = eng.problem(split, split_locs)
-            idx = flat_index_table(eng.nx, eng.nv, segs)
-            self._d.interior_U()[:, :] = y.cpu().numpy().reshape(-1)[idx]
+            nbl = d.nb(btype.LEFT)
+            U_all[nbl:nbl + eng.nx] = eng.flat_to_block(y, split, split_locs)
+        d._adopt_device(x_all, U_all)      # ghost positions may move (bc.py:56-151); the interior mesh does not
 
     # -- list related methods (simulation.py:81-264) -----------------------------------------------------
     def get_shape_from_list(self, l):
@@ -111,6 +128,15 @@ class Simulation:
         if len(l) % nv != 0:
             raise SFXM("List length not aligned with interior size")
         return len(l) // nv, nv
+
+    @staticmethod
+    def _check_listify(nv, split, split_locs):
+        """The errors Domain.listify_interior raises (domain.py:276-312) - evolve / steady_state start with it."""
+        if split:
+            if not split_locs:
+                raise SFXM("Split locations must be specified when splitting is enabled")
+            if sorted(set(split_locs))[-1] > nv:
+                raise SFXM("Split locations exceed the number of columns in the interior values")
 
     def _check_split(self, nv, split, split_locs, msg_none, msg_range):
         if split:
@@ -183,11 +209,11 @@ class Simulation:
         """Advance the Domain by t_diff (simulation.py:396-472).  'Euler' and 'RK45' run on the device; like the
         reference, rtol/atol are accepted but scipy's defaults are what is used (they are never forwarded,
         simulation.py:468-469)."""
-        y0 = self._d.listify_interior(split, split_locs)
-        num_points, nv = self.get_shape_from_list(y0)
+        num_points, nv = self._d._nx, self._d.num_components()
+        self._check_listify(nv, split, split_locs)
         ext_bounds = self.extend_bounds(bounds, num_points, nv, split, split_locs)
         eng = self._engine()
-        y = eng.to_device(y0)
+        y = self._state(eng, split, split_locs)
         ghost_state = None
         if method == "Euler":
             on_step = None
@@ -198,11 +224,18 @@ class Simulation:
                     checker.report(yd, t)
             y, ghost_state, _ = euler(eng, y, t_diff, max_step, split, split_locs, on_step)
         elif method == "RK45":
-            stepper = RK45Stepper(eng, split, split_locs, 1e-3, 1e-6, max_step)
+            on_step = None
+            if bounds is not None:
+                # the reference hands one event per unknown to solve_ivp (simhelper.py:31-88); scipy evaluates them at the
+                # start and after every accepted step, and each evaluation prints the warnings - reproduced per step (the
+                # extra evaluations of scipy's event root-refinement are not)
+                checker = DeviceBounds(ext_bounds, eng.device)
+
+                def on_step(yd, t):
+                    checker.report(yd, t)
+            stepper = RK45Stepper(eng, split, split_locs, 1e-3, 1e-6, max_step, on_step=on_step)
             y = stepper.integrate(y, t_diff)
             ghost_state = stepper.last_rhs_state
-            if bounds is not None:
-                DeviceBounds(ext_bounds, eng.device).report(y, t_diff)
         else:
             # Any other scipy method (RK23, DOP853, LSODA, Radau, BDF ...): scipy.integrate.solve_ivp drives, exactly as
             # in the reference (simulation.py:466-469), with the right-hand side and - for the implicit methods - the
@@ -210,6 +243,7 @@ class Simulation:
             # linear algebra stay scipy's, as they are in the reference.
             from scipy.integrate import solve_ivp
             last = {}
+            y0 = y.cpu().numpy().reshape(-1)
 
             def f(_, yv):
                 yd = eng.to_device(np.asarray(yv, dtype=np.float64))
@@ -228,14 +262,14 @@ class Simulation:
 
     def steady_state(self, split=False, split_locs=None, sparse=True, dt0=0.0, dtmax=1.0, armijo=False, bounds=None):
         """Newton / Split-Newton to steady state (simulation.py:474-526); returns the iteration count."""
-        x0 = self._d.listify_interior(split, split_locs)
-        num_points, nv = self.get_shape_from_list(x0)
+        num_points, nv = self._d._nx, self._d.num_components()
+        self._check_listify(nv, split, split_locs)
         ext_bounds = self.extend_bounds(bounds, num_points, nv, split, split_locs)
         if split:
             self._check_split(nv, split, split_locs, "Split location must be specified in this case",
                               "Split locations must be between 0 and nv-1")
         eng = self._engine()
-        y = eng.to_device(x0)
+        y = self._state(eng, split, split_locs)
         drv = NewtonDriver(eng, split, split_locs, dt0, dtmax, armijo, ext_bounds)
         maxiter = self._ss.get("maxiter", math.inf) if isinstance(self._ss, dict) else math.inf
         it = drv.run(y, maxiter)

@@ -8,11 +8,26 @@ import pytest
 
 
 def _report(flags, names):
+    """flags as the device kernels produce them (here CPU tensors) -> the reference's loc / c / keep dictionaries ->
+    show_changes(loc, c, keep), the reference's signature (refine.py:284)."""
+    import torch
+    from splitfxm_b200.refine import Refiner
+    loc, c, keep = Refiner._dicts_from_flags({k: torch.from_numpy(v) for k, v in flags.items()}, names)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        Refiner().show_changes(loc, c, keep)
+    return buf.getvalue()
+
+
+def test_show_changes_takes_the_reference_dictionaries():
+    """refine.py:284-312 verbatim behaviour: dict order is print order, only keep == -1 is a deletion."""
     from splitfxm_b200.refine import Refiner
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
-        Refiner().show_changes(flags, names)
-    return buf.getvalue()
+        Refiner().show_changes({4: 1, 1: 1}, {"v": 1, "point 4": 1}, {0: 1, 3: -1, 2: 1, 7: -1})
+    bar = "#" * 78
+    assert buf.getvalue() == (f"{bar}\nRefining grid...\nNew points inserted after grid points \n4 1     to resolve v point 4 \n"
+                              f"Deleted points at \n3 7 \n{bar}\n")
 
 
 def test_report_lists_insertions_reasons_and_deletions():
