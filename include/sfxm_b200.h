@@ -193,6 +193,18 @@ int sfxm_sumsq(const double *v, int64_t lo, int64_t hi, int64_t batch, double *o
 int sfxm_update_norms(double *y, const double *s, const double *alpha, const int32_t *active, int32_t update, int64_t lo,
                       int64_t hi, int64_t batch, double *out2, double *work, void *stream);
 
+/* Per-member bookkeeping of the Newton / Split-Newton iteration (the loop the reference delegates to the third-party
+ * splitnewton, simulation.py:515-523; specification: oracle/newton.py).  All arrays are device arrays [batch].
+ * begin: run[m] = parent[m] (NULL = all) && crit[m] >= 1 && it[m] < maxiter; shift[m] = -1 / dt[m] (shift NULL: no
+ *        pseudo-transient term); *any_flag = 1 if any member runs (zeroed first).
+ * end:   for running members crit[m] = sqrt(ss[m]) / (abs_tol + rel_tol * sqrt(yy[m])), it[m] += 1, and, if dt != NULL,
+ *        dt[m] = min(dt[m] * sqrt(r_old_sq[m]) / sqrt(r_new_sq[m]), dtmax) (dtmax when the new residual is zero). */
+int sfxm_newton_begin(int64_t batch, const int32_t *parent, const double *crit, const int64_t *it, double maxiter,
+                      const double *dt, int32_t *run, double *shift, int32_t *any_flag, void *stream);
+int sfxm_newton_end(int64_t batch, const int32_t *run, const double *ss, const double *yy, double abs_tol, double rel_tol,
+                    double *crit, int64_t *it, double *dt, const double *r_old_sq, const double *r_new_sq, double dtmax,
+                    void *stream);
+
 /* y[q, m] += alpha[m] * s[q, m] for q in [lo, hi) and members with active[m] != 0. */
 int sfxm_axpy_masked(double *y, const double *s, const double *alpha, const int32_t *active, int64_t lo, int64_t hi,
                      int64_t batch, void *stream);

@@ -68,6 +68,8 @@ SIGNATURES = {
     "sfxm_sumsq_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "sfxm_sumsq": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "sfxm_update_norms": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "sfxm_newton_begin": (ctypes.c_int, [c_i64, c_vp, c_vp, c_vp, c_f64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_newton_end": (ctypes.c_int, [c_i64, c_vp, c_vp, c_vp, c_f64, c_f64, c_vp, c_vp, c_vp, c_vp, c_vp, c_f64, c_vp]),
     "sfxm_axpy_masked": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "sfxm_rk_lincomb": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_f64), c_i32, c_f64, c_vp, c_i64, c_vp]),
     "sfxm_rk_dense_end": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_f64), c_i32, c_f64, c_vp, c_i64, c_vp]),

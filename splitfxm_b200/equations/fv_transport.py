@@ -47,8 +47,9 @@ class FVTransportEquation:
         uv = stencil_values(lambda v: v, cell_sub, dev)
         nv = Fv.shape[1]
         out = torch.empty(nv, dtype=torch.float64, device=dev)
+        xs, Sv = stencil_x(cell_sub, dev), source_values(self.S, cell_sub, nv, dev)     # named: alive until the launch
         _lib.check(lib.sfxm_fv_cell_residual(_scheme_ids[scheme], nv, Fv.data_ptr(), Dv.data_ptr(), uv.data_ptr(),
-                                             stencil_x(cell_sub, dev).data_ptr(), source_values(self.S, cell_sub, nv, dev).data_ptr(),
-                                             sigma, _lib.ptr(eig), out.data_ptr(), _lib.stream_ptr()))
+                                             xs.data_ptr(), Sv.data_ptr(), sigma, _lib.ptr(eig), out.data_ptr(),
+                                             _lib.stream_ptr()))
         _lib.count()
         return out.cpu().numpy()

@@ -8,7 +8,11 @@ Newton step on the next segment out.
 
 Every ensemble member carries its own iteration count, criterion and pseudo time step; members that have
 converged are masked out of the solve/update kernels, so each member follows exactly the scalar algorithm.
-Per iteration the host reads back one flag ("any member still active").
+
+Per iteration the per-member bookkeeping is two small kernels (csrc/sfxm_newton_ctl.cu: ``_begin`` - who still runs,
+the pseudo-transient shift, one "any member active" flag for the host; ``_end`` - criterion, counts, time-step growth);
+on CPU tensors (the driver's control logic is tested on CPU over an oracle-backed engine) the same bookkeeping runs as
+tensor expressions.  The host reads back one flag per iteration.
 """
 import math
 
@@ -42,12 +46,16 @@ class NewtonDriver:
         self.rt = torch.empty((eng.n, B), dtype=torch.float64, device=dev) if (armijo or dt0 > 0) else None
         self.yt = torch.empty((eng.n, B), dtype=torch.float64, device=dev) if armijo else None
         self.status = torch.zeros(B, dtype=torch.int32, device=dev)
-        self.all_active = torch.ones(B, dtype=torch.bool, device=dev)
         # a slab-decomposed mesh (spike.SlabNewtonEngine) reduces the host-side decisions over the ranks
         fused_ok = getattr(eng, "fused_solve_supported", None)
         self.fused = bool(fused_ok(split, split_locs)) if (fused and fused_ok is not None) else False
         self._reduce_min = getattr(eng, "reduce_min", lambda t: t)
         self._reduce_any = getattr(eng, "reduce_any", lambda flag: flag)
+        # per-member bookkeeping on the device through the C ABI when the engine has one (CUDA), else tensor expressions
+        self._lib = getattr(eng, "lib", None) if dev.type == "cuda" else None
+        if self._lib is not None:
+            self._any = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._shift = torch.empty(B, dtype=torch.float64, device=dev) if dt0 > 0 else None
 
     def rows(self, k):
         o, s = self.segs[k]
@@ -57,21 +65,63 @@ class NewtonDriver:
         if self.lb is not None and self._reduce_any(bool(((y < self.lb) | (y > self.ub)).any())):
             raise ValueError("Initial guess is outside the bounds")
 
+    # -- per-member bookkeeping --------------------------------------------------------------------------
+    def _new_state(self, with_dt):
+        """(it, crit, dt, run) of one loop level, all [batch]."""
+        B, dev = self.eng.batch, self.eng.device
+        it = torch.zeros(B, dtype=torch.int64, device=dev)
+        crit = torch.full((B,), math.inf, dtype=torch.float64, device=dev)
+        dt = torch.full((B,), self.dt0, dtype=torch.float64, device=dev) if with_dt else None
+        run = torch.zeros(B, dtype=torch.int32, device=dev)
+        return it, crit, dt, run
+
+    def _begin(self, parent, it, crit, dt, run, maxiter):
+        """run <- parent & (crit >= 1) & (it < maxiter) (int32 mask, in place); -> (any member runs, shift or None)."""
+        use_shift = dt is not None and self.dt0 > 0
+        if self._lib is not None:
+            from . import _lib
+            shift = self._shift if use_shift else None
+            _lib.check(self._lib.sfxm_newton_begin(self.eng.batch, _lib.ptr(parent), _lib.ptr(crit), _lib.ptr(it),
+                                                   float(min(maxiter, 1e300)), _lib.ptr(dt) if use_shift else None, _lib.ptr(run),
+                                                   _lib.ptr(shift), _lib.ptr(self._any), _lib.stream_ptr()))
+            _lib.count()
+            return bool(int(self._any[0])), shift
+        r = (crit >= 1) & (it < maxiter)
+        if parent is not None:
+            r = r & (parent != 0)
+        run.copy_(r.to(torch.int32))
+        return bool(r.any()), ((-1.0 / dt) if use_shift else None)
+
+    def _end(self, run, ss, yy, it, crit, dt=None, r_old_sq=None, r_new_sq=None):
+        """crit, it (and the pseudo time step) of the members that ran, in place."""
+        if self._lib is not None:
+            from . import _lib
+            _lib.check(self._lib.sfxm_newton_end(self.eng.batch, _lib.ptr(run), _lib.ptr(ss), _lib.ptr(yy), ABS_TOL, REL_TOL,
+                                                 _lib.ptr(crit), _lib.ptr(it), _lib.ptr(dt), _lib.ptr(r_old_sq), _lib.ptr(r_new_sq),
+                                                 self.dtmax, _lib.stream_ptr()))
+            _lib.count()
+            return
+        on = run != 0
+        c = torch.sqrt(ss) / (ABS_TOL + REL_TOL * torch.sqrt(yy))
+        crit.copy_(torch.where(on, c, crit))
+        it.add_(on.to(torch.int64))
+        if dt is not None:
+            rn, rnorm = torch.sqrt(r_new_sq), torch.sqrt(r_old_sq)
+            grown = torch.where(rn > 0, torch.clamp(dt * rnorm / rn, max=self.dtmax), torch.full_like(dt, self.dtmax))
+            dt.copy_(torch.where(on, grown, dt))
+
     # -- Newton on ONE segment (all segments when unsplit) -------------------------------------------
     def newton_segment(self, y, k, maxiter, parent):
         eng = self.eng
         lo, hi = self.rows(k)
         B, dev = eng.batch, eng.device
-        it = torch.zeros(B, dtype=torch.int64, device=dev)
-        crit = torch.full((B,), math.inf, dtype=torch.float64, device=dev)
-        dt = torch.full((B,), self.dt0, dtype=torch.float64, device=dev)
+        ptc = self.dt0 > 0
+        it, crit, dt, run32 = self._new_state(ptc)
+        need_rnorm = self.armijo or ptc
         while True:
-            run = parent & (crit >= 1) & (it < maxiter)
-            if not bool(run.any()):
+            any_run, shift = self._begin(parent, it, crit, dt, run32, maxiter)
+            if not any_run:
                 break
-            run32 = run.to(torch.int32)
-            shift = (-1.0 / dt) if self.dt0 > 0 else None
-            need_rnorm = self.armijo or self.dt0 > 0
             if self.fused:
                 # ensembles: the sweeping thread evaluates each cell's block row itself (J never touches HBM)
                 eng.newton_solve_fused(y, self.s, self.split, self.split_locs, k, self.eps, shift=shift, active=run32,
@@ -81,9 +131,11 @@ class NewtonDriver:
                 J = eng.jacobian(y, self.split, self.split_locs, self.eps, r0=self.r, seg_lo=k, seg_hi=k + 1)
                 eng.solve(J, self.r, self.s, self.split, self.split_locs, k, k + 1, shift=shift, active=run32,
                           status=self.status)
-            rnorm = torch.sqrt(eng.sumsq(self.r, lo, hi)) if need_rnorm else None
+            r_old_sq = eng.sumsq(self.r, lo, hi) if need_rnorm else None
             scale = None
             if self.armijo:
+                run = run32 != 0
+                rnorm = torch.sqrt(r_old_sq)
                 alpha = torch.ones(B, dtype=torch.float64, device=dev)
                 done = ~run
                 for _ in range(ARMIJO_MAX_HALVINGS):
@@ -100,16 +152,14 @@ class NewtonDriver:
                 lam = self._bound_lambda(y, lo, hi, scale)
                 scale = lam if scale is None else scale * lam
             if scale is not None:
+                run = run32 != 0
                 self.s[lo:hi] = torch.where(run[None, :], self.s[lo:hi] * scale[None, :], self.s[lo:hi])
             ss, yy = eng.update_norms(y, self.s, run32, lo, hi)       # y += s and both norms of the criterion, one pass
-            if self.dt0 > 0:
+            r_new_sq = None
+            if ptc:
                 eng.residual(y, self.rt, self.split, self.split_locs)
-                rn = torch.sqrt(eng.sumsq(self.rt, lo, hi))
-                grown = torch.where(rn > 0, torch.clamp(dt * rnorm / rn, max=self.dtmax), torch.full_like(dt, self.dtmax))
-                dt = torch.where(run, grown, dt)
-            c = torch.sqrt(ss) / (ABS_TOL + REL_TOL * torch.sqrt(yy))
-            crit = torch.where(run, c, crit)
-            it = it + run.to(torch.int64)
+                r_new_sq = eng.sumsq(self.rt, lo, hi)
+            self._end(run32, ss, yy, it, crit, dt, r_old_sq if ptc else None, r_new_sq)
         return it
 
     def _bound_lambda(self, y, lo, hi, scale):
@@ -129,24 +179,20 @@ class NewtonDriver:
             return self.newton_segment(y, k0, maxiter, parent)
         eng = self.eng
         lo, _ = self.rows(k0)
-        B, dev = eng.batch, eng.device
-        it = torch.zeros(B, dtype=torch.int64, device=dev)
-        crit = torch.full((B,), math.inf, dtype=torch.float64, device=dev)
+        it, crit, _, run32 = self._new_state(False)
         while True:
-            run = parent & (crit >= 1) & (it < maxiter)
-            if not bool(run.any()):
+            any_run, _ = self._begin(parent, it, crit, None, run32, maxiter)
+            if not any_run:
                 break
-            self.split_newton(y, k0 + 1, maxiter, run)      # inner segments to convergence
-            self.newton_segment(y, k0, 1, run)              # one step on this segment
+            self.split_newton(y, k0 + 1, maxiter, run32)      # inner segments to convergence
+            self.newton_segment(y, k0, 1, run32)              # one step on this segment
             ss, yy = eng.update_norms(y, self.s, None, lo, eng.n, update=False)
-            c = torch.sqrt(ss) / (ABS_TOL + REL_TOL * torch.sqrt(yy))
-            crit = torch.where(run, c, crit)
-            it = it + run.to(torch.int64)
+            self._end(run32, ss, yy, it, crit)
         return it
 
     def run(self, y, maxiter=math.inf):
         """In place on y [n, batch]; returns per-member iteration counts (int64 [batch])."""
         self.check_initial(y)
         if len(self.segs) == 1:
-            return self.newton_segment(y, 0, maxiter, self.all_active)
-        return self.split_newton(y, 0, maxiter, self.all_active)
+            return self.newton_segment(y, 0, maxiter, None)
+        return self.split_newton(y, 0, maxiter, None)

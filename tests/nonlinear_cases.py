@@ -128,23 +128,24 @@ def oracle_case(name):
     return P, U0, c
 
 
-def oracle_solve(name, maxiter=200):
-    """The specification's run -> (x0 flat, xf flat, iterations, trace)."""
+def oracle_solve(name, maxiter=200, dense=False):
+    """The specification's run -> (x0 flat, xf flat, iterations, trace).  dense: LAPACK instead of SuperLU linear solves
+    (a different rounding of the same algorithm - used to show that a case is not rounding-sensitive)."""
     from oracle import core, newton as onewton
     P, U0, c = oracle_case(name)
     nx, nv = U0.shape
     split, locs = c["split"], c["locs"]
     x0 = core.to_flat(U0, split, locs)
     f = lambda u: P.residual(u, split, locs)
-    jac = lambda u: P.jacobian_matrix(u, split, locs)
+    jac = (lambda u: P.jacobian_matrix(u, split, locs).toarray()) if dense else (lambda u: P.jacobian_matrix(u, split, locs))
     kw = dict(c["kw"])
     if "bounds" in kw:
         kw["bounds"] = extend_bounds(kw["bounds"], nx, nv, split, locs)
     trace = []
     if split:
-        xf, _, it = onewton.split_newton(f, jac, x0, [nx * i for i in locs], maxiter=maxiter, sparse=True, trace=trace, **kw)
+        xf, _, it = onewton.split_newton(f, jac, x0, [nx * i for i in locs], maxiter=maxiter, sparse=not dense, trace=trace, **kw)
     else:
-        xf, _, it = onewton.newton(f, jac, x0, maxiter=maxiter, sparse=True, trace=trace, **kw)
+        xf, _, it = onewton.newton(f, jac, x0, maxiter=maxiter, sparse=not dense, trace=trace, **kw)
     return x0, xf, it, trace
 
 

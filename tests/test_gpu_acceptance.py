@@ -108,13 +108,13 @@ def test_simulation_api_smoke():
 
 
 def test_error_paths_on_the_device_path():
-    """Inputs the kernels cannot take raise SFXM (never a silent fallback): meshes smaller than twice the stencil,
+    """Inputs the kernels cannot take raise SFXM (never a silent fallback): meshes smaller than the stencil,
     UPWIND with a non-diagonal flux Jacobian, Newton on an odd periodic mesh with a 4-cell stencil, wrong lengths."""
     import splitfxm_b200 as sf
     from splitfxm_b200.models.advection_diffusion import AdvectionDiffusion
     from splitfxm_b200.models.euler1d import Euler1DConservative
     per = {"left": "periodic", "right": "periodic"}
-    d = sf.Domain.from_size(4, 1, 1, ["u"])
+    d = sf.Domain.from_size(2, 1, 1, ["u"])
     s = sf.Simulation(d, AdvectionDiffusion(0.2, 0.001, "FVM"), {"u": "sine"}, {"u": per}, sf.FVSchemes.LAX_FRIEDRICHS)
     with pytest.raises(sf.SFXM):
         s.get_residuals_from_list(d.listify_interior(False))

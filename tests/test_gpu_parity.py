@@ -12,6 +12,9 @@ from helpers import EVOLVE_CASES, RESIDUAL_CASES, load, oracle_problem, product_
 pytestmark = pytest.mark.gpu
 
 TOL_FP = 1e-10
+# fixtures whose Jacobian pattern may differ from the reference's by this many round-off entries per side (see
+# test_jacobian_matches_reference; measured on B200: profiles/r2_euler_pattern.json)
+EULER_PATTERN_NOISE = {"sod_prim_nx60_t0p02": 2}
 
 
 @pytest.mark.parametrize("name", RESIDUAL_CASES)
@@ -41,16 +44,29 @@ def test_jacobian_matches_reference(name):
         assert np.array_equal(rows, z["jac_row"]) and np.array_equal(cols, z["jac_col"])
         assert np.array_equal(vals, z["jac_val"])
     else:
-        # finite-difference noise: entries are differences of O(1) numbers divided by 1e-8, so a 1e-16
-        # relative change in the residual moves an entry by ~1e-8 absolute; compare on that scale and
-        # compare the pattern on entries that are not pure noise
+        # Values: entries are differences of O(100) residuals divided by 1e-8, so a last-bit difference in a residual
+        # (closed-form spectral radius here, LAPACK eigvals in the reference, flux.pyx:99) moves an entry by ~1e-6 absolute.
         dense_ref = np.zeros(J.shape)
         dense_ref[z["jac_row"], z["jac_col"]] = z["jac_val"]
         dense = np.zeros(J.shape)
         dense[rows, cols] = vals
-        assert np.max(np.abs(dense - dense_ref)) <= 1e-6 * np.max(np.abs(z["jac_val"]))
-        big = np.abs(dense_ref) > 1e-5 * np.max(np.abs(z["jac_val"]))
-        assert np.array_equal(dense[big] != 0, dense_ref[big] != 0)
+        scale = np.max(np.abs(z["jac_val"]))
+        assert np.max(np.abs(dense - dense_ref)) <= 1e-6 * scale
+        # Sparsity (north_star: bit-exact indexing).  The reference's lil_matrix drops exact zeros, so its pattern contains
+        # entries that are pure round-off (down to 2e-16) - and the CUDA path reproduces them: rows/cols are bit-equal on
+        # every conservative-Euler fixture and on the primitive-variable Sod state.  The one exception is recorded in
+        # EULER_PATTERN_NOISE: on the evolved primitive-variable state one entry that is round-off noise in the reference
+        # (6.8e-13) is an exact zero here and vice versa (1.4e-9) - their value depends on the last bit of the spectral
+        # radius.  Allowed there: at most that many entries, each below the finite-difference noise floor.
+        allowed = EULER_PATTERN_NOISE.get(name, 0)
+        if allowed == 0:
+            assert np.array_equal(rows, z["jac_row"]) and np.array_equal(cols, z["jac_col"])
+        else:
+            only_ref = (dense_ref != 0) & (dense == 0)
+            only_got = (dense_ref == 0) & (dense != 0)
+            assert only_ref.sum() <= allowed and only_got.sum() <= allowed
+            floor = 64 * np.finfo(np.float64).eps * np.max(np.abs(z["residual"])) / 1e-8
+            assert np.all(np.abs(dense_ref[only_ref]) < floor) and np.all(np.abs(dense[only_got]) < floor)
 
 
 @pytest.mark.parametrize("name", EVOLVE_CASES)
