@@ -12,7 +12,12 @@ converged are masked out of the solve/update kernels, so each member follows exa
 Per iteration the per-member bookkeeping is two small kernels (csrc/sfxm_newton_ctl.cu: ``_begin`` - who still runs,
 the pseudo-transient shift, one "any member active" flag for the host; ``_end`` - criterion, counts, time-step growth);
 on CPU tensors (the driver's control logic is tested on CPU over an oracle-backed engine) the same bookkeeping runs as
-tensor expressions.  The host reads back one flag per iteration.
+tensor expressions.
+
+The host never stalls the device on that flag: it is copied to pinned memory behind an event, the iteration's kernels -
+all masked by the per-member run flags, so an iteration nobody needs is a no-op - are launched right away, and only then
+does the host look at the flag (``_peek`` before, ``_wait`` after).  When the device is already idle the flag is known
+at once and nothing is launched speculatively.
 """
 import math
 
@@ -53,8 +58,12 @@ class NewtonDriver:
         self._reduce_any = getattr(eng, "reduce_any", lambda flag: flag)
         # per-member bookkeeping on the device through the C ABI when the engine has one (CUDA), else tensor expressions
         self._lib = getattr(eng, "lib", None) if dev.type == "cuda" else None
+        # on a slab-decomposed mesh every iteration contains collectives: all ranks must take the same decision, so the flag
+        # is always awaited there (whether an event has completed yet differs from rank to rank)
+        self._speculate = not hasattr(eng, "comm")
         if self._lib is not None:
             self._any = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._any_host = torch.zeros(1, dtype=torch.int32).pin_memory()
             self._shift = torch.empty(B, dtype=torch.float64, device=dev) if dt0 > 0 else None
 
     def rows(self, k):
@@ -76,7 +85,8 @@ class NewtonDriver:
         return it, crit, dt, run
 
     def _begin(self, parent, it, crit, dt, run, maxiter):
-        """run <- parent & (crit >= 1) & (it < maxiter) (int32 mask, in place); -> (any member runs, shift or None)."""
+        """run <- parent & (crit >= 1) & (it < maxiter) (int32 mask, in place); -> (ticket for _peek / _wait, shift or
+        None).  On the device the "any member runs" flag travels to pinned host memory behind an event."""
         use_shift = dt is not None and self.dt0 > 0
         if self._lib is not None:
             from . import _lib
@@ -85,12 +95,29 @@ class NewtonDriver:
                                                    float(min(maxiter, 1e300)), _lib.ptr(dt) if use_shift else None, _lib.ptr(run),
                                                    _lib.ptr(shift), _lib.ptr(self._any), _lib.stream_ptr()))
             _lib.count()
-            return bool(int(self._any[0])), shift
+            self._any_host.copy_(self._any, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            return ev, shift
         r = (crit >= 1) & (it < maxiter)
         if parent is not None:
             r = r & (parent != 0)
         run.copy_(r.to(torch.int32))
         return bool(r.any()), ((-1.0 / dt) if use_shift else None)
+
+    def _peek(self, ticket):
+        """True / False if it is already known whether any member runs, None while the flag is still in flight."""
+        if isinstance(ticket, bool):
+            return ticket
+        if not self._speculate:
+            return self._wait(ticket)
+        return bool(int(self._any_host[0])) if ticket.query() else None
+
+    def _wait(self, ticket):
+        if isinstance(ticket, bool):
+            return ticket
+        ticket.synchronize()
+        return bool(int(self._any_host[0]))
 
     def _end(self, run, ss, yy, it, crit, dt=None, r_old_sq=None, r_new_sq=None):
         """crit, it (and the pseudo time step) of the members that ran, in place."""
@@ -119,9 +146,11 @@ class NewtonDriver:
         it, crit, dt, run32 = self._new_state(ptc)
         need_rnorm = self.armijo or ptc
         while True:
-            any_run, shift = self._begin(parent, it, crit, dt, run32, maxiter)
-            if not any_run:
+            ticket, shift = self._begin(parent, it, crit, dt, run32, maxiter)
+            known = self._peek(ticket)
+            if known is False:
                 break
+            # everything below is masked by run32: launched before the flag is known, it is a no-op if nobody runs
             if self.fused:
                 # ensembles: the sweeping thread evaluates each cell's block row itself (J never touches HBM)
                 eng.newton_solve_fused(y, self.s, self.split, self.split_locs, k, self.eps, shift=shift, active=run32,
@@ -160,6 +189,10 @@ class NewtonDriver:
                 eng.residual(y, self.rt, self.split, self.split_locs)
                 r_new_sq = eng.sumsq(self.rt, lo, hi)
             self._end(run32, ss, yy, it, crit, dt, r_old_sq if ptc else None, r_new_sq)
+            if maxiter == 1:          # one step (the outer segments of Split-Newton): nobody can run a second time
+                break
+            if known is None and not self._wait(ticket):
+                break
         return it
 
     def _bound_lambda(self, y, lo, hi, scale):
@@ -181,13 +214,16 @@ class NewtonDriver:
         lo, _ = self.rows(k0)
         it, crit, _, run32 = self._new_state(False)
         while True:
-            any_run, _ = self._begin(parent, it, crit, None, run32, maxiter)
-            if not any_run:
+            ticket, _ = self._begin(parent, it, crit, None, run32, maxiter)
+            known = self._peek(ticket)
+            if known is False:
                 break
             self.split_newton(y, k0 + 1, maxiter, run32)      # inner segments to convergence
             self.newton_segment(y, k0, 1, run32)              # one step on this segment
             ss, yy = eng.update_norms(y, self.s, None, lo, eng.n, update=False)
             self._end(run32, ss, yy, it, crit)
+            if known is None and not self._wait(ticket):
+                break
         return it
 
     def run(self, y, maxiter=math.inf):

@@ -95,7 +95,8 @@ def test_slab_refine_long_deletion_run_crosses_slabs():
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
         x_ref, U_ref, flags = r.refine_arrays(x, U)
-        r.show_changes(flags, ["component 0", "component 1"])
+        import torch
+        r.show_changes(*r._dicts_from_flags({k: torch.from_numpy(v) for k, v in flags.items()}, ["component 0", "component 1"]))
     assert (flags["keep"] == 0).sum() > 40                 # a long run of deletions exists
     for G in (2, 5):
         out = io.StringIO()
