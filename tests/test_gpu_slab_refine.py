@@ -85,6 +85,7 @@ def test_slab_refine_sod_sequence():
 def test_slab_refine_long_deletion_run_crosses_slabs():
     """A flat field with pruning on: one deletion run spans every slab, so the odd/even rule depends on the run start
     carried across ranks; the report lists the same global indices as the single-GPU Refiner."""
+    import torch
     from splitfxm_b200.refine import Refiner
     n = 203
     x = np.linspace(0.0, 1.0, n)
@@ -95,7 +96,6 @@ def test_slab_refine_long_deletion_run_crosses_slabs():
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
         x_ref, U_ref, flags = r.refine_arrays(x, U)
-        import torch
         r.show_changes(*r._dicts_from_flags({k: torch.from_numpy(v) for k, v in flags.items()}, ["component 0", "component 1"]))
     assert (flags["keep"] == 0).sum() > 40                 # a long run of deletions exists
     for G in (2, 5):
