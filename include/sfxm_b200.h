@@ -146,6 +146,13 @@ int sfxm_newton_fused_supported(const sfxm_problem_t *prob);
 int sfxm_newton_solve_fused(const sfxm_problem_t *prob, const double *x_int, const double *params, int64_t param_stride,
                             const double *geom, const double *y, double eps, const double *shift, const int32_t *active,
                             int32_t seg, double *s, double *r0, double *work, int32_t *status, void *stream);
+/* The same solve with the Newton update folded into the back substitution: y += s for the active members (in place)
+ * and norms2[m] = sum s^2, norms2[batch + m] = sum y_new^2 over the segment (the two sums of the convergence
+ * criterion), accumulated by the one thread that owns member m - no separate update + reduction pass over (y, s). */
+int sfxm_newton_step_fused(const sfxm_problem_t *prob, const double *x_int, const double *params, int64_t param_stride,
+                           const double *geom, double *y, double eps, const double *shift, const int32_t *active,
+                           int32_t seg, double *s, double *r0, double *work, int32_t *status, double *norms2,
+                           void *stream);
 
 /* Same contract as sfxm_block_tridiag_solve, by block parallel cyclic reduction: one thread per (cell, member)
  * and ceil(log2 nx) streaming passes instead of one thread per member - the solver for a single large mesh or
@@ -197,13 +204,15 @@ int sfxm_update_norms(double *y, const double *s, const double *alpha, const int
  * splitnewton, simulation.py:515-523; specification: oracle/newton.py).  All arrays are device arrays [batch].
  * begin: run[m] = parent[m] (NULL = all) && crit[m] >= 1 && it[m] < maxiter; shift[m] = -1 / dt[m] (shift NULL: no
  *        pseudo-transient term); *any_flag = 1 if any member runs (zeroed first).
- * end:   for running members crit[m] = sqrt(ss[m]) / (abs_tol + rel_tol * sqrt(yy[m])), it[m] += 1, and, if dt != NULL,
+ * end:   for running members crit[m] = sqrt(SS) / (abs_tol + rel_tol * sqrt(YY)) with SS = sum_{q < nsum} ss[q*batch + m]
+ *        (YY likewise; nsum = 1: one segment's sums; an enclosing Split-Newton level sums the kept sums of its segments),
+ *        it[m] += 1, keep_ss[m] = SS / keep_yy[m] = YY if given, and, if dt != NULL,
  *        dt[m] = min(dt[m] * sqrt(r_old_sq[m]) / sqrt(r_new_sq[m]), dtmax) (dtmax when the new residual is zero). */
 int sfxm_newton_begin(int64_t batch, const int32_t *parent, const double *crit, const int64_t *it, double maxiter,
                       const double *dt, int32_t *run, double *shift, int32_t *any_flag, void *stream);
-int sfxm_newton_end(int64_t batch, const int32_t *run, const double *ss, const double *yy, double abs_tol, double rel_tol,
-                    double *crit, int64_t *it, double *dt, const double *r_old_sq, const double *r_new_sq, double dtmax,
-                    void *stream);
+int sfxm_newton_end(int64_t batch, const int32_t *run, const double *ss, const double *yy, int32_t nsum, double abs_tol,
+                    double rel_tol, double *crit, int64_t *it, double *dt, const double *r_old_sq, const double *r_new_sq,
+                    double dtmax, double *keep_ss, double *keep_yy, void *stream);
 
 /* y[q, m] += alpha[m] * s[q, m] for q in [lo, hi) and members with active[m] != 0. */
 int sfxm_axpy_masked(double *y, const double *s, const double *alpha, const int32_t *active, int64_t lo, int64_t hi,
@@ -242,6 +251,16 @@ int sfxm_refine_flags(const void *work, int64_t n, uint8_t *loc_out, uint8_t *ke
                       int32_t *comp_out, void *stream);
 int sfxm_refine_apply(const double *x, const double *U, int64_t n, int32_t nv, const void *work, double *x_out,
                       double *U_out, void *stream);
+/* The whole refinement pass of ONE mesh in three launches (stats + zero-fill, mark, single-pass scan + apply with
+ * decoupled look-back): x_out / U_out need capacity 2n - 1 cells; counts_dev[0] = new size, [1] = inserted,
+ * [2] = deleted.  work: sfxm_refine_fused_workspace_bytes(n).  sfxm_refine_fused_flags copies the decision flags out
+ * (as sfxm_refine_flags) for the reference's report (refine.py:284-312). */
+int64_t sfxm_refine_fused_workspace_bytes(int64_t n);
+int sfxm_refine_fused(const double *x, const double *U, int64_t n, int32_t nv, double ratio, double slope, double curve,
+                      double prune, double min_range, double min_grid, void *work, double *x_out, double *U_out,
+                      int64_t *counts_dev, void *stream);
+int sfxm_refine_fused_flags(const void *work, int64_t n, uint8_t *loc_out, uint8_t *keep_out, uint8_t *gridpt_out,
+                            int32_t *comp_out, void *stream);
 /* Explicit flags instead of sfxm_refine_mark - Refiner.perform_changes(d, loc, keep), refine.py:239-282:
  * keep_in[t] = 0 deletes cell t, loc_in[t] = 1 inserts the midpoint after cell t (device byte arrays [n]); fills the
  * workspace (scans, counts_dev as for sfxm_refine_mark) so that sfxm_refine_apply builds the new mesh. */

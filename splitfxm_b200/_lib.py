@@ -57,6 +57,8 @@ SIGNATURES = {
     "sfxm_newton_fused_supported": (ctypes.c_int, [_PP]),
     "sfxm_newton_solve_fused": (ctypes.c_int, [_PP, c_vp, c_vp, c_i64, c_vp, c_vp, c_f64, c_vp, c_vp, c_i32, c_vp, c_vp,
                                                c_vp, c_vp, c_vp]),
+    "sfxm_newton_step_fused": (ctypes.c_int, [_PP, c_vp, c_vp, c_i64, c_vp, c_vp, c_f64, c_vp, c_vp, c_i32, c_vp, c_vp,
+                                              c_vp, c_vp, c_vp, c_vp]),
     "sfxm_pcr_workspace_bytes": (c_i64, [_PP]),
     "sfxm_block_tridiag_solve_pcr": (ctypes.c_int, [_PP, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_band4_workspace_bytes": (c_i64, [_PP]),
@@ -69,7 +71,8 @@ SIGNATURES = {
     "sfxm_sumsq": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "sfxm_update_norms": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "sfxm_newton_begin": (ctypes.c_int, [c_i64, c_vp, c_vp, c_vp, c_f64, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "sfxm_newton_end": (ctypes.c_int, [c_i64, c_vp, c_vp, c_vp, c_f64, c_f64, c_vp, c_vp, c_vp, c_vp, c_vp, c_f64, c_vp]),
+    "sfxm_newton_end": (ctypes.c_int, [c_i64, c_vp, c_vp, c_vp, c_i32, c_f64, c_f64, c_vp, c_vp, c_vp, c_vp, c_vp, c_f64,
+                                       c_vp, c_vp, c_vp]),
     "sfxm_axpy_masked": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "sfxm_rk_lincomb": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_f64), c_i32, c_f64, c_vp, c_i64, c_vp]),
     "sfxm_rk_dense_end": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_f64), c_i32, c_f64, c_vp, c_i64, c_vp]),
@@ -81,6 +84,10 @@ SIGNATURES = {
     "sfxm_refine_mark": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_f64, c_f64, c_f64, c_f64, c_f64, c_f64, c_vp, c_vp, c_vp]),
     "sfxm_refine_flags": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_refine_apply": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_refine_fused_workspace_bytes": (c_i64, [c_i64]),
+    "sfxm_refine_fused": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_f64, c_f64, c_f64, c_f64, c_f64, c_f64, c_vp, c_vp, c_vp,
+                                         c_vp, c_vp]),
+    "sfxm_refine_fused_flags": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_refine_set_flags": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "sfxm_refine_window_stats": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "sfxm_refine_window_mark": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, c_i64, c_i64, c_f64, c_f64, c_f64,
@@ -137,6 +144,7 @@ def stream_ptr():
 
 
 AMR_MARK_LAUNCHES = 10   # kernels sfxm_refine_mark issues (csrc/sfxm_amr.cu)
+AMR_FUSED_LAUNCHES = 3   # kernels of sfxm_refine_fused
 LAUNCHES = [0]   # number of kernel launches issued through the C ABI (bench.py reports it)
 
 

@@ -361,6 +361,297 @@ __global__ void amr_set_flags_kernel(const uint8_t *__restrict__ loc_in, const u
   ins_cnt[t] = (l && t + 1 < n) ? 1 : 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// One mesh on one GPU in THREE launches (round 2; the window phases above stay for slab-decomposed meshes):
+//   1. amr_stats_zero_kernel  : per-block min/max partials, the last block to finish folds them (ticket counter);
+//                               the same grid zero-fills the flag bytes and the tile descriptors of launch 3
+//   2. amr_mark_kernel        : unchanged
+//   3. amr_scan_apply_kernel  : ONE pass over the flags with two chained decoupled look-backs per tile - the max-scan
+//                               of deletion-run starts (refine.py:231-233), then, with the final keep flags it yields,
+//                               the exclusive counts of kept and inserted cells - and the new mesh is written straight
+//                               from the tile (capacity 2n - 1; the new size comes back in counts[0]).
+// Replaces 10 launches incl. three cub::DeviceScan passes over 8-byte arrays (profile r1: 0.178 ms at nx = 1e6).
+// ------------------------------------------------------------------------------------------------------------------
+static constexpr int kScanThreads = 256, kScanItems = 4, kScanTile = kScanThreads * kScanItems;
+
+struct TileDesc {                 // status in the two top bits: 0 = not ready, 1 = tile aggregate, 2 = inclusive prefix
+  unsigned long long run;         // low 62 bits: 1 + latest deletion-run start (0 = none)
+  unsigned long long cnt;         // low 62 bits: kept << 31 | inserted
+};
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+amr_stats_zero_kernel(const double *__restrict__ z, const double *__restrict__ U, const Window wd, double *__restrict__ part,
+                      Stats *__restrict__ out, unsigned int *__restrict__ ticket, uint4 *__restrict__ zero_lo, int64_t zero_n16) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < zero_n16; q += (int64_t)gridDim.x * blockDim.x)
+    zero_lo[q] = make_uint4(0u, 0u, 0u, 0u);
+  double lo_v[NV], hi_v[NV], lo_s[NV], hi_s[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { lo_v[i] = lo_s[i] = INFINITY; hi_v[i] = hi_s[i] = -INFINITY; }
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < wd.ne; j += (int64_t)gridDim.x * blockDim.x) {
+    const bool has_s = j + 1 < wd.ne;
+    const double dz = has_s ? __ldg(z + j + 1) - __ldg(z + j) : 1.0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const double v = __ldg(U + j * NV + i);
+      lo_v[i] = fmin(lo_v[i], v);
+      hi_v[i] = fmax(hi_v[i], v);
+      if (has_s) {
+        const double sl = (__ldg(U + (j + 1) * NV + i) - v) / dz;
+        lo_s[i] = fmin(lo_s[i], sl);
+        hi_s[i] = fmax(hi_s[i], sl);
+      }
+    }
+  }
+  __shared__ double sh[8][4 * NV];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const double a = warp_min(lo_v[i]), b = warp_max(hi_v[i]), c = warp_min(lo_s[i]), d = warp_max(hi_s[i]);
+    if (lane == 0) { sh[w][4 * i] = a; sh[w][4 * i + 1] = b; sh[w][4 * i + 2] = c; sh[w][4 * i + 3] = d; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 4 * NV) {
+    const bool is_min = (threadIdx.x & 1) == 0;
+    double acc = sh[0][threadIdx.x];
+    for (int k = 1; k < 8; ++k) acc = is_min ? fmin(acc, sh[k][threadIdx.x]) : fmax(acc, sh[k][threadIdx.x]);
+    part[(int64_t)blockIdx.x * 4 * NV + threadIdx.x] = acc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x < 4 * NV) {            // min / max are exact: the fold order does not matter
+    const int t = threadIdx.x;
+    const bool is_min = (t & 1) == 0;
+    const volatile double *vp = part;
+    double acc = vp[t];
+    for (unsigned k = 1; k < gridDim.x; ++k) acc = is_min ? fmin(acc, vp[(int64_t)k * 4 * NV + t]) : fmax(acc, vp[(int64_t)k * 4 * NV + t]);
+    const int i = t >> 2, f = t & 3;
+    if (f == 0) out->vmin[i] = acc;
+    else if (f == 1) out->vmax[i] = acc;
+    else if (f == 2) out->smin[i] = acc;
+    else out->smax[i] = acc;
+  }
+}
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+  return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+
+// Exclusive prefix of tile `tile` from the descriptors of the tiles before it (warp 0 of the block; standard decoupled
+// look-back, 32 predecessors per step).  MAXOP: combine with max (run starts), else with + (packed counts).
+template <bool MAXOP>
+__device__ __forceinline__ unsigned long long tile_lookback(const unsigned long long *desc, int stride_u64, int tile) {
+  constexpr unsigned long long kMask = (1ull << 62) - 1;
+  const int lane = threadIdx.x & 31;
+  unsigned long long acc = 0;
+  for (int base = tile - 1; base >= 0; base -= 32) {
+    const int p = base - lane;
+    unsigned long long v = 2ull << 62;                      // tiles before the first one: inclusive prefix = identity
+    if (p >= 0) {
+      do { v = ld_volatile_u64(desc + (int64_t)p * stride_u64); } while ((v >> 62) == 0ull);
+    }
+    const unsigned incl = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
+    const int stop = incl ? (__ffs(incl) - 1) : 31;         // nearest predecessor (lowest lane) with an inclusive prefix
+    unsigned long long val = lane <= stop ? (v & kMask) : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, val, o);
+      val = MAXOP ? (val > other ? val : other) : (val + other);
+    }
+    acc = MAXOP ? (acc > val ? acc : val) : (acc + val);
+    if (incl) break;
+  }
+  return acc;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kScanThreads)
+amr_scan_apply_kernel(const double *__restrict__ z, const double *__restrict__ U, int64_t n,
+                      const uint8_t *__restrict__ keep1, const uint8_t *__restrict__ visited, const uint8_t *__restrict__ loc,
+                      uint8_t *__restrict__ keepf, TileDesc *__restrict__ desc, unsigned int *__restrict__ tile_counter,
+                      double *__restrict__ z_out, double *__restrict__ U_out, int64_t *__restrict__ counts) {
+  constexpr unsigned long long kMask = (1ull << 62) - 1;
+  __shared__ int s_tile;
+  __shared__ unsigned long long s_warp[kScanThreads / 32];
+  __shared__ unsigned long long s_prefix;
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd(tile_counter, 1u);     // tiles start in index order: look-back cannot deadlock
+  __syncthreads();
+  const int tile = s_tile;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t t0 = (int64_t)tile * kScanTile + threadIdx.x * kScanItems;
+  bool del0[kScanItems], lc[kScanItems];
+  bool prev = t0 > 0 && t0 - 1 < n && visited[t0 - 1] && !keep1[t0 - 1];
+  long long run[kScanItems];                              // 1 + latest run start <= t inside the thread's items (0 = none)
+  long long running = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const int64_t t = t0 + k;
+    const bool in = t < n;
+    del0[k] = in && visited[t] && !keep1[t];
+    lc[k] = in && loc[t] && t + 1 < n;
+    if (del0[k] && !prev) running = t + 1;
+    run[k] = running;
+    prev = del0[k];
+  }
+  // ---- scan 1: inclusive max of the run starts -----------------------------------------------------------------
+  unsigned long long incl = (unsigned long long)running;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long other = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o && other > incl) incl = other;
+  }
+  if (lane == 31) s_warp[w] = incl;
+  __syncthreads();
+  unsigned long long before = 0;                          // max over the threads before this one, inside the tile
+  {
+    const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane > 0) before = up;
+    for (int q = 0; q < w; ++q) before = s_warp[q] > before ? s_warp[q] : before;
+  }
+  unsigned long long agg = 0;
+  for (int q = 0; q < kScanThreads / 32; ++q) agg = s_warp[q] > agg ? s_warp[q] : agg;
+  if (threadIdx.x == 0) {
+    *reinterpret_cast<volatile unsigned long long *>(&desc[tile].run) = (tile == 0 ? (2ull << 62) : (1ull << 62)) | agg;
+  }
+  if (w == 0) {
+    unsigned long long excl = 0;
+    if (tile > 0) {
+      excl = tile_lookback<true>(&desc[0].run, (int)(sizeof(TileDesc) / 8), tile);
+      if (lane == 0) {
+        const unsigned long long inc = excl > agg ? excl : agg;
+        __threadfence();
+        *reinterpret_cast<volatile unsigned long long *>(&desc[tile].run) = (2ull << 62) | inc;
+      }
+    }
+    if (lane == 0) s_prefix = excl;
+  }
+  __syncthreads();
+  const unsigned long long base_run = s_prefix > before ? s_prefix : before;
+  // final keep flags (refine.py:231-233: inside a run of deletions every odd offset is kept) and the counts
+  bool kp[kScanItems];
+  unsigned long long mine = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const int64_t t = t0 + k;
+    const unsigned long long rs1 = (unsigned long long)run[k] > base_run ? (unsigned long long)run[k] : base_run;   // 1 + run start
+    const bool del = del0[k] && (((t - ((int64_t)rs1 - 1)) & 1) == 0);
+    kp[k] = (t < n) && !del;
+    mine += (kp[k] ? (1ull << 31) : 0ull) + (lc[k] ? 1ull : 0ull);
+  }
+  __syncthreads();                                        // s_warp / s_prefix are reused
+  // ---- scan 2: exclusive sums of (kept, inserted) ---------------------------------------------------------------
+  unsigned long long isum = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long other = __shfl_up_sync(0xffffffffu, isum, o);
+    if (lane >= o) isum += other;
+  }
+  if (lane == 31) s_warp[w] = isum;
+  __syncthreads();
+  unsigned long long tbefore = isum - mine;
+  for (int q = 0; q < w; ++q) tbefore += s_warp[q];
+  unsigned long long tagg = 0;
+  for (int q = 0; q < kScanThreads / 32; ++q) tagg += s_warp[q];
+  if (threadIdx.x == 0) {
+    *reinterpret_cast<volatile unsigned long long *>(&desc[tile].cnt) = (tile == 0 ? (2ull << 62) : (1ull << 62)) | tagg;
+  }
+  if (w == 0) {
+    unsigned long long excl = 0;
+    if (tile > 0) {
+      excl = tile_lookback<false>(&desc[0].cnt, (int)(sizeof(TileDesc) / 8), tile);
+      if (lane == 0) {
+        __threadfence();
+        *reinterpret_cast<volatile unsigned long long *>(&desc[tile].cnt) = (2ull << 62) | ((excl + tagg) & kMask);
+      }
+    }
+    if (lane == 0) s_prefix = excl;
+  }
+  __syncthreads();
+  unsigned long long pos = s_prefix + tbefore;             // kept << 31 | inserted, before the thread's first item
+  // ---- write the new mesh --------------------------------------------------------------------------------------
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const int64_t t = t0 + k;
+    if (t >= n) break;
+    keepf[t] = kp[k] ? 1 : 0;
+    const int64_t kb = (int64_t)(pos >> 31), ib = (int64_t)(pos & ((1ull << 31) - 1));
+    if (kp[k]) {
+      const int64_t o = kb + ib;
+      z_out[o] = __ldg(z + t);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) U_out[o * NV + i] = __ldg(U + t * NV + i);
+    }
+    if (lc[k]) {
+      const int64_t o = kb + (kp[k] ? 1 : 0) + ib;
+      z_out[o] = 0.5 * (__ldg(z + t + 1) + __ldg(z + t));                                 // refine.py:268
+#pragma unroll
+      for (int i = 0; i < NV; ++i) U_out[o * NV + i] = 0.5 * (__ldg(U + (t + 1) * NV + i) + __ldg(U + t * NV + i));   // :269
+    }
+    pos += (kp[k] ? (1ull << 31) : 0ull) + (lc[k] ? 1ull : 0ull);
+  }
+  if (t0 <= n - 1 && n - 1 < t0 + kScanItems) {            // the thread that owns the last cell reports the totals
+    const int64_t kept = (int64_t)(pos >> 31), ins = (int64_t)(pos & ((1ull << 31) - 1));
+    counts[0] = kept + ins;
+    counts[1] = ins;
+    counts[2] = n - kept;
+  }
+}
+
+struct FusedLayout {
+  int64_t off_part, off_stats, off_stats_ticket, off_zero, off_keep1, off_visited, off_loc, off_gridpt, off_comp, off_ticket, off_desc, zero_bytes,
+      off_keepf, total;
+};
+
+static FusedLayout fused_layout(int64_t n) {
+  FusedLayout w{};
+  int64_t o = 0;
+  auto take = [&](int64_t bytes) { int64_t r = o; o += align256(bytes); return r; };
+  w.off_part = take(1024 * 4 * SFXM_MAX_NV * 8);
+  w.off_stats = take(sizeof(Stats));
+  w.off_stats_ticket = take(16);                           // last-block ticket of launch 1 (zeroed by a 4-byte memset)
+  w.off_zero = o;                                          // everything from here to off_keepf is zero-filled by launch 1
+  w.off_keep1 = take(n);
+  w.off_visited = take(n);
+  w.off_loc = take(n);
+  w.off_gridpt = take(n);
+  w.off_comp = take(SFXM_MAX_NV * 4);
+  w.off_ticket = take(16);
+  w.off_desc = take(((n + kScanTile - 1) / kScanTile) * (int64_t)sizeof(TileDesc));
+  w.zero_bytes = o - w.off_zero;
+  w.off_keepf = take(n);
+  w.total = o;
+  return w;
+}
+
+template <int NV>
+static int amr_fused_t(const double *z, const double *U, int64_t n, const Criteria &cr, char *work, double *x_out, double *U_out,
+                       int64_t *counts_dev, cudaStream_t st) {
+  const FusedLayout w = fused_layout(n);
+  const Window wd{n, 0, n, 0, n};
+  const int64_t blocks_all = (n + 255) / 256;
+  const int sblocks = (int)(blocks_all < 592 ? blocks_all : 592);                 // 4 x 148 SMs
+  unsigned int *stats_ticket = (unsigned int *)(work + w.off_stats_ticket);
+  unsigned int *tile_counter = (unsigned int *)(work + w.off_ticket);            // inside the region launch 1 zero-fills
+  cudaMemsetAsync(stats_ticket, 0, sizeof(unsigned int), st);
+  amr_stats_zero_kernel<NV><<<sblocks, 256, 0, st>>>(z, U, wd, (double *)(work + w.off_part), (Stats *)(work + w.off_stats),
+                                                     stats_ticket, (uint4 *)(work + w.off_zero), w.zero_bytes / 16);
+  amr_mark_kernel<NV><<<(unsigned)blocks_all, 256, 0, st>>>(z, U, wd, cr, (const Stats *)(work + w.off_stats),
+                                                            (uint8_t *)(work + w.off_keep1), (uint8_t *)(work + w.off_visited),
+                                                            (uint8_t *)(work + w.off_loc), (int32_t *)(work + w.off_comp),
+                                                            (uint8_t *)(work + w.off_gridpt));
+  const unsigned tiles = (unsigned)((n + kScanTile - 1) / kScanTile);
+  amr_scan_apply_kernel<NV><<<tiles, kScanThreads, 0, st>>>(z, U, n, (const uint8_t *)(work + w.off_keep1),
+                                                            (const uint8_t *)(work + w.off_visited), (const uint8_t *)(work + w.off_loc),
+                                                            (uint8_t *)(work + w.off_keepf), (TileDesc *)(work + w.off_desc),
+                                                            tile_counter, x_out, U_out, counts_dev);
+  return check_launch("sfxm_refine_fused");
+}
+
 #define SFXM_NV_SWITCH(nv, CALL)                                   \
   switch (nv) {                                                    \
     case 1: { constexpr int NVV = 1; e = CALL; } break;            \
@@ -393,6 +684,33 @@ extern "C" int sfxm_refine_mark(const double *x, const double *U, int64_t n, int
   SFXM_NV_SWITCH(nv, (amr_mark_t<NVV>(x, U, wd, cr, stats, wk, nullptr, st)));
   if (e) return e;
   return amr_finalize_t(wd, -1, wk, counts_dev, st);
+}
+
+extern "C" int64_t sfxm_refine_fused_workspace_bytes(int64_t n) { return n > 0 ? fused_layout(n).total : 0; }
+
+extern "C" int sfxm_refine_fused(const double *x, const double *U, int64_t n, int32_t nv, double ratio, double slope,
+                                 double curve, double prune, double min_range, double min_grid, void *work, double *x_out,
+                                 double *U_out, int64_t *counts_dev, void *stream) {
+  if (!x || !U || !work || !x_out || !U_out || !counts_dev) return set_error("sfxm_refine_fused: null argument");
+  if (n < 3) return set_error("sfxm_refine_fused: need at least 3 interior cells");
+  if (n > 1073741823LL) return set_error("sfxm_refine_fused: mesh too large for the packed counts");
+  const Criteria cr{ratio, slope, curve, prune, min_range, min_grid};
+  int e = 0;
+  SFXM_NV_SWITCH(nv, (amr_fused_t<NVV>(x, U, n, cr, (char *)work, x_out, U_out, counts_dev, (cudaStream_t)stream)));
+  return e;
+}
+
+extern "C" int sfxm_refine_fused_flags(const void *work, int64_t n, uint8_t *loc_out, uint8_t *keep_out, uint8_t *gridpt_out,
+                                       int32_t *comp_out, void *stream) {
+  if (!work || n < 1) return set_error("sfxm_refine_fused_flags: bad argument");
+  const FusedLayout w = fused_layout(n);
+  const char *wk = (const char *)work;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (loc_out) cudaMemcpyAsync(loc_out, wk + w.off_loc, n, cudaMemcpyDeviceToDevice, st);
+  if (keep_out) cudaMemcpyAsync(keep_out, wk + w.off_keepf, n, cudaMemcpyDeviceToDevice, st);
+  if (gridpt_out) cudaMemcpyAsync(gridpt_out, wk + w.off_gridpt, n, cudaMemcpyDeviceToDevice, st);
+  if (comp_out) cudaMemcpyAsync(comp_out, wk + w.off_comp, SFXM_MAX_NV * 4, cudaMemcpyDeviceToDevice, st);
+  return check_launch("sfxm_refine_fused_flags");
 }
 
 extern "C" int sfxm_refine_set_flags(const uint8_t *loc_in, const uint8_t *keep_in, int64_t n, void *work,

@@ -152,16 +152,16 @@ extern "C" int sfxm_newton_fused_supported(const sfxm_problem_t *prob) {
   return 0;
 }
 
-extern "C" int sfxm_newton_solve_fused(const sfxm_problem_t *prob, const double *x_int, const double *params,
-                                       int64_t param_stride, const double *geom, const double *y, double eps,
-                                       const double *shift, const int32_t *active, int32_t seg, double *s, double *r0,
-                                       double *work, int32_t *status, void *stream) {
+static int newton_fused_common(const sfxm_problem_t *prob, const double *x_int, const double *params, int64_t param_stride,
+                               const double *geom, const double *y, double eps, const double *shift, const int32_t *active,
+                               int32_t seg, double *s, double *r0, double *work, int32_t *status, double *y_upd,
+                               double *norms, void *stream) {
   if (!prob || !x_int || !params || !y || !s || !work) return set_error("sfxm_newton_solve_fused: null argument");
   if (!(eps > 0.0)) return set_error("sfxm_newton_solve_fused: epsilon must be positive");
   if (int e = validate(*prob)) return e;
   if (!sfxm_newton_fused_supported(prob)) return set_error("sfxm_newton_solve_fused: no fused kernel for this model / scheme");
   FusedLaunch L{prob, FusedArgs{x_int, params, param_stride, y, eps, geom, 0u, r0}, seg, shift, active, s, work, status,
-                (cudaStream_t)stream};
+                (cudaStream_t)stream, StepUpd{y_upd, norms}};
   int e = -2;
   switch (prob->model) {
     case SFXM_MODEL_AD: e = fused_ad3(L); break;
@@ -170,4 +170,21 @@ extern "C" int sfxm_newton_solve_fused(const sfxm_problem_t *prob, const double 
   }
   if (e == -2) return set_error("sfxm_newton_solve_fused: no fused kernel for this model / scheme");
   return e;
+}
+
+extern "C" int sfxm_newton_solve_fused(const sfxm_problem_t *prob, const double *x_int, const double *params,
+                                       int64_t param_stride, const double *geom, const double *y, double eps,
+                                       const double *shift, const int32_t *active, int32_t seg, double *s, double *r0,
+                                       double *work, int32_t *status, void *stream) {
+  return newton_fused_common(prob, x_int, params, param_stride, geom, y, eps, shift, active, seg, s, r0, work, status, nullptr,
+                             nullptr, stream);
+}
+
+extern "C" int sfxm_newton_step_fused(const sfxm_problem_t *prob, const double *x_int, const double *params,
+                                      int64_t param_stride, const double *geom, double *y, double eps, const double *shift,
+                                      const int32_t *active, int32_t seg, double *s, double *r0, double *work, int32_t *status,
+                                      double *norms2, void *stream) {
+  if (!norms2) return set_error("sfxm_newton_step_fused: null argument");
+  return newton_fused_common(prob, x_int, params, param_stride, geom, y, eps, shift, active, seg, s, r0, work, status, y, norms2,
+                             stream);
 }

@@ -265,6 +265,7 @@ struct FusedLaunch {
   double *s, *work;
   int32_t *status;
   cudaStream_t st;
+  StepUpd upd;      // {y, norms}: apply the step and return the criterion's sums from the same sweep (nullptr: do not)
 };
 
 template <class Model, int SCHEME, int NV, int S>
@@ -277,11 +278,11 @@ static int fused_launch_s(const FusedLaunch &L, int o, int cyclic) {
   const int threads = kThomasThreads;
   const unsigned blocks = (unsigned)((P.batch + threads - 1) / threads);
   if (cyclic == 1)
-    block_thomas_ll_kernel<Src, NV, S><<<blocks, threads, 0, L.st>>>(P, o, L.args, L.shift, L.active, L.s, workC, workR, L.status);
+    block_thomas_ll_kernel<Src, NV, S><<<blocks, threads, 0, L.st>>>(P, o, L.args, L.shift, L.active, L.s, workC, workR, L.status, L.upd);
   else if (cyclic)
-    block_thomas_kernel<Src, NV, S, true><<<blocks, threads, 0, L.st>>>(P, o, L.args, L.shift, L.active, L.s, workC, workR, L.status);
+    block_thomas_kernel<Src, NV, S, true><<<blocks, threads, 0, L.st>>>(P, o, L.args, L.shift, L.active, L.s, workC, workR, L.status, L.upd);
   else
-    block_thomas_kernel<Src, NV, S, false><<<blocks, threads, 0, L.st>>>(P, o, L.args, L.shift, L.active, L.s, workC, workR, L.status);
+    block_thomas_kernel<Src, NV, S, false><<<blocks, threads, 0, L.st>>>(P, o, L.args, L.shift, L.active, L.s, workC, workR, L.status, L.upd);
   return check_launch("sfxm_newton_solve_fused");
 }
 

@@ -81,11 +81,11 @@ static int launch_thomas(const sfxm_problem_t &P, int o, int cyclic, const doubl
   const typename MemSrc<NV>::Args src{J, f};
   const unsigned blocks = (unsigned)((P.batch + threads - 1) / threads);
   if (cyclic == 1)   // lower-left corner only
-    block_thomas_ll_kernel<MemSrc<NV>, NV, S><<<blocks, threads, 0, st>>>(P, o, src, shift, active, s, workC, workR, status);
+    block_thomas_ll_kernel<MemSrc<NV>, NV, S><<<blocks, threads, 0, st>>>(P, o, src, shift, active, s, workC, workR, status, StepUpd{nullptr, nullptr});
   else if (cyclic)
-    block_thomas_kernel<MemSrc<NV>, NV, S, true><<<blocks, threads, 0, st>>>(P, o, src, shift, active, s, workC, workR, status);
+    block_thomas_kernel<MemSrc<NV>, NV, S, true><<<blocks, threads, 0, st>>>(P, o, src, shift, active, s, workC, workR, status, StepUpd{nullptr, nullptr});
   else
-    block_thomas_kernel<MemSrc<NV>, NV, S, false><<<blocks, threads, 0, st>>>(P, o, src, shift, active, s, workC, workR, status);
+    block_thomas_kernel<MemSrc<NV>, NV, S, false><<<blocks, threads, 0, st>>>(P, o, src, shift, active, s, workC, workR, status, StepUpd{nullptr, nullptr});
   return check_launch("sfxm_block_tridiag_solve");
 }
 

@@ -113,6 +113,37 @@ struct MemSrc {
   }
 };
 
+// The Newton update folded into the back substitution: the thread that computes a member's step also applies it,
+// y += s, and accumulates the two sums of the convergence criterion (sum s^2, sum y_new^2) on the way - one thread owns
+// one member for the whole sweep, so the per-member norms need no reduction at all and the separate update + norms pass
+// over (y, s) (sfxm_update_norms: two launches, ~0.11 ms per segment of the bench ensemble) disappears.  Every read of y
+// by the row source precedes the first write of a step (the forward sweep and the last-row set-up come first).
+struct StepUpd {
+  double *y;        // state to update in place (nullptr: the step is only stored)
+  double *norms;    // norms[m] = sum s^2, norms[batch + m] = sum y_new^2 over the segment (nullptr with y == nullptr)
+};
+
+struct StepSink {
+  double *s_out, *y;
+  double ss, yy;
+  __device__ __forceinline__ StepSink(double *s, const StepUpd &u) : s_out(s), y(u.y), ss(0.0), yy(0.0) {}
+  __device__ __forceinline__ void put(int64_t idx, double v) {
+    s_out[idx] = v;
+    if (y) {
+      const double yn = y[idx] + v;
+      y[idx] = yn;
+      ss += v * v;
+      yy += yn * yn;
+    }
+  }
+  __device__ __forceinline__ void finish(const StepUpd &u, int64_t B, int64_t m) const {
+    if (u.y && u.norms) {
+      u.norms[m] = ss;
+      u.norms[B + m] = yy;
+    }
+  }
+};
+
 // The kernels below take their block rows from a row source `Src`: MemSrc (an assembled Jacobian in HBM) or the fused
 // source of sfxm_fused.cuh, which evaluates the block row of a cell on the fly so that J never exists in memory.
 // Protocol per block row i: src.prepare(P, i, m) once, then src.block<S>(P, i, d, o, m, blk) / src.rhs(P, i, o, r, m).
@@ -125,7 +156,7 @@ __global__ void __launch_bounds__(Src::kMaxThreads, Src::kMinCtas)
 block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __grid_constant__ typename Src::Args sargs,
                     const double *__restrict__ shift,
                     const int32_t *__restrict__ active, double *__restrict__ s_out, double *__restrict__ workC,
-                    double *__restrict__ workR, int32_t *__restrict__ status) {
+                    double *__restrict__ workR, int32_t *__restrict__ status, const StepUpd upd) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t B = P.batch;
   if (m >= B) return;
@@ -137,6 +168,7 @@ block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __gri
   const int64_t n = P.nx;
   const int64_t ne = CYCLIC ? n - 1 : n;
   bool ok = true;
+  StepSink sink(s_out, upd);
   double Cp[S][S], Rp[S][NR];   // C'_{i-1}, rhs'_{i-1}
   auto fidx = [&](int64_t i, int r) { return (P.var_base[o + r] + i * (int64_t)P.var_stride[o + r] + P.var_off[o + r]) * B + m; };
   for (int64_t i = 0; i < ne; ++i) {
@@ -204,7 +236,7 @@ block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __gri
     for (int c = 0; c < NR; ++c) X[r][c] = Rp[r][c];
   if constexpr (!CYCLIC) {
 #pragma unroll
-    for (int r = 0; r < S; ++r) s_out[fidx(ne - 1, r)] = X[r][0];
+    for (int r = 0; r < S; ++r) sink.put(fidx(ne - 1, r), X[r][0]);
   } else {
 #pragma unroll
     for (int r = 0; r < S; ++r)
@@ -270,7 +302,7 @@ block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __gri
       for (int c = 0; c < NR; ++c) X[r][c] = Rn[r][c];
     if constexpr (!CYCLIC) {
 #pragma unroll
-      for (int r = 0; r < S; ++r) s_out[fidx(i, r)] = X[r][0];
+      for (int r = 0; r < S; ++r) sink.put(fidx(i, r), X[r][0]);
     } else {
 #pragma unroll
       for (int r = 0; r < S; ++r)
@@ -312,7 +344,7 @@ block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __gri
       }
     ok = gj_solve<S, 1>(Bd, rhs) && ok;
 #pragma unroll
-    for (int r = 0; r < S; ++r) s_out[fidx(n - 1, r)] = rhs[r][0];
+    for (int r = 0; r < S; ++r) sink.put(fidx(n - 1, r), rhs[r][0]);
     for (int64_t i = 0; i < ne; ++i) {
       if (i + PrefetchDist<S>::value < ne) {
 #pragma unroll
@@ -327,10 +359,11 @@ block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __gri
         double xv = w[0];
 #pragma unroll
         for (int c = 0; c < S; ++c) xv -= w[(int64_t)(1 + c) * B] * rhs[c][0];
-        s_out[fidx(i, r)] = xv;
+        sink.put(fidx(i, r), xv);
       }
     }
   }
+  sink.finish(upd, B, m);
   if (status && !ok) status[m] = 1;
 }
 
@@ -344,7 +377,7 @@ __global__ void __launch_bounds__(Src::kMaxThreads, Src::kMinCtas)
 block_thomas_ll_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __grid_constant__ typename Src::Args sargs,
                        const double *__restrict__ shift,
                        const int32_t *__restrict__ active, double *__restrict__ s_out, double *__restrict__ workC,
-                       double *__restrict__ workR, int32_t *__restrict__ status) {
+                       double *__restrict__ workR, int32_t *__restrict__ status, const StepUpd upd) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t B = P.batch;
   if (m >= B) return;
@@ -353,6 +386,7 @@ block_thomas_ll_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __
   const double sh = shift ? shift[m] : 0.0;
   const int64_t n = P.nx;
   bool ok = true;
+  StepSink sink(s_out, upd);
   auto fidx = [&](int64_t i, int r) { return (P.var_base[o + r] + i * (int64_t)P.var_stride[o + r] + P.var_off[o + r]) * B + m; };
   double G[S][S], Alast[S][S], Blast[S][S], dl[S];
   src.prepare(P, n - 1, m);
@@ -437,7 +471,7 @@ block_thomas_ll_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __
   }
   ok = gj_solve<S, 1>(Blast, X) && ok;
 #pragma unroll
-  for (int r = 0; r < S; ++r) s_out[fidx(n - 1, r)] = X[r][0];
+  for (int r = 0; r < S; ++r) sink.put(fidx(n - 1, r), X[r][0]);
   constexpr int KB = S * S + S;
   constexpr int DB = RingDepth<KB>::value;
   __shared__ double ring[DB][KB][kThomasThreads];
@@ -472,9 +506,10 @@ block_thomas_ll_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __
 #pragma unroll
     for (int r = 0; r < S; ++r) {
       X[r][0] = Xn[r];
-      s_out[fidx(i, r)] = Xn[r];
+      sink.put(fidx(i, r), Xn[r]);
     }
   }
+  sink.finish(upd, B, m);
   if (status && !ok) status[m] = 1;
 }
 

@@ -301,6 +301,21 @@ class Engine:
         _lib.count()
         return s
 
+    def newton_step_fused(self, y, s, split=False, split_locs=None, seg=0, eps=1e-8, shift=None, active=None,
+                          status=None, r0=None):
+        """newton_solve_fused with the update folded into the back substitution: y += s in place for the active members;
+        -> (sum s^2, sum y_new^2) over the segment, per member (valid for the active members)."""
+        P, _ = self.problem(split, split_locs)
+        nbytes = self.lib.sfxm_solve_workspace_bytes(ctypes.byref(P))
+        work = self._scratch("solve", nbytes // 8)
+        out2 = torch.empty(2 * self.batch, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.sfxm_newton_step_fused(ctypes.byref(P), _lib.ptr(self.x_int), _lib.ptr(self.params),
+                                                   self.param_stride, _lib.ptr(self._geom), _lib.ptr(y), float(eps),
+                                                   _lib.ptr(shift), _lib.ptr(active), int(seg), _lib.ptr(s), _lib.ptr(r0),
+                                                   _lib.ptr(work), _lib.ptr(status), _lib.ptr(out2), _lib.stream_ptr()))
+        _lib.count()
+        return out2[:self.batch], out2[self.batch:]
+
     def _pcr_launches(self, P, seg, n=None):
         """Kernel launches of one PCR segment solve (csrc/sfxm_pcr.cu): 1 when the rows fit in shared memory
         (pcr_smem_kernel); large meshes: chunk reduce + separator rows + fold around the solve of the nx / 256

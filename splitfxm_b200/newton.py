@@ -51,6 +51,10 @@ class NewtonDriver:
         self.rt = torch.empty((eng.n, B), dtype=torch.float64, device=dev) if (armijo or dt0 > 0) else None
         self.yt = torch.empty((eng.n, B), dtype=torch.float64, device=dev) if armijo else None
         self.status = torch.zeros(B, dtype=torch.int32, device=dev)
+        # per segment: sum s^2 of the member's last step there and sum y^2 of its current state there - an enclosing
+        # Split-Newton level forms its criterion from these instead of another pass over (y, s)
+        self.seg_ss = torch.zeros((len(self.segs), B), dtype=torch.float64, device=dev)
+        self.seg_yy = torch.zeros((len(self.segs), B), dtype=torch.float64, device=dev)
         # a slab-decomposed mesh (spike.SlabNewtonEngine) reduces the host-side decisions over the ranks
         fused_ok = getattr(eng, "fused_solve_supported", None)
         self.fused = bool(fused_ok(split, split_locs)) if (fused and fused_ok is not None) else False
@@ -119,16 +123,27 @@ class NewtonDriver:
         ticket.synchronize()
         return bool(int(self._any_host[0]))
 
-    def _end(self, run, ss, yy, it, crit, dt=None, r_old_sq=None, r_new_sq=None):
-        """crit, it (and the pseudo time step) of the members that ran, in place."""
+    def _end(self, run, ss, yy, it, crit, dt=None, r_old_sq=None, r_new_sq=None, nsum=1, keep=None):
+        """crit, it (and the pseudo time step) of the members that ran, in place.  ss, yy: [batch], or [nsum, batch] whose
+        rows are summed (the kept sums of the segments of an enclosing Split-Newton level); keep = (ss_row, yy_row)
+        receives the sums of the members that ran."""
         if self._lib is not None:
             from . import _lib
-            _lib.check(self._lib.sfxm_newton_end(self.eng.batch, _lib.ptr(run), _lib.ptr(ss), _lib.ptr(yy), ABS_TOL, REL_TOL,
-                                                 _lib.ptr(crit), _lib.ptr(it), _lib.ptr(dt), _lib.ptr(r_old_sq), _lib.ptr(r_new_sq),
-                                                 self.dtmax, _lib.stream_ptr()))
+            _lib.check(self._lib.sfxm_newton_end(self.eng.batch, _lib.ptr(run), _lib.ptr(ss), _lib.ptr(yy), int(nsum), ABS_TOL,
+                                                 REL_TOL, _lib.ptr(crit), _lib.ptr(it), _lib.ptr(dt), _lib.ptr(r_old_sq),
+                                                 _lib.ptr(r_new_sq), self.dtmax, _lib.ptr(keep[0]) if keep else None,
+                                                 _lib.ptr(keep[1]) if keep else None, _lib.stream_ptr()))
             _lib.count()
             return
         on = run != 0
+        if nsum > 1:
+            a, b = ss[0].clone(), yy[0].clone()
+            for q in range(1, nsum):
+                a, b = a + ss[q], b + yy[q]
+            ss, yy = a, b
+        if keep is not None:
+            keep[0].copy_(torch.where(on, ss, keep[0]))
+            keep[1].copy_(torch.where(on, yy, keep[1]))
         c = torch.sqrt(ss) / (ABS_TOL + REL_TOL * torch.sqrt(yy))
         crit.copy_(torch.where(on, c, crit))
         it.add_(on.to(torch.int64))
@@ -151,8 +166,13 @@ class NewtonDriver:
             if known is False:
                 break
             # everything below is masked by run32: launched before the flag is known, it is a no-op if nobody runs
-            if self.fused:
-                # ensembles: the sweeping thread evaluates each cell's block row itself (J never touches HBM)
+            stepped = None
+            if self.fused and not self.armijo and self.lb is None:
+                # ensembles, full steps: the sweeping thread evaluates each cell's block row itself (J never touches HBM),
+                # applies the step and accumulates the criterion's sums on its way back
+                stepped = eng.newton_step_fused(y, self.s, self.split, self.split_locs, k, self.eps, shift=shift,
+                                                active=run32, status=self.status, r0=self.r if need_rnorm else None)
+            elif self.fused:
                 eng.newton_solve_fused(y, self.s, self.split, self.split_locs, k, self.eps, shift=shift, active=run32,
                                        status=self.status, r0=self.r if need_rnorm else None)
             else:
@@ -183,12 +203,15 @@ class NewtonDriver:
             if scale is not None:
                 run = run32 != 0
                 self.s[lo:hi] = torch.where(run[None, :], self.s[lo:hi] * scale[None, :], self.s[lo:hi])
-            ss, yy = eng.update_norms(y, self.s, run32, lo, hi)       # y += s and both norms of the criterion, one pass
+            if stepped is not None:
+                ss, yy = stepped
+            else:
+                ss, yy = eng.update_norms(y, self.s, run32, lo, hi)   # y += s and both norms of the criterion, one pass
             r_new_sq = None
             if ptc:
                 eng.residual(y, self.rt, self.split, self.split_locs)
                 r_new_sq = eng.sumsq(self.rt, lo, hi)
-            self._end(run32, ss, yy, it, crit, dt, r_old_sq if ptc else None, r_new_sq)
+            self._end(run32, ss, yy, it, crit, dt, r_old_sq if ptc else None, r_new_sq, keep=(self.seg_ss[k], self.seg_yy[k]))
             if maxiter == 1:          # one step (the outer segments of Split-Newton): nobody can run a second time
                 break
             if known is None and not self._wait(ticket):
@@ -220,8 +243,8 @@ class NewtonDriver:
                 break
             self.split_newton(y, k0 + 1, maxiter, run32)      # inner segments to convergence
             self.newton_segment(y, k0, 1, run32)              # one step on this segment
-            ss, yy = eng.update_norms(y, self.s, None, lo, eng.n, update=False)
-            self._end(run32, ss, yy, it, crit)
+            # |s| and |y| over segments k0.. from the sums each segment kept of its last step (no pass over the vectors)
+            self._end(run32, self.seg_ss[k0:], self.seg_yy[k0:], it, crit, nsum=K - k0)
             if known is None and not self._wait(ticket):
                 break
         return it

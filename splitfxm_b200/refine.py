@@ -40,39 +40,41 @@ class Refiner:
         self._npmax = npmax
 
     # ------------------------------------------------------------------------------------------------
-    def _refine_device(self, xd, Ud, want_flags=True):
-        """Device refinement of one mesh: xd [n], Ud [n, nv] CUDA tensors -> (x_new, U_new, flags) on the device.
-        The only host round trip is the new mesh size (the allocation needs it); flags = dict(loc, keep, gridpt, comp):
-        device byte/int arrays for the report, or None."""
+    def _refine_device(self, xd, Ud, want_flags=True, pad=(0, 0)):
+        """Device refinement of one mesh: xd [n], Ud [n, nv] CUDA tensors -> (x_buf, U_buf, n_new, flags) on the device.
+
+        Three launches (sfxm_refine_fused: statistics, marking, single-pass scan + compaction).  The new mesh is written
+        into buffers of capacity pad[0] + (2n - 1) + pad[1] cells starting at cell pad[0] (room for the caller's ghost
+        cells); the only host round trip is the new size n_new.  flags = dict(loc, keep, gridpt, comp): device byte/int
+        arrays for the report, or None."""
         import torch
         lib = _lib.load()
         n, nv = Ud.shape
         if n > self._npmax:
             raise SFXM("Exceeded maximum number of points")        # refine.py:124-125
         dev = xd.device
-        work = torch.empty(lib.sfxm_refine_workspace_bytes(n), dtype=torch.uint8, device=dev)
+        work = torch.empty(lib.sfxm_refine_fused_workspace_bytes(n), dtype=torch.uint8, device=dev)
         counts = torch.zeros(3, dtype=torch.int64, device=dev)
+        cap = pad[0] + 2 * n - 1 + pad[1]
+        x_buf = torch.empty(cap, dtype=torch.float64, device=dev)
+        U_buf = torch.empty((cap, nv), dtype=torch.float64, device=dev)
         st = _lib.stream_ptr()
-        _lib.check(lib.sfxm_refine_mark(xd.data_ptr(), Ud.data_ptr(), n, nv, float(self._ratio), float(self._slope),
-                                        float(self._curve), float(self._prune), float(self._min_range),
-                                        float(self._min_grid), work.data_ptr(), counts.data_ptr(), st))
-        _lib.count(_lib.AMR_MARK_LAUNCHES)
-        n_new = int(counts[0])          # the one read-back the new allocation needs
-        x_new = torch.empty(n_new, dtype=torch.float64, device=dev)
-        U_new = torch.empty((n_new, nv), dtype=torch.float64, device=dev)
-        _lib.check(lib.sfxm_refine_apply(xd.data_ptr(), Ud.data_ptr(), n, nv, work.data_ptr(), x_new.data_ptr(),
-                                         U_new.data_ptr(), st))
-        _lib.count()
+        _lib.check(lib.sfxm_refine_fused(xd.data_ptr(), Ud.data_ptr(), n, nv, float(self._ratio), float(self._slope),
+                                         float(self._curve), float(self._prune), float(self._min_range),
+                                         float(self._min_grid), work.data_ptr(), x_buf[pad[0]:].data_ptr(),
+                                         U_buf[pad[0]:].data_ptr(), counts.data_ptr(), st))
+        _lib.count(_lib.AMR_FUSED_LAUNCHES)
         flags = None
         if want_flags:
             loc = torch.empty(n, dtype=torch.uint8, device=dev)
             keep = torch.empty(n, dtype=torch.uint8, device=dev)
             gridpt = torch.empty(n, dtype=torch.uint8, device=dev)
             comp = torch.empty(_lib.MAX_NV, dtype=torch.int32, device=dev)
-            _lib.check(lib.sfxm_refine_flags(work.data_ptr(), n, loc.data_ptr(), keep.data_ptr(), gridpt.data_ptr(),
-                                             comp.data_ptr(), st))
+            _lib.check(lib.sfxm_refine_fused_flags(work.data_ptr(), n, loc.data_ptr(), keep.data_ptr(), gridpt.data_ptr(),
+                                                   comp.data_ptr(), st))
             flags = dict(loc=loc, keep=keep, gridpt=gridpt, comp=comp)
-        return x_new, U_new, flags
+        n_new = int(counts[0])          # the one read-back
+        return x_buf, U_buf, n_new, flags
 
     def refine_arrays(self, x, U, want_flags=True):
         """Host arrays in, host arrays out (x[n], U[n, nv]) -> (x_new, U_new, flags as NumPy arrays or None)."""
@@ -82,10 +84,10 @@ class Refiner:
         dev = torch.device("cuda", torch.cuda.current_device())
         xd = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
         Ud = torch.from_numpy(np.ascontiguousarray(U, dtype=np.float64)).to(dev)
-        x_new, U_new, flags = self._refine_device(xd, Ud, want_flags)
+        x_buf, U_buf, n_new, flags = self._refine_device(xd, Ud, want_flags)
         if flags is not None:
             flags = {k: v.cpu().numpy() for k, v in flags.items()}
-        return x_new.cpu().numpy(), U_new.cpu().numpy(), flags
+        return x_buf[:n_new].cpu().numpy(), U_buf[:n_new].cpu().numpy(), flags
 
     @staticmethod
     def _dicts_from_flags(flags, names):
@@ -112,12 +114,16 @@ class Refiner:
             raise SFXM("splitfxm_b200 needs a CUDA device (there is no CPU fallback)")
         nbl, nbr, nx = d.nb(btype.LEFT), d.nb(btype.RIGHT), d._nx
         dx, dU = d._device()
-        x_new, U_new, flags = self._refine_device(dx[nbl:nbl + nx], dU[nbl:nbl + nx])
+        # the kernels write the new interior between the places of the ghost cells: no concatenation afterwards
+        x_buf, U_buf, n_new, flags = self._refine_device(dx[nbl:nbl + nx], dU[nbl:nbl + nx], pad=(nbl, nbr))
         names = [d.component_name(i) for i in range(d.num_components())]
         self.show_changes(*self._dicts_from_flags(flags, names))
         n_old = dx.shape[0]
-        d._adopt_device(torch.cat([dx[:nbl], x_new, dx[n_old - nbr:]]), torch.cat([dU[:nbl], U_new, dU[n_old - nbr:]]),
-                        nx=x_new.shape[0], mesh_changed=True)
+        x_buf[:nbl] = dx[:nbl]
+        U_buf[:nbl] = dU[:nbl]
+        x_buf[nbl + n_new:nbl + n_new + nbr] = dx[n_old - nbr:]
+        U_buf[nbl + n_new:nbl + n_new + nbr] = dU[n_old - nbr:]
+        d._adopt_device(x_buf[:nbl + n_new + nbr], U_buf[:nbl + n_new + nbr], nx=n_new, mesh_changed=True)
 
     def perform_changes(self, d, loc, keep):
         """Apply explicit changes (refine.py:239-282): a midpoint cell after every index in `loc`, every cell whose
