@@ -677,8 +677,13 @@ def extras(torch, sf, ens, Y, dev, peak):
             e1.solve(Jb, rr, ss, SPLIT, LOCS, status=st1)
             e1.update_norms(y, ss)
         ms_n = timed(newton_iteration, 3)
+        U0 = d.values(interior=True)
+        sim.steady_state(split=SPLIT, split_locs=LOCS)               # warm-up (allocations, first launches)
+        d.interior_U()[:, :] = U0                                    # host write: the timed call uploads the state again
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
-        iters = sim.steady_state(split=SPLIT, split_locs=LOCS)       # public API, host buffers in and out
+        iters = sim.steady_state(split=SPLIT, split_locs=LOCS)       # public API: host state in, device-resident result,
+        torch.cuda.synchronize()                                     # iteration count back
         t_ss = time.perf_counter() - t0
         if nx == 1000000:
             rooflines.append(roof("jacobian_scalar_kernel (one mesh, nx=1e6)", nx * (24 + 8 + 15 * 8), ms_j,
@@ -699,7 +704,7 @@ def extras(torch, sf, ens, Y, dev, peak):
     import io
     comps = ["rho", "rhou", "E"]
     nbc = {c: {"left": {"neumann": 0.0}, "right": {"neumann": 0.0}} for c in comps}
-    for nx in (100000, 1000000):
+    for nx in (100000, 1000000, 10000000):
         d = sf.Domain.from_size(nx, 1, 1, comps)
         xs = d.interior_x()
         d.interior_U()[:, 0] = np.where(xs < 0.5, 1.0, 0.125) + 0.01 * np.tanh(200 * (xs - 0.3))
@@ -710,24 +715,27 @@ def extras(torch, sf, ens, Y, dev, peak):
         xd = torch.from_numpy(np.ascontiguousarray(d.interior_x())).to(dev)
         Ud = torch.from_numpy(np.ascontiguousarray(d.interior_U())).to(dev)
         lib = _lib_mod.load()
-        work = torch.empty(lib.sfxm_refine_workspace_bytes(nx), dtype=torch.uint8, device=dev)
+        work = torch.empty(lib.sfxm_refine_fused_workspace_bytes(nx), dtype=torch.uint8, device=dev)
         counts = torch.zeros(3, dtype=torch.int64, device=dev)
         xo = torch.empty(2 * nx, dtype=torch.float64, device=dev)
         Uo = torch.empty((2 * nx, 3), dtype=torch.float64, device=dev)
 
-        def amr_pass():
-            _lib_mod.check(lib.sfxm_refine_mark(xd.data_ptr(), Ud.data_ptr(), nx, 3, 2.0, 0.05, 0.05, -0.001, 0.01, 1e-10,
-                                                work.data_ptr(), counts.data_ptr(), _lib_mod.stream_ptr()))
-            _lib_mod.check(lib.sfxm_refine_apply(xd.data_ptr(), Ud.data_ptr(), nx, 3, work.data_ptr(), xo.data_ptr(),
-                                                 Uo.data_ptr(), _lib_mod.stream_ptr()))
+        def amr_pass():      # statistics + marking + scan/compaction: three launches
+            _lib_mod.check(lib.sfxm_refine_fused(xd.data_ptr(), Ud.data_ptr(), nx, 3, 2.0, 0.05, 0.05, -0.001, 0.01, 1e-10,
+                                                 work.data_ptr(), xo.data_ptr(), Uo.data_ptr(), counts.data_ptr(),
+                                                 _lib_mod.stream_ptr()))
         ms_amr = timed(amr_pass, 5)
-        t0 = time.perf_counter()
         with contextlib.redirect_stdout(io.StringIO()):
-            r.refine(d)
+            r.refine(sf.Domain.from_arrays(d._host()[0], d._host()[1], 1, 1, comps))      # warm-up
+            d._device()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r.refine(d)                                               # device-resident Domain in, device-resident out
+            torch.cuda.synchronize()
         t_api = time.perf_counter() - t0
-        if nx == 1000000:
-            rooflines.append(roof("AMR pass (sfxm_refine_mark + sfxm_refine_apply), nx=1e6", nx * 96, ms_amr,
-                                  "SURVEY 8(d): ~96 B per cell over both passes"))
+        if nx >= 1000000:
+            rooflines.append(roof("AMR pass (sfxm_refine_fused: 3 launches), nx=%.0e" % nx, nx * 96, ms_amr,
+                                  "SURVEY 8(d): ~96 B per cell over both passes (1e6 cells = 96 MB: launch-latency-bound)"))
         out.setdefault("amr", []).append({"nx": nx, "device_pass_ms": ms_amr, "GBps": nx * 96 / ms_amr / 1e6,
                                           "cells_after": int(counts[0]), "refine_api_s": t_api})
     d = sf.Domain.from_size(100000, 1, 1, comps)
@@ -735,11 +743,19 @@ def extras(torch, sf, ens, Y, dev, peak):
     d.interior_U()[:, 0] = np.where(xs < 0.5, 1.0, 0.125)
     d.interior_U()[:, 2] = np.where(xs < 0.5, 2.5, 0.25)
     sim = sf.Simulation(d, Euler1DConservative(1.4, "FVM"), {}, nbc, sf.FVSchemes.LAX_FRIEDRICHS)
+    U0 = d.values(interior=True)
+    sim.evolve(2.0e-4, split=True, split_locs=[1])          # warm-up (allocations, tableau import)
+    d.interior_U()[:, :] = U0
+    torch.cuda.synchronize()
     before = _lib_mod.LAUNCHES[0]
     t0 = time.perf_counter()
     sim.evolve(2.0e-4, split=True, split_locs=[1])          # ~20 CFL-limited RK45 steps at dx = 1e-5
+    torch.cuda.synchronize()
     t_ev = time.perf_counter() - t0
-    out["rk45_evolve_sod_nx1e5"] = {"t_diff": 2.0e-4, "seconds": t_ev, "launches": _lib_mod.LAUNCHES[0] - before,
+    launches = _lib_mod.LAUNCHES[0] - before
+    out["rk45_evolve_sod_nx1e5"] = {"t_diff": 2.0e-4, "seconds": t_ev, "launches": launches,
+                                    "rhs_evaluations_est": (launches - 8) // 33 * 6 + 2,
+                                    "ms_per_rk45_step_est": 1e3 * t_ev / max((launches - 8) // 33, 1),
                                     "finite": bool(np.isfinite(d.values()).all())}
     return out
 

@@ -58,6 +58,29 @@ static __global__ void reduce_final_kernel(const double *__restrict__ partial, i
   out[m] = acc;
 }
 
+// Final stage for few members and many tiles (one large mesh: 1465 tiles at nx = 1e6, which the one-thread-per-member
+// loop above adds serially in ~0.1 ms): one CTA per member; thread t adds tiles t, t + 256, ... in increasing order,
+// then the 256 partial sums are folded by a fixed binary tree.  The order depends on (ntiles) only: bit-reproducible.
+static __global__ void __launch_bounds__(256)
+reduce_final_tree_kernel(const double *__restrict__ partial, int64_t ntiles, int64_t B, double *__restrict__ out) {
+  __shared__ double sh[256];
+  const int64_t m = blockIdx.x;
+  double acc = 0.0;
+  for (int64_t k = threadIdx.x; k < ntiles; k += 256) acc += partial[k * B + m];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[m] = sh[0];
+}
+
+static inline void reduce_final(const double *partial, int64_t ntiles, int64_t B, double *out, cudaStream_t st) {
+  if (B <= 64 && ntiles > 64) reduce_final_tree_kernel<<<(unsigned)B, 256, 0, st>>>(partial, ntiles, B, out);
+  else reduce_final_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(partial, ntiles, B, out);
+}
+
 // two sums per member from one pass: term(q, m) returns a double2; partial[(tile * 2 + w) * B + m], out2[w * B + m].
 // Same tiles and the same order of additions as reduce_partial_kernel, so each sum has the bits the one-sum kernel gives.
 template <class Term>
@@ -102,7 +125,7 @@ static void reduce_rows2(Term term, int64_t lo, int64_t hi, int64_t batch, doubl
     dim3 g((unsigned)ntiles, (unsigned)((batch + b.x - 1) / b.x));
     reduce_partial2_kernel<Term><<<g, b, 0, st>>>(term, lo, hi, batch, work);
   }
-  reduce_final_kernel<<<(unsigned)((2 * batch + 127) / 128), 128, 0, st>>>(work, ntiles, 2 * batch, out2);
+  reduce_final(work, ntiles, 2 * batch, out2, st);
 }
 
 // work must hold reduce_tiles(hi - lo, batch) * batch doubles
@@ -114,7 +137,7 @@ static void reduce_rows(Term term, int64_t lo, int64_t hi, int64_t batch, double
     dim3 g((unsigned)ntiles, (unsigned)((batch + b.x - 1) / b.x));
     reduce_partial_kernel<Term><<<g, b, 0, st>>>(term, lo, hi, batch, work);
   }
-  reduce_final_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(work, ntiles, batch, out);
+  reduce_final(work, ntiles, batch, out, st);
 }
 
 }  // namespace sfxm

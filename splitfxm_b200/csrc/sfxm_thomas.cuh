@@ -127,14 +127,21 @@ struct StepSink {
   double *s_out, *y;
   double ss, yy;
   __device__ __forceinline__ StepSink(double *s, const StepUpd &u) : s_out(s), y(u.y), ss(0.0), yy(0.0) {}
-  __device__ __forceinline__ void put(int64_t idx, double v) {
+  __device__ __forceinline__ void put(int64_t idx, double v) {     // y[idx] read here: one exposed load
     s_out[idx] = v;
-    if (y) {
-      const double yn = y[idx] + v;
-      y[idx] = yn;
-      ss += v * v;
-      yy += yn * yn;
-    }
+    if (y) put_y(idx, v, y[idx]);
+  }
+  // yold = y[idx] fetched ahead of time (the back substitution is a chain of dependent iterations: a load issued inside
+  // an iteration would add one HBM round trip to each of them - measured 16 ms instead of 5.5 ms per steady state)
+  __device__ __forceinline__ void put(int64_t idx, double v, double yold) {
+    s_out[idx] = v;
+    if (y) put_y(idx, v, yold);
+  }
+  __device__ __forceinline__ void put_y(int64_t idx, double v, double yold) {
+    const double yn = yold + v;
+    y[idx] = yn;
+    ss += v * v;
+    yy += yn * yn;
   }
   __device__ __forceinline__ void finish(const StepUpd &u, int64_t B, int64_t m) const {
     if (u.y && u.norms) {
@@ -255,8 +262,9 @@ block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __gri
     for (int c = 0; c < NR; ++c) Xlast[r][c] = X[r][c];
   constexpr int KB = S * S + S * NR;
   constexpr int DB = RingDepth<KB>::value;
-  __shared__ double ring[DB][KB][kThomasThreads];
+  __shared__ double ring[DB][KB + S][kThomasThreads];   // + S: the state values the step is added to (StepUpd)
   const int tx = threadIdx.x;
+  const bool upd_y = !CYCLIC && upd.y != nullptr;       // (cyclic: the steps are only known after the last row)
   auto issue = [&](int64_t row) {     // one commit group per call, empty past the first row: uniform group count
     if (row >= 0) {
       const int slot = (int)(row & (DB - 1));
@@ -268,6 +276,7 @@ block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __gri
 #pragma unroll
         for (int c = 0; c < NR; ++c)
           cp_async8(&ring[slot][S * S + r * NR + c][tx], workR + ((row * NV + (o + r)) * (int64_t)(1 + NV) + c) * B + m);
+        if (upd_y) cp_async8(&ring[slot][KB + r][tx], upd.y + fidx(row, r));
       }
     }
     cp_async_commit();
@@ -275,7 +284,7 @@ block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __gri
 #pragma unroll
   for (int k = 0; k < DB; ++k) issue(ne - 2 - k);
   for (int64_t i = ne - 2; i >= 0; --i) {
-    double C[S][S], Rn[S][NR];
+    double C[S][S], Rn[S][NR], yold[S];
     cp_async_wait<DB - 1>();          // the oldest group in flight (row i) has landed
     {
       const int slot = (int)(i & (DB - 1));
@@ -285,6 +294,7 @@ block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __gri
         for (int c = 0; c < S; ++c) C[r][c] = ring[slot][r * S + c][tx];
 #pragma unroll
         for (int c = 0; c < NR; ++c) Rn[r][c] = ring[slot][S * S + r * NR + c][tx];
+        yold[r] = upd_y ? ring[slot][KB + r][tx] : 0.0;
       }
     }
     issue(i - DB);                    // refills the slot just read
@@ -302,7 +312,7 @@ block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __gri
       for (int c = 0; c < NR; ++c) X[r][c] = Rn[r][c];
     if constexpr (!CYCLIC) {
 #pragma unroll
-      for (int r = 0; r < S; ++r) sink.put(fidx(i, r), X[r][0]);
+      for (int r = 0; r < S; ++r) sink.put(fidx(i, r), X[r][0], yold[r]);
     } else {
 #pragma unroll
       for (int r = 0; r < S; ++r)
@@ -352,6 +362,10 @@ block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __gri
 #pragma unroll
           for (int c = 0; c < NR; ++c)
             prefetch_l1(workR + (((i + PrefetchDist<S>::value) * NV + (o + r)) * (int64_t)(1 + NV) + c) * B + m);
+        if (upd.y) {
+#pragma unroll
+          for (int r = 0; r < S; ++r) prefetch_l1(upd.y + fidx(i + PrefetchDist<S>::value, r));
+        }
       }
 #pragma unroll
       for (int r = 0; r < S; ++r) {
@@ -474,13 +488,15 @@ block_thomas_ll_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __
   for (int r = 0; r < S; ++r) sink.put(fidx(n - 1, r), X[r][0]);
   constexpr int KB = S * S + S;
   constexpr int DB = RingDepth<KB>::value;
-  __shared__ double ring[DB][KB][kThomasThreads];
+  __shared__ double ring[DB][KB + S][kThomasThreads];   // + S: the state values the step is added to (StepUpd)
   const int tx = threadIdx.x;
+  const bool upd_y = upd.y != nullptr;
   auto issue = [&](int64_t row) {
     if (row >= 0) {
       const int slot = (int)(row & (DB - 1));
 #pragma unroll
       for (int r = 0; r < S; ++r) {
+        if (upd_y) cp_async8(&ring[slot][KB + r][tx], upd.y + fidx(row, r));
         cp_async8(&ring[slot][S * S + r][tx], workR + ((row * NV + (o + r)) * (int64_t)(1 + NV)) * B + m);
 #pragma unroll
         for (int c = 0; c < S; ++c)
@@ -492,7 +508,7 @@ block_thomas_ll_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __
 #pragma unroll
   for (int k = 0; k < DB; ++k) issue(n - 2 - k);
   for (int64_t i = n - 2; i >= 0; --i) {
-    double Xn[S];
+    double Xn[S], yold[S];
     cp_async_wait<DB - 1>();
     const int slot = (int)(i & (DB - 1));
 #pragma unroll
@@ -501,12 +517,13 @@ block_thomas_ll_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __
 #pragma unroll
       for (int c = 0; c < S; ++c) v -= ring[slot][r * S + c][tx] * X[c][0];
       Xn[r] = v;
+      yold[r] = upd_y ? ring[slot][KB + r][tx] : 0.0;
     }
     issue(i - DB);
 #pragma unroll
     for (int r = 0; r < S; ++r) {
       X[r][0] = Xn[r];
-      sink.put(fidx(i, r), Xn[r]);
+      sink.put(fidx(i, r), Xn[r], yold[r]);
     }
   }
   sink.finish(upd, B, m);

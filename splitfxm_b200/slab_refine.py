@@ -151,5 +151,4 @@ class SlabRefiner(Refiner):
         flags = dict(loc=np.concatenate([p[1] for p in pieces]), keep=np.concatenate([p[2] for p in pieces]),
                      gridpt=np.concatenate([p[3] for p in pieces]), comp=np.max([p[4] for p in pieces], axis=0))
         names = getattr(self, "names", None) or [f"component {i}" for i in range(_lib.MAX_NV)]
-        import torch
         self.show_changes(*self._dicts_from_flags({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in flags.items()}, names))
