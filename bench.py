@@ -407,7 +407,36 @@ def run_gpu(args):
                   "decoupled advection-diffusion equations)"}
     checksum = float(Jh[(e2e_steps - 1) % 2][:, 1, 0, :].sum())
     e2e["checksum_diag_u"] = checksum
-    del Jh
+    # what the host link gives when every rank copies at once: e2e is bound by the device->host copy of the Jacobians,
+    # so its scaling over the GPUs of one box is the scaling of this number (measured, not assumed)
+    probe = torch.empty(32 * 1024 * 1024, dtype=torch.float64, device=dev)          # 256 MB
+    host = Jh[0].reshape(-1)[:probe.numel()] if Jh[0].numel() >= probe.numel() else torch.empty(probe.numel(), dtype=torch.float64).pin_memory()
+    rates = []
+    for direction in ("d2h", "h2d"):
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(4):
+            if direction == "d2h":
+                host.copy_(probe, non_blocking=True)
+            else:
+                probe.copy_(host, non_blocking=True)
+        p1.record()
+        torch.cuda.synchronize()
+        rates.append(4 * probe.numel() * 8 / (p0.elapsed_time(p1) * 1e-3) / 1e9)
+    rt = torch.tensor(rates, dtype=torch.float64, device=dev)
+    if world > 1:
+        allr = [torch.empty_like(rt) for _ in range(world)]
+        dist.all_gather(allr, rt)
+        allr = torch.stack(allr).cpu().numpy()
+    else:
+        allr = rt.cpu().numpy()[None, :]
+    e2e["pcie_probe"] = {"what": "all ranks copy 4 x 256 MB pinned <-> device at the same time (GB/s per rank)",
+                         "d2h_GBps_per_rank": [round(float(v), 1) for v in allr[:, 0]],
+                         "h2d_GBps_per_rank": [round(float(v), 1) for v in allr[:, 1]],
+                         "d2h_GBps_aggregate": round(float(allr[:, 0].sum()), 1),
+                         "e2e_d2h_GBps_aggregate": round(e2e["value"] / total * world * e2e["d2h_bytes_per_step"] / 1e9, 1)}
+    del Jh, probe, host
 
     # ---- one large mesh, slab-decomposed over the ranks (BASELINE config 5): every rank, N > 1 only ----
     slab = None

@@ -85,3 +85,33 @@ def test_large_mesh_idempotent_when_resolved():
     x_new, U_new, flags = r.refine_arrays(x, U)
     assert np.array_equal(x_new, x) and np.array_equal(U_new, U)
     assert flags["loc"].sum() == 0 and (flags["keep"] == 1).all()
+
+
+def test_refinement_at_config3_scale_identical_to_reference():
+    """BASELINE config 3's mesh size: three consecutive passes on a 100,000-cell Sod-like state (-> 98,683 -> 119,221
+    -> 129,044 cells, each pass inserting ~2e4 and deleting 5e3-2e4 cells) through the Domain API, device-resident
+    between the passes.  Identical meshes are identical byte strings: sizes, SHA-256 digests of positions and values and
+    every 997th cell are compared with what the unmodified reference produced (tests/golden/make_amr_large_golden.py)."""
+    import os
+    import sys
+    import splitfxm_b200 as sf
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_amr_large_golden as g
+    z = load("amr_large")
+    x, U = g.sod_like_state(int(z["nx0"]))
+    assert g.digest(x) == str(z["input_x_sha"]) and g.digest(U) == str(z["input_U_sha"])     # same input on this machine
+    d = sf.Domain.from_size(int(z["nx0"]), 1, 1, ["rho", "rhou", "E"])
+    assert np.array_equal(d.interior_x(), x)
+    d.interior_U()[:, :] = U
+    r = sf.Refiner()
+    r.set_criteria(*[float(v) for v in z["criteria"]])
+    r.set_max_points(10 * int(z["nx0"]))
+    for k in range(g.PASSES):
+        with contextlib.redirect_stdout(io.StringIO()):
+            r.refine(d)
+        assert not d._host_ok                       # the new mesh stays on the device between the passes
+        dx, dU = d.device_arrays()
+        xs, Us = dx[1:-1].cpu().numpy(), dU[1:-1].cpu().numpy()
+        assert xs.shape[0] == int(z[f"n{k}"]), (k, xs.shape[0])
+        assert np.array_equal(xs[::997], z[f"x_sample{k}"]) and np.array_equal(Us[::997], z[f"U_sample{k}"])
+        assert g.digest(xs) == str(z[f"x_sha{k}"]) and g.digest(Us) == str(z[f"U_sha{k}"])
