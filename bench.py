@@ -291,8 +291,10 @@ def run_gpu(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    if world > 1 or os.environ.get("SFXM_BENCH_FORCE_DIST"):      # (the env switch: NCCL initialised on one GPU, for diagnosis)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"), rank=rank, world_size=world)
     dev = torch.device(f"cuda:{local}")
     B = args.members
     total = B * world

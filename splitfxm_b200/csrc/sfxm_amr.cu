@@ -25,6 +25,7 @@
 #include <cstdint>
 #include "../../include/sfxm_b200.h"
 #include "sfxm_host.h"
+#include "sfxm_device.cuh"   // div_known / sane: exact quotients by a divisor whose reciprocal is shared (section 3.1)
 
 namespace sfxm {
 
@@ -37,6 +38,21 @@ struct Window {   // a rank's view of the global mesh: array index t <-> global 
 struct Stats {   // per variable: min/max of values and of slopes (refine.py:146-153)
   double vmin[SFXM_MAX_NV], vmax[SFXM_MAX_NV], smin[SFXM_MAX_NV], smax[SFXM_MAX_NV];
 };
+
+// One mesh on one GPU: what the marking kernel divides by for every cell, prepared once by the statistics kernel.
+// The refinement kernels were bound by their IEEE divisions (ncu r2h: issue slots 71-73 % busy, ~17 divisions of ~35
+// instructions per cell in the marking kernel); a quotient by a divisor whose correctly rounded reciprocal is known costs
+// five FMAs and has the same bits (div_known; each thread checks its operands and otherwise divides).
+struct MarkConst {
+  double rdmax_slope[SFXM_MAX_NV];   // RN(1 / (slope * (vmax - vmin) + ulp)), refine.py:160
+  int32_t ok[SFXM_MAX_NV];           // divisor within 2^+-120
+};
+
+// a / b with rb = RN(1 / b): five FMAs when the operands are sane, the IEEE division otherwise (same result)
+__device__ __forceinline__ double div_shared(double a, double b, double rb, bool b_ok) {
+  return (b_ok && sane(a, 120)) ? div_known<true>(a, b, rb) : div_ieee(a, b);
+}
+__device__ __forceinline__ bool divisor_ok(double b) { return sane(b, 120) && b != 0.0; }
 
 __device__ __forceinline__ double warp_min(double v) {
   for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -109,7 +125,8 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 amr_mark_kernel(const double *__restrict__ z, const double *__restrict__ U, const Window wd, const Criteria cr,
                 const Stats *__restrict__ st, uint8_t *__restrict__ keep1, uint8_t *__restrict__ visited,
-                uint8_t *__restrict__ loc, int32_t *__restrict__ comp, uint8_t *__restrict__ gridpt) {
+                uint8_t *__restrict__ loc, int32_t *__restrict__ comp, uint8_t *__restrict__ gridpt,
+                const MarkConst *__restrict__ mc) {
   // t: index into the window arrays; j: the global cell index every rule of refine.py is written in
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= wd.ne) return;
@@ -123,6 +140,10 @@ amr_mark_kernel(const double *__restrict__ z, const double *__restrict__ U, cons
   const double zj = __ldg(z + t);
   const double dzj = j + 1 < n ? __ldg(z + t + 1) - zj : 0.0;          // dz[j]
   const double dzj1 = j + 2 < n ? __ldg(z + t + 2) - __ldg(z + t + 1) : 0.0;   // dz[j+1]
+  // reciprocals shared by the NV slopes of an interval (mc == nullptr: the window path, plain divisions)
+  const bool z0_ok = mc != nullptr && divisor_ok(dzj), z1_ok = mc != nullptr && divisor_ok(dzj1);
+  const double rz0 = 1.0 / dzj, rz1 = 1.0 / dzj1;
+  const double ulp_dz = div_shared(kUlp, dzj, rz0, z0_ok);                    // kUlp / dz[j], refine.py:188
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const double vmin = st->vmin[i], vmax = st->vmax[i], smin = st->smin[i], smax = st->smax[i];
@@ -133,7 +154,7 @@ amr_mark_kernel(const double *__restrict__ z, const double *__restrict__ U, cons
     // slope criterion on interval j (refine.py:159-173)
     if (j + 1 < n && (vmax - vmin) > cr.min_range * aa) {
       const double dmax = cr.slope * (vmax - vmin) + kUlp;
-      const double r = fabs(v1 - v0) / dmax;
+      const double r = mc != nullptr ? div_shared(fabs(v1 - v0), dmax, mc->rdmax_slope[i], mc->ok[i] != 0) : fabs(v1 - v0) / dmax;
       if (r > 1.0 && dzj >= 2 * cr.min_grid) { loc[t] = 1; if (own) comp[i] = 1; }
       if (r >= cr.prune) { keep1[t] = 1; keep1[t + 1] = 1; }
       else visited[t] = 1;
@@ -141,10 +162,10 @@ amr_mark_kernel(const double *__restrict__ z, const double *__restrict__ U, cons
     // curvature criterion on the pair of intervals (j, j+1) (refine.py:179-197)
     if (j + 2 < n && (smax - smin) > cr.min_range * ss) {
       const double v2 = __ldg(U + (t + 2) * NV + i);
-      const double s0 = (v1 - v0) / dzj;
-      const double s1 = (v2 - v1) / dzj1;
+      const double s0 = div_shared(v1 - v0, dzj, rz0, z0_ok);
+      const double s1 = div_shared(v2 - v1, dzj1, rz1, z1_ok);
       const double dmax = cr.curve * (smax - smin);
-      const double r = fabs(s1 - s0) / (dmax + (kUlp / dzj));
+      const double r = fabs(s1 - s0) / (dmax + ulp_dz);
       if (r > 1.0 && dzj >= 2 * cr.min_grid && dzj1 >= 2 * cr.min_grid) { if (own) comp[i] = 1; loc[t] = 1; loc[t + 1] = 1; }
       if (r >= cr.prune) keep1[t + 1] = 1;
       else visited[t + 1] = 1;
@@ -304,7 +325,7 @@ static int amr_mark_t(const double *z, const double *U, const Window &wd, const 
   amr_mark_kernel<NV><<<blocks, threads, 0, st>>>(z, U, wd, cr, (const Stats *)stats_dev,
                                                   (uint8_t *)(work + w.off_keep1), (uint8_t *)(work + w.off_visited),
                                                   (uint8_t *)(work + w.off_loc), (int32_t *)(work + w.off_comp),
-                                                  (uint8_t *)(work + w.off_gridpt));
+                                                  (uint8_t *)(work + w.off_gridpt), nullptr);
   amr_run_start_kernel<<<blocks, threads, 0, st>>>((const uint8_t *)(work + w.off_keep1),
                                                    (const uint8_t *)(work + w.off_visited), wd, (int64_t *)(work + w.off_start));
   size_t cb = (size_t)w.cub_bytes;
@@ -382,7 +403,8 @@ struct TileDesc {                 // status in the two top bits: 0 = not ready, 
 template <int NV>
 __global__ void __launch_bounds__(256)
 amr_stats_zero_kernel(const double *__restrict__ z, const double *__restrict__ U, const Window wd, double *__restrict__ part,
-                      Stats *__restrict__ out, unsigned int *__restrict__ ticket, uint4 *__restrict__ zero_lo, int64_t zero_n16) {
+                      Stats *__restrict__ out, MarkConst *__restrict__ mc, double slope, unsigned int *__restrict__ ticket,
+                      uint4 *__restrict__ zero_lo, int64_t zero_n16) {
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < zero_n16; q += (int64_t)gridDim.x * blockDim.x)
     zero_lo[q] = make_uint4(0u, 0u, 0u, 0u);
   double lo_v[NV], hi_v[NV], lo_s[NV], hi_s[NV];
@@ -391,13 +413,15 @@ amr_stats_zero_kernel(const double *__restrict__ z, const double *__restrict__ U
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < wd.ne; j += (int64_t)gridDim.x * blockDim.x) {
     const bool has_s = j + 1 < wd.ne;
     const double dz = has_s ? __ldg(z + j + 1) - __ldg(z + j) : 1.0;
+    const bool dz_ok = divisor_ok(dz);
+    const double rz = 1.0 / dz;                            // shared by the NV slopes of the interval
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const double v = __ldg(U + j * NV + i);
       lo_v[i] = fmin(lo_v[i], v);
       hi_v[i] = fmax(hi_v[i], v);
       if (has_s) {
-        const double sl = (__ldg(U + (j + 1) * NV + i) - v) / dz;
+        const double sl = div_shared(__ldg(U + (j + 1) * NV + i) - v, dz, rz, dz_ok);
         lo_s[i] = fmin(lo_s[i], sl);
         hi_s[i] = fmax(hi_s[i], sl);
       }
@@ -424,17 +448,39 @@ amr_stats_zero_kernel(const double *__restrict__ z, const double *__restrict__ U
   __syncthreads();
   if (!last) return;
   __threadfence();
-  if (threadIdx.x < 4 * NV) {            // min / max are exact: the fold order does not matter
+  // min / max are exact: the fold order does not matter.  256 threads fold the partials of the 4 NV statistics in
+  // groups (a one-thread-per-statistic loop over ~600 partials was half of this kernel's time), then 4 NV threads finish.
+  __shared__ double fold[256];
+  constexpr int NS = 4 * NV, NG = 256 / NS;
+  {
+    const int v = threadIdx.x % NS, g = threadIdx.x / NS;
+    const bool is_min = (v & 1) == 0;
+    double acc = is_min ? INFINITY : -INFINITY;
+    if (g < NG) {
+      const volatile double *vp = part;
+      for (unsigned k = g; k < gridDim.x; k += NG) acc = is_min ? fmin(acc, vp[(int64_t)k * NS + v]) : fmax(acc, vp[(int64_t)k * NS + v]);
+    }
+    fold[threadIdx.x] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < NS) {
     const int t = threadIdx.x;
     const bool is_min = (t & 1) == 0;
-    const volatile double *vp = part;
-    double acc = vp[t];
-    for (unsigned k = 1; k < gridDim.x; ++k) acc = is_min ? fmin(acc, vp[(int64_t)k * 4 * NV + t]) : fmax(acc, vp[(int64_t)k * 4 * NV + t]);
+    double acc = fold[t];
+    for (int g = 1; g < NG; ++g) acc = is_min ? fmin(acc, fold[g * NS + t]) : fmax(acc, fold[g * NS + t]);
     const int i = t >> 2, f = t & 3;
     if (f == 0) out->vmin[i] = acc;
     else if (f == 1) out->vmax[i] = acc;
     else if (f == 2) out->smin[i] = acc;
     else out->smax[i] = acc;
+    fold[t] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {                                  // the slope criterion's divisor, the same expression as in
+    const int i = threadIdx.x;                             // amr_mark_kernel (refine.py:160), and its reciprocal
+    const double dmax = slope * (fold[4 * i + 1] - fold[4 * i]) + kUlp;
+    mc->rdmax_slope[i] = 1.0 / dmax;
+    mc->ok[i] = divisor_ok(dmax) ? 1 : 0;
   }
 }
 
@@ -485,15 +531,32 @@ amr_scan_apply_kernel(const double *__restrict__ z, const double *__restrict__ U
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t t0 = (int64_t)tile * kScanTile + threadIdx.x * kScanItems;
   bool del0[kScanItems], lc[kScanItems];
+  static_assert(kScanItems == 4, "the flags of a thread's items are one 32-bit word");
+  // the flag arrays are 256-byte aligned and padded (fused_layout), t0 is a multiple of 4: one word per array
+  uint32_t wv = 0, wk = 0, wl = 0;
+  if (t0 < n) {
+    wv = *reinterpret_cast<const uint32_t *>(visited + t0);
+    wk = *reinterpret_cast<const uint32_t *>(keep1 + t0);
+    wl = *reinterpret_cast<const uint32_t *>(loc + t0);
+  }
   bool prev = t0 > 0 && t0 - 1 < n && visited[t0 - 1] && !keep1[t0 - 1];
+  // the cells the thread will copy or average, requested now: their latency hides behind the two look-backs
+  double zc[kScanItems + 1], Uc[kScanItems + 1][NV];
+#pragma unroll
+  for (int k = 0; k <= kScanItems; ++k) {
+    const int64_t t = t0 + k;
+    zc[k] = t < n ? __ldg(z + t) : 0.0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) Uc[k][i] = t < n ? __ldg(U + t * NV + i) : 0.0;
+  }
   long long run[kScanItems];                              // 1 + latest run start <= t inside the thread's items (0 = none)
   long long running = 0;
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
     const int64_t t = t0 + k;
     const bool in = t < n;
-    del0[k] = in && visited[t] && !keep1[t];
-    lc[k] = in && loc[t] && t + 1 < n;
+    del0[k] = in && ((wv >> (8 * k)) & 0xffu) && !((wk >> (8 * k)) & 0xffu);
+    lc[k] = in && ((wl >> (8 * k)) & 0xffu) && t + 1 < n;
     if (del0[k] && !prev) running = t + 1;
     run[k] = running;
     prev = del0[k];
@@ -582,15 +645,15 @@ amr_scan_apply_kernel(const double *__restrict__ z, const double *__restrict__ U
     const int64_t kb = (int64_t)(pos >> 31), ib = (int64_t)(pos & ((1ull << 31) - 1));
     if (kp[k]) {
       const int64_t o = kb + ib;
-      z_out[o] = __ldg(z + t);
+      z_out[o] = zc[k];
 #pragma unroll
-      for (int i = 0; i < NV; ++i) U_out[o * NV + i] = __ldg(U + t * NV + i);
+      for (int i = 0; i < NV; ++i) U_out[o * NV + i] = Uc[k][i];
     }
     if (lc[k]) {
       const int64_t o = kb + (kp[k] ? 1 : 0) + ib;
-      z_out[o] = 0.5 * (__ldg(z + t + 1) + __ldg(z + t));                                 // refine.py:268
+      z_out[o] = 0.5 * (zc[k + 1] + zc[k]);                                               // refine.py:268
 #pragma unroll
-      for (int i = 0; i < NV; ++i) U_out[o * NV + i] = 0.5 * (__ldg(U + (t + 1) * NV + i) + __ldg(U + t * NV + i));   // :269
+      for (int i = 0; i < NV; ++i) U_out[o * NV + i] = 0.5 * (Uc[k + 1][i] + Uc[k][i]);   // :269
     }
     pos += (kp[k] ? (1ull << 31) : 0ull) + (lc[k] ? 1ull : 0ull);
   }
@@ -603,7 +666,7 @@ amr_scan_apply_kernel(const double *__restrict__ z, const double *__restrict__ U
 }
 
 struct FusedLayout {
-  int64_t off_part, off_stats, off_stats_ticket, off_zero, off_keep1, off_visited, off_loc, off_gridpt, off_comp, off_ticket, off_desc, zero_bytes,
+  int64_t off_part, off_stats, off_stats_ticket, off_mc, off_zero, off_keep1, off_visited, off_loc, off_gridpt, off_comp, off_ticket, off_desc, zero_bytes,
       off_keepf, total;
 };
 
@@ -614,6 +677,7 @@ static FusedLayout fused_layout(int64_t n) {
   w.off_part = take(1024 * 4 * SFXM_MAX_NV * 8);
   w.off_stats = take(sizeof(Stats));
   w.off_stats_ticket = take(16);                           // last-block ticket of launch 1 (zeroed by a 4-byte memset)
+  w.off_mc = take(sizeof(MarkConst));
   w.off_zero = o;                                          // everything from here to off_keepf is zero-filled by launch 1
   w.off_keep1 = take(n);
   w.off_visited = take(n);
@@ -639,11 +703,12 @@ static int amr_fused_t(const double *z, const double *U, int64_t n, const Criter
   unsigned int *tile_counter = (unsigned int *)(work + w.off_ticket);            // inside the region launch 1 zero-fills
   cudaMemsetAsync(stats_ticket, 0, sizeof(unsigned int), st);
   amr_stats_zero_kernel<NV><<<sblocks, 256, 0, st>>>(z, U, wd, (double *)(work + w.off_part), (Stats *)(work + w.off_stats),
-                                                     stats_ticket, (uint4 *)(work + w.off_zero), w.zero_bytes / 16);
+                                                     (MarkConst *)(work + w.off_mc), cr.slope, stats_ticket,
+                                                     (uint4 *)(work + w.off_zero), w.zero_bytes / 16);
   amr_mark_kernel<NV><<<(unsigned)blocks_all, 256, 0, st>>>(z, U, wd, cr, (const Stats *)(work + w.off_stats),
                                                             (uint8_t *)(work + w.off_keep1), (uint8_t *)(work + w.off_visited),
                                                             (uint8_t *)(work + w.off_loc), (int32_t *)(work + w.off_comp),
-                                                            (uint8_t *)(work + w.off_gridpt));
+                                                            (uint8_t *)(work + w.off_gridpt), (const MarkConst *)(work + w.off_mc));
   const unsigned tiles = (unsigned)((n + kScanTile - 1) / kScanTile);
   amr_scan_apply_kernel<NV><<<tiles, kScanThreads, 0, st>>>(z, U, n, (const uint8_t *)(work + w.off_keep1),
                                                             (const uint8_t *)(work + w.off_visited), (const uint8_t *)(work + w.off_loc),
