@@ -202,14 +202,15 @@ int sfxm_update_norms(double *y, const double *s, const double *alpha, const int
 
 /* Per-member bookkeeping of the Newton / Split-Newton iteration (the loop the reference delegates to the third-party
  * splitnewton, simulation.py:515-523; specification: oracle/newton.py).  All arrays are device arrays [batch].
- * begin: run[m] = parent[m] (NULL = all) && crit[m] >= 1 && it[m] < maxiter; shift[m] = -1 / dt[m] (shift NULL: no
- *        pseudo-transient term); *any_flag = 1 if any member runs (zeroed first).
+ * begin: (reset != 0: first crit[m] = inf, it[m] = 0, dt[m] = dt0 - the start of a loop;) run[m] = parent[m] (NULL = all)
+ *        && crit[m] >= 1 && it[m] < maxiter; shift[m] = -1 / dt[m] (shift NULL: no pseudo-transient term); *any_flag = 1
+ *        if any member runs (zeroed first).
  * end:   for running members crit[m] = sqrt(SS) / (abs_tol + rel_tol * sqrt(YY)) with SS = sum_{q < nsum} ss[q*batch + m]
  *        (YY likewise; nsum = 1: one segment's sums; an enclosing Split-Newton level sums the kept sums of its segments),
  *        it[m] += 1, keep_ss[m] = SS / keep_yy[m] = YY if given, and, if dt != NULL,
  *        dt[m] = min(dt[m] * sqrt(r_old_sq[m]) / sqrt(r_new_sq[m]), dtmax) (dtmax when the new residual is zero). */
-int sfxm_newton_begin(int64_t batch, const int32_t *parent, const double *crit, const int64_t *it, double maxiter,
-                      const double *dt, int32_t *run, double *shift, int32_t *any_flag, void *stream);
+int sfxm_newton_begin(int64_t batch, const int32_t *parent, double *crit, int64_t *it, double maxiter, double *dt, double dt0,
+                      int32_t reset, int32_t *run, double *shift, int32_t *any_flag, void *stream);
 int sfxm_newton_end(int64_t batch, const int32_t *run, const double *ss, const double *yy, int32_t nsum, double abs_tol,
                     double rel_tol, double *crit, int64_t *it, double *dt, const double *r_old_sq, const double *r_new_sq,
                     double dtmax, double *keep_ss, double *keep_yy, void *stream);

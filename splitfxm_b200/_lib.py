@@ -70,7 +70,7 @@ SIGNATURES = {
     "sfxm_sumsq_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "sfxm_sumsq": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "sfxm_update_norms": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
-    "sfxm_newton_begin": (ctypes.c_int, [c_i64, c_vp, c_vp, c_vp, c_f64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_newton_begin": (ctypes.c_int, [c_i64, c_vp, c_vp, c_vp, c_f64, c_vp, c_f64, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_newton_end": (ctypes.c_int, [c_i64, c_vp, c_vp, c_vp, c_i32, c_f64, c_f64, c_vp, c_vp, c_vp, c_vp, c_vp, c_f64,
                                        c_vp, c_vp, c_vp]),
     "sfxm_axpy_masked": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
@@ -139,8 +139,18 @@ def ptr(t):
 
 
 def stream_ptr():
-    import torch
-    return torch.cuda.current_stream().cuda_stream
+    return _torch().cuda.current_stream().cuda_stream
+
+
+_torch_mod = None
+
+
+def _torch():
+    global _torch_mod
+    if _torch_mod is None:
+        import torch
+        _torch_mod = torch
+    return _torch_mod
 
 
 AMR_MARK_LAUNCHES = 10   # kernels sfxm_refine_mark issues (csrc/sfxm_amr.cu)

@@ -15,12 +15,17 @@
 
 namespace sfxm {
 
-__global__ void newton_begin_kernel(int64_t batch, const int32_t *__restrict__ parent, const double *__restrict__ crit,
-                                    const int64_t *__restrict__ it, double maxiter, const double *__restrict__ dt,
+__global__ void newton_begin_kernel(int64_t batch, const int32_t *__restrict__ parent, double *__restrict__ crit,
+                                    int64_t *__restrict__ it, double maxiter, double *__restrict__ dt, double dt0, int reset,
                                     int32_t *__restrict__ run, double *__restrict__ shift, int32_t *__restrict__ any_flag) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool r = false;
   if (m < batch) {
+    if (reset) {                                         // first iteration of a loop: fresh counters, no fill launches
+      crit[m] = INFINITY;
+      it[m] = 0;
+      if (dt) dt[m] = dt0;
+    }
     r = (parent == nullptr || parent[m] != 0) && crit[m] >= 1.0 && (double)it[m] < maxiter;
     run[m] = r ? 1 : 0;
     if (shift) shift[m] = -1.0 / dt[m];
@@ -54,12 +59,13 @@ __global__ void newton_end_kernel(int64_t batch, const int32_t *__restrict__ run
 
 using namespace sfxm;
 
-extern "C" int sfxm_newton_begin(int64_t batch, const int32_t *parent, const double *crit, const int64_t *it, double maxiter,
-                                 const double *dt, int32_t *run, double *shift, int32_t *any_flag, void *stream) {
+extern "C" int sfxm_newton_begin(int64_t batch, const int32_t *parent, double *crit, int64_t *it, double maxiter, double *dt,
+                                 double dt0, int32_t reset, int32_t *run, double *shift, int32_t *any_flag, void *stream) {
   if (batch < 1 || !crit || !it || !run || !any_flag || (shift && !dt)) return set_error("sfxm_newton_begin: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(any_flag, 0, sizeof(int32_t), st);
-  newton_begin_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, st>>>(batch, parent, crit, it, maxiter, dt, run, shift, any_flag);
+  newton_begin_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, st>>>(batch, parent, crit, it, maxiter, dt, dt0, reset, run, shift,
+                                                                      any_flag);
   return check_launch("sfxm_newton_begin");
 }
 

@@ -5,6 +5,7 @@ Both front ends sit on it: ``Simulation`` (batch = 1, the reference's API) and `
 tiny per-member control vectors only; all arithmetic on the state is in csrc/*.cu.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -37,6 +38,9 @@ def flat_index_table(nx, nv, segs):
     return idx
 
 
+GEOM_TABLE_MIN_NX = int(os.environ.get("SFXM_GEOM_MIN_NX", "16384"))   # measurement switch; huge value = never
+
+
 class Engine:
     def __init__(self, model_id, scheme_id, nv, nbl, nbr, x_int, xmin, xmax, params, batch=1, device=None):
         if not torch.cuda.is_available():
@@ -47,6 +51,7 @@ class Engine:
         self.W = self.nbl + self.nbr + 1
         self.batch = int(batch)
         self.model_id, self.scheme_id = int(model_id), int(scheme_id)
+        self.decoupled = self.model_id == _lib.MODEL_AD        # one scalar equation per variable (ModelAD::kDecoupled)
         self.xmin, self.xmax = float(xmin), float(xmax)
         self.set_mesh(x_int)
         self.set_params(params)
@@ -113,8 +118,11 @@ class Engine:
             raise SFXM("boundary conditions not set")
         self._bc_filler(P)
         self._probs[key] = (P, segs)
-        if self.batch >= 32 and self._geom is None:
-            # mesh-only data shared by all members: computed once per mesh (the split layout does not enter)
+        if (self.batch >= 32 or (self.decoupled and self.nx >= GEOM_TABLE_MIN_NX)) and self._geom is None:
+            # mesh-only data shared by all members: computed once per mesh (the split layout does not enter).  One large
+            # mesh of a decoupled model (one thread per unknown) uses the table too: without it every thread derives the
+            # scheme's divisors and their reciprocals itself - four IEEE divisions, which made those kernels
+            # instruction-bound (0.041 ms for the 56 MB of a 1e6-cell residual)
             self._geom = torch.empty(10 * self.nx, dtype=torch.float64, device=self.device)
             _lib.check(self.lib.sfxm_geometry(ctypes.byref(P), _lib.ptr(self.x_int), _lib.ptr(self._geom), _lib.stream_ptr()))
             _lib.count()
@@ -308,7 +316,7 @@ class Engine:
         P, _ = self.problem(split, split_locs)
         nbytes = self.lib.sfxm_solve_workspace_bytes(ctypes.byref(P))
         work = self._scratch("solve", nbytes // 8)
-        out2 = torch.empty(2 * self.batch, dtype=torch.float64, device=self.device)
+        out2 = self._scratch("norms_step", 2 * self.batch)[:2 * self.batch]
         _lib.check(self.lib.sfxm_newton_step_fused(ctypes.byref(P), _lib.ptr(self.x_int), _lib.ptr(self.params),
                                                    self.param_stride, _lib.ptr(self._geom), _lib.ptr(y), float(eps),
                                                    _lib.ptr(shift), _lib.ptr(active), int(seg), _lib.ptr(s), _lib.ptr(r0),

@@ -67,7 +67,10 @@ class NewtonDriver:
         self._speculate = not hasattr(eng, "comm")
         if self._lib is not None:
             self._any = torch.zeros(1, dtype=torch.int32, device=dev)
-            self._any_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            # one pinned flag word + one event per loop level: an enclosing level's ticket stays valid while the loops
+            # inside it issue theirs
+            self._any_host = torch.zeros(4 * (len(self.segs) + 1), dtype=torch.int32).pin_memory()
+            self._states, self._reset, self._slots = {}, False, {}
             self._shift = torch.empty(B, dtype=torch.float64, device=dev) if dt0 > 0 else None
 
     def rows(self, k):
@@ -79,30 +82,45 @@ class NewtonDriver:
             raise ValueError("Initial guess is outside the bounds")
 
     # -- per-member bookkeeping --------------------------------------------------------------------------
-    def _new_state(self, with_dt):
-        """(it, crit, dt, run) of one loop level, all [batch]."""
+    def _new_state(self, with_dt, key):
+        """(it, crit, dt, run) of one loop level, all [batch].  On the device the buffers of a level are allocated once
+        and reset by the loop's first sfxm_newton_begin; a level's previous counts have been consumed by then (the
+        caller reads them only after the whole run)."""
         B, dev = self.eng.batch, self.eng.device
+        if self._lib is not None:
+            st = self._states.get(key)
+            if st is None:
+                st = (torch.zeros(B, dtype=torch.int64, device=dev), torch.empty(B, dtype=torch.float64, device=dev),
+                      torch.empty(B, dtype=torch.float64, device=dev) if with_dt else None,
+                      torch.zeros(B, dtype=torch.int32, device=dev))
+                self._states[key] = st
+            self._reset = True
+            return st
         it = torch.zeros(B, dtype=torch.int64, device=dev)
         crit = torch.full((B,), math.inf, dtype=torch.float64, device=dev)
         dt = torch.full((B,), self.dt0, dtype=torch.float64, device=dev) if with_dt else None
         run = torch.zeros(B, dtype=torch.int32, device=dev)
         return it, crit, dt, run
 
-    def _begin(self, parent, it, crit, dt, run, maxiter):
+    def _begin(self, parent, it, crit, dt, run, maxiter, key=None):
         """run <- parent & (crit >= 1) & (it < maxiter) (int32 mask, in place); -> (ticket for _peek / _wait, shift or
-        None).  On the device the "any member runs" flag travels to pinned host memory behind an event."""
+        None).  On the device the "any member runs" flag travels to the loop level's pinned word behind its event."""
         use_shift = dt is not None and self.dt0 > 0
         if self._lib is not None:
             from . import _lib
             shift = self._shift if use_shift else None
+            reset, self._reset = self._reset, False
             _lib.check(self._lib.sfxm_newton_begin(self.eng.batch, _lib.ptr(parent), _lib.ptr(crit), _lib.ptr(it),
-                                                   float(min(maxiter, 1e300)), _lib.ptr(dt) if use_shift else None, _lib.ptr(run),
-                                                   _lib.ptr(shift), _lib.ptr(self._any), _lib.stream_ptr()))
+                                                   float(min(maxiter, 1e300)), _lib.ptr(dt) if use_shift else None, self.dt0,
+                                                   1 if reset else 0, _lib.ptr(run), _lib.ptr(shift), _lib.ptr(self._any),
+                                                   _lib.stream_ptr()))
             _lib.count()
-            self._any_host.copy_(self._any, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
-            return ev, shift
+            slot = self._slots.get(key)
+            if slot is None:
+                slot = self._slots[key] = (len(self._slots), torch.cuda.Event())
+            self._any_host[slot[0]:slot[0] + 1].copy_(self._any, non_blocking=True)
+            slot[1].record()
+            return slot, shift
         r = (crit >= 1) & (it < maxiter)
         if parent is not None:
             r = r & (parent != 0)
@@ -115,13 +133,13 @@ class NewtonDriver:
             return ticket
         if not self._speculate:
             return self._wait(ticket)
-        return bool(int(self._any_host[0])) if ticket.query() else None
+        return bool(int(self._any_host[ticket[0]])) if ticket[1].query() else None
 
     def _wait(self, ticket):
         if isinstance(ticket, bool):
             return ticket
-        ticket.synchronize()
-        return bool(int(self._any_host[0]))
+        ticket[1].synchronize()
+        return bool(int(self._any_host[ticket[0]]))
 
     def _end(self, run, ss, yy, it, crit, dt=None, r_old_sq=None, r_new_sq=None, nsum=1, keep=None):
         """crit, it (and the pseudo time step) of the members that ran, in place.  ss, yy: [batch], or [nsum, batch] whose
@@ -158,10 +176,11 @@ class NewtonDriver:
         lo, hi = self.rows(k)
         B, dev = eng.batch, eng.device
         ptc = self.dt0 > 0
-        it, crit, dt, run32 = self._new_state(ptc)
+        level = ("seg", k, maxiter == 1)
+        it, crit, dt, run32 = self._new_state(ptc, level)
         need_rnorm = self.armijo or ptc
         while True:
-            ticket, shift = self._begin(parent, it, crit, dt, run32, maxiter)
+            ticket, shift = self._begin(parent, it, crit, dt, run32, maxiter, level)
             known = self._peek(ticket)
             if known is False:
                 break
@@ -235,9 +254,10 @@ class NewtonDriver:
             return self.newton_segment(y, k0, maxiter, parent)
         eng = self.eng
         lo, _ = self.rows(k0)
-        it, crit, _, run32 = self._new_state(False)
+        level = ("split", k0)
+        it, crit, _, run32 = self._new_state(False, level)
         while True:
-            ticket, _ = self._begin(parent, it, crit, None, run32, maxiter)
+            ticket, _ = self._begin(parent, it, crit, None, run32, maxiter, level)
             known = self._peek(ticket)
             if known is False:
                 break
@@ -253,5 +273,5 @@ class NewtonDriver:
         """In place on y [n, batch]; returns per-member iteration counts (int64 [batch])."""
         self.check_initial(y)
         if len(self.segs) == 1:
-            return self.newton_segment(y, 0, maxiter, None)
-        return self.split_newton(y, 0, maxiter, None)
+            return self.newton_segment(y, 0, maxiter, None).clone()
+        return self.split_newton(y, 0, maxiter, None).clone()
