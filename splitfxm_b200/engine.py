@@ -38,7 +38,10 @@ def flat_index_table(nx, nv, segs):
     return idx
 
 
-GEOM_TABLE_MIN_NX = int(os.environ.get("SFXM_GEOM_MIN_NX", "16384"))   # measurement switch; huge value = never
+# Measured on B200 (bench extras, nx = 1e6): with the table the one-mesh kernels are SLOWER (Jacobian 0.153 vs 0.139 ms,
+# residual 0.049 vs 0.041 ms - ten more doubles per cell to read), so it stays off for one mesh; SFXM_GEOM_MIN_NX=<nx>
+# switches it on from that mesh size for measurements.
+GEOM_TABLE_MIN_NX = int(os.environ.get("SFXM_GEOM_MIN_NX", str(1 << 62)))
 
 
 class Engine:
