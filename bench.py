@@ -482,13 +482,18 @@ def newton_leg(args, torch, dist, ens, Y_host, dev, world, total, barrier, peak)
     ens.steady_state(Y, split=SPLIT, split_locs=LOCS)             # warm the allocator (first call allocates ~2 GB)
     barrier()
     _lib.LAUNCHES[0] = 0
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(steps):
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    host_s = []
+    marks[0].record()
+    for k in range(steps):
+        h0 = time.perf_counter()
         Yf, its = ens.steady_state(Y, split=SPLIT, split_locs=LOCS)
-    t1.record()
+        host_s.append(time.perf_counter() - h0)
+        marks[k + 1].record()
+    t0, t1 = marks[0], marks[-1]
     barrier()
     launches = _lib.LAUNCHES[0]
+    per_step = [marks[k].elapsed_time(marks[k + 1]) for k in range(steps)]
     t = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -513,6 +518,7 @@ def newton_leg(args, torch, dist, ens, Y_host, dev, world, total, barrier, peak)
     # on the outer segment; fused algorithmic bytes per cell-member per sweep: s = 1 -> 48, s = 2 -> 128
     return {"metric": NEWTON_METRIC, "value": total / (ms * 1e-3), "unit": NEWTON_UNIT, "steps": steps, "ms_per_step": ms,
             "gpu_launches": launches, "iterations_min_max": [it_lo, it_hi], "max_abs_residual": res,
+            "per_step_ms_rank0": [round(v, 3) for v in per_step], "host_ms_per_call_rank0": [round(1e3 * v, 3) for v in host_s],
             "e2e": {"value": total / (ms_e * 1e-3), "unit": NEWTON_UNIT, "ms_per_step": ms_e,
                     "h2d_bytes_per_step": int(Y_host.numel() * 8), "d2h_bytes_per_step": int(out_host.numel() * 8 + B * 8),
                     "api": "EnsembleSimulation.steady_state_host(pinned host states -> pinned host steady states + "

@@ -73,7 +73,7 @@ if "newton_mesh" in ops or "residual_mesh" in ops or "jacobian_mesh" in ops:
 if "amr" in ops or "euler_sod" in ops or "rk45_sod" in ops:
     comps = ["rho", "rhou", "E"]
     nbc = {c: {"left": {"neumann": 0.0}, "right": {"neumann": 0.0}} for c in comps}
-    nx = 1_000_000
+    nx = int(os.environ.get("PROF_NX", "1000000"))
     d = sf.Domain.from_size(nx, 1, 1, comps)
     xs = d.interior_x()
     U = d.interior_U()
