@@ -207,6 +207,25 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+class quiet_host:
+    """Timed regions run with Python's cyclic garbage collector off (as `timeit` does): a generation-2 collection of an
+    interpreter that has imported torch + scipy pauses the host for tens of milliseconds, which showed up as 5.9 / 7.7 /
+    27 ms outliers among 4.4 ms Newton steps (the legs whose kernels are launched step by step from Python)."""
+
+    def __enter__(self):
+        import gc
+        gc.collect()
+        self.was = gc.isenabled()
+        gc.disable()
+        return self
+
+    def __exit__(self, *exc):
+        import gc
+        if self.was:
+            gc.enable()
+        return False
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------------
@@ -322,11 +341,12 @@ def run_gpu(args):
         sampler.start()
     _lib.LAUNCHES[0] = 0
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    ev[0].record()
-    for k in range(args.steps):
-        eng.jacobian(Y, SPLIT, LOCS, J=J)
-        ev[k + 1].record()
-    barrier()
+    with quiet_host():
+        ev[0].record()
+        for k in range(args.steps):
+            eng.jacobian(Y, SPLIT, LOCS, J=J)
+            ev[k + 1].record()
+        barrier()
     launches = _lib.LAUNCHES[0]
     if sampler:
         sampler.stop_flag.set()
@@ -388,14 +408,15 @@ def run_gpu(args):
         ens.jacobian_host(Y_host, Jh[k], SPLIT, LOCS, slot=k)
     ens.sync_host()
     barrier()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for k in range(e2e_steps):
-        ens.jacobian_host(Y_host, Jh[k % 2], SPLIT, LOCS, slot=k % 2)
-    ens.sync_host()
-    t1 = torch.cuda.Event(enable_timing=True)
-    t1.record()
-    barrier()
+    with quiet_host():
+        t0 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for k in range(e2e_steps):
+            ens.jacobian_host(Y_host, Jh[k % 2], SPLIT, LOCS, slot=k % 2)
+        ens.sync_host()
+        t1 = torch.cuda.Event(enable_timing=True)
+        t1.record()
+        barrier()
     torch.cuda.synchronize()
     te = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)   # t1 is recorded after both streams drained
     if world > 1:
@@ -484,14 +505,15 @@ def newton_leg(args, torch, dist, ens, Y_host, dev, world, total, barrier, peak)
     _lib.LAUNCHES[0] = 0
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     host_s = []
-    marks[0].record()
-    for k in range(steps):
-        h0 = time.perf_counter()
-        Yf, its = ens.steady_state(Y, split=SPLIT, split_locs=LOCS)
-        host_s.append(time.perf_counter() - h0)
-        marks[k + 1].record()
-    t0, t1 = marks[0], marks[-1]
-    barrier()
+    with quiet_host():
+        marks[0].record()
+        for k in range(steps):
+            h0 = time.perf_counter()
+            Yf, its = ens.steady_state(Y, split=SPLIT, split_locs=LOCS)
+            host_s.append(time.perf_counter() - h0)
+            marks[k + 1].record()
+        t0, t1 = marks[0], marks[-1]
+        barrier()
     launches = _lib.LAUNCHES[0]
     per_step = [marks[k].elapsed_time(marks[k + 1]) for k in range(steps)]
     t = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
@@ -505,11 +527,12 @@ def newton_leg(args, torch, dist, ens, Y_host, dev, world, total, barrier, peak)
     ens.steady_state_host(Y_host, out_host, its_host, SPLIT, LOCS)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        ens.steady_state_host(Y_host, out_host, its_host, SPLIT, LOCS)
-    e1.record()
-    barrier()
+    with quiet_host():
+        e0.record()
+        for _ in range(steps):
+            ens.steady_state_host(Y_host, out_host, its_host, SPLIT, LOCS)
+        e1.record()
+        barrier()
     te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)

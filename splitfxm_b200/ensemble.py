@@ -115,7 +115,13 @@ class EnsembleSimulation:
                      maxiter=math.inf):
         """-> (Y_final [n, batch] device tensor, iterations int64[batch])."""
         y = self._state(Y).clone()
-        drv = NewtonDriver(self.eng, split, split_locs, dt0, dtmax, armijo, bounds)
+        # the driver (work vectors, per-level counters, events) is kept between calls with the same options
+        key = (bool(split), tuple(split_locs) if split_locs else None, float(dt0), float(dtmax), bool(armijo))
+        drv = getattr(self, "_driver", None)
+        if bounds is not None or drv is None or self._driver_key != key:
+            drv = NewtonDriver(self.eng, split, split_locs, dt0, dtmax, armijo, bounds)
+            if bounds is None:
+                self._driver, self._driver_key = drv, key
         its = drv.run(y, maxiter)
         return y, its
 
