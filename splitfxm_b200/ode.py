@@ -189,3 +189,71 @@ class RK45Stepper:
             self.last_rhs_state = y
             self.K[0].copy_(self.K[6])      # FSAL: f_new becomes f of the next step
         return result
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Implicit BDF: scipy's variable-order step control, the linear algebra on the device
+# ---------------------------------------------------------------------------------------------------------------------
+class _DeviceJacobian:
+    """Stands for the constant Jacobian at y0 (simulation.py:441-443) inside scipy's BDF: `I - c * J` evaluates to a
+    token that remembers c, nothing is formed on the host."""
+
+    def __rmul__(self, c):
+        return _ScaledJacobian(float(c))
+
+    __mul__ = __rmul__
+
+
+class _ScaledJacobian:
+    def __init__(self, c):
+        self.c = c
+
+    def __rsub__(self, other):
+        return _ShiftedSystem(self.c)
+
+
+class _ShiftedSystem:       # I - c J
+    def __init__(self, c):
+        self.c = c
+
+
+class _Identity:
+    def __sub__(self, other):
+        return other.__rsub__(self)
+
+
+def device_bdf(eng, y0_dev, split, split_locs, eps=1e-8):
+    """-> a scipy.integrate.BDF subclass for solve_ivp(method=...) whose Newton systems (I - c J) d = b are solved by the
+    block-tridiagonal kernels (sfxm_block_tridiag_solve[_pcr]) on the banded finite-difference Jacobian assembled once at
+    y0 on the device.  The reference passes that constant Jacobian to scipy (simulation.py:441-443, 468-469), which
+    factorises I - c J with SuperLU on the host; here only the right-hand sides and solutions (n doubles) cross PCIe.
+    (I - c J) d = b  <=>  (J - I / c) d = -(b / c): the solver's shifted form with shift = -1 / c, f = b / c.
+    In split mode the reference's Jacobian is block-diagonal over the segments (simulation.py:373-392), so the system
+    decouples into the per-segment solves the kernel does anyway."""
+    from scipy.integrate import BDF
+    Jb = eng.jacobian(y0_dev, split, split_locs, eps).clone()
+    shift = torch.empty(1, dtype=torch.float64, device=eng.device)
+    status = torch.zeros(1, dtype=torch.int32, device=eng.device)
+    sol = torch.zeros((eng.n, 1), dtype=torch.float64, device=eng.device)
+
+    def lu(A):
+        if not isinstance(A, _ShiftedSystem):
+            raise SFXM("device BDF: unexpected linear system")
+        return A
+
+    def solve_lu(LU, b):
+        f = eng.to_device(np.ascontiguousarray(b, dtype=np.float64) / LU.c)
+        shift.fill_(-1.0 / LU.c)
+        eng.solve(Jb, f, sol, split, split_locs, shift=shift, status=status)
+        return sol.cpu().numpy().reshape(-1)
+
+    class DeviceBDF(BDF):
+        def __init__(self, fun, t0, y0, t_bound, **kw):
+            super().__init__(fun, t0, y0, t_bound, **kw)
+            self.J = _DeviceJacobian()
+            self.I = _Identity()
+            self.lu = lu
+            self.solve_lu = solve_lu
+            self.LU = None
+
+    return DeviceBDF

@@ -251,11 +251,18 @@ class Simulation:
                 return eng.residual(yd, None, split, split_locs).cpu().numpy().reshape(-1)
 
             jac = None
-            if method in JAC_REQUIRED:
+            solver = method
+            if method == "BDF" and eng.W == 3:
+                # scipy's step control as in the reference; the Newton systems (I - c J) d = b on the device (ode.device_bdf)
+                from scipy.sparse import identity
+                from .ode import device_bdf
+                solver = device_bdf(eng, y, split, split_locs)
+                jac = identity(y0.shape[0], format="csc")      # placeholder of the right shape: replaced by the device J
+            elif method in JAC_REQUIRED:
                 jac = self.jacobian(y0, split, split_locs)
                 eng = self._engine()
             events = create_bound_events(y0, ext_bounds)
-            sol = solve_ivp(f, (0, t_diff), y0, method=method, t_eval=[t_diff], jac=jac, max_step=max_step, events=events)
+            sol = solve_ivp(f, (0, t_diff), y0, method=solver, t_eval=[t_diff], jac=jac, max_step=max_step, events=events)
             y = eng.to_device(np.ascontiguousarray(sol.y.reshape(-1)))
             ghost_state = last.get("y")
         self._store(eng, y, split, split_locs, ghost_state)

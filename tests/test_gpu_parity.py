@@ -75,8 +75,14 @@ def test_evolve_matches_reference(name):
     s, d, m = product_simulation(z, z["x_init"], z["U_init"])
     s.evolve(float(z["t"]), m["split"], m["locs"], method=str(z["ode_method"]), max_step=float(z["max_step"]))
     assert np.array_equal(np.array(d.positions()), z["x_all"])
-    tol = 0.0 if str(z["ode_method"]) == "Euler" else 1e-13   # RK stage sums: BLAS dgemv order in scipy
-    assert rel_err(d.values(), z["U_all"]) <= tol
+    # Euler: bit-exact.  RK stage sums: BLAS dgemv order in scipy -> 1e-13.  BDF: scipy's step control on the host, every
+    # Newton system (I - c J) d = b solved by the block-tridiagonal kernels instead of SuperLU (ode.device_bdf) -> the
+    # linear solves round differently; north_star's 1e-10.
+    method = str(z["ode_method"])
+    tol = 0.0 if method == "Euler" else (1e-10 if method == "BDF" else 1e-13)
+    err = rel_err(d.values(), z["U_all"])
+    print(name, method, "rel err", err)
+    assert err <= tol
 
 
 @pytest.mark.parametrize("name", ["sod_cons_nx100_t0p05", "sod_cons_nx60_unsplit_t0p02", "sod_prim_nx60_t0p02"])
