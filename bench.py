@@ -500,8 +500,9 @@ def newton_leg(args, torch, dist, ens, Y_host, dev, world, total, barrier, peak)
     B = eng.batch
     Y = Y_host.to(dev)
     steps = max(1, min(args.steps, args.newton_steps))
-    ens.steady_state(Y, split=SPLIT, split_locs=LOCS)             # warm the allocator (first call allocates ~2 GB)
-    barrier()
+    for _ in range(3):       # warm-up with the timed loop's own assignment pattern: the caching allocator reaches its steady
+        Yf, its = ens.steady_state(Y, split=SPLIT, split_locs=LOCS)      # state (a first-time cudaMalloc of a 393 MB state
+    barrier()                                                            # block showed up as one 31 ms step among 4.3 ms ones)
     _lib.LAUNCHES[0] = 0
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     host_s = []
@@ -524,7 +525,8 @@ def newton_leg(args, torch, dist, ens, Y_host, dev, world, total, barrier, peak)
     it_lo, it_hi = int(its.min()), int(its.max())
     out_host = torch.empty((eng.n, B), dtype=torch.float64).pin_memory()
     its_host = torch.empty(B, dtype=torch.int64).pin_memory()
-    ens.steady_state_host(Y_host, out_host, its_host, SPLIT, LOCS)
+    for _ in range(2):
+        ens.steady_state_host(Y_host, out_host, its_host, SPLIT, LOCS)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with quiet_host():
