@@ -593,7 +593,11 @@ jacobian_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restri
 // RESTRICT: only the columns of the requested segments are evaluated (sfxm_jacobian_segments).  A separate
 // instantiation, because the per-column branch ends the straight-line code in which the compiler interleaves the
 // independent column evaluations (measured: 0.57 -> 0.70 ms when the unrestricted kernel carried the test).
-template <class Model, int SCHEME, int NV, int W, bool RESTRICT>
+// BULK (decoupled models, full 64-member tiles): the W * NV stored rows of the block row - 512 contiguous bytes each in
+// the member-fastest layout - are staged in shared memory and handed to the copy engine by one lane
+// (cp.async.bulk.global.shared::cta, SASS UBLKCP) instead of NV * W 16-byte STG per lane: ncu r1j showed the l1tex -> xbar
+// store path as the busiest unit after the FP64 pipe.
+template <class Model, int SCHEME, int NV, int W, bool RESTRICT, bool BULK = false>
 __global__ void __launch_bounds__(32, SFXM_PAIR_MIN_CTAS)
 jacobian_pair_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restrict__ x_int,
                      const double *__restrict__ params, int64_t param_stride, const double *__restrict__ y,
@@ -658,6 +662,8 @@ jacobian_pair_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
     for (int j = 0; j < NV; ++j) *reinterpret_cast<double2 *>(r0_out + off[j]) = make_double2(r0[0][j], r0[1][j]);
   }
   double *p = J + (i * W) * (int64_t)(NV * NV) * B + m0;
+  __shared__ __align__(128) double2 stage[BULK ? W * NV : 1][32];
+  const bool bulk = BULK && (int64_t)(blockIdx.x + 1) * 64 <= B;      // a full tile of 64 members (warp-uniform)
 #pragma unroll
   for (int d = 0; d < W; ++d) {
     double cols[2][NV][NV];   // [member][c][r]
@@ -674,6 +680,13 @@ jacobian_pair_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
         upc[d] = u[v][d][c] + eps;                          // simulation.py:337
         jac_column<Model, SCHEME, NV, W, true>(prm[v], u[v], upc, c, geom, r0[v], eps, reps, cols[v][c]);
       }
+    if constexpr (BULK) {
+      if (bulk) {
+#pragma unroll
+        for (int c = 0; c < NV; ++c) stage[d * NV + c][threadIdx.x] = make_double2(cols[0][c][c], cols[1][c][c]);
+        continue;
+      }
+    }
 #pragma unroll
     for (int r = 0; r < NV; ++r)
 #pragma unroll
@@ -682,6 +695,23 @@ jacobian_pair_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
           *reinterpret_cast<double2 *>(p) = make_double2(cols[0][c][r], cols[1][c][r]);
         p += B;
       }
+  }
+  if constexpr (BULK) {
+    if (bulk) {
+      bulk_fence_smem();
+      __syncwarp();
+      if (threadIdx.x == 0) {
+        double *row0 = J + (i * W) * (int64_t)(NV * NV) * B + (int64_t)blockIdx.x * 64;
+#pragma unroll
+        for (int d = 0; d < W; ++d)
+#pragma unroll
+          for (int c = 0; c < NV; ++c)
+            if (entry_mask & (1u << (c * NV + c)))
+              bulk_store(row0 + ((int64_t)(d * NV + c) * NV + c) * B, &stage[d * NV + c][0], 512u);
+        bulk_commit();
+        bulk_wait_read();
+      }
+    }
   }
 }
 
@@ -855,6 +885,14 @@ static bool pair_enabled() {
   }
   return v != 0;
 }
+static bool jac_bulk_enabled() {        // bulk (TMA) stores of the Jacobian block rows, see jacobian_pair_kernel
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SFXM_JAC_BULK");
+    v = e ? atoi(e) : 0;
+  }
+  return v != 0;
+}
 static bool residual_ring_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -972,7 +1010,10 @@ static int launch_t(const Launch &L) {
     if (g.z > 65535) return set_error("mesh too large for one launch");
     if (restricted)
       jacobian_pair_kernel<Model, SCHEME, NV, W, true><<<g, dim3(32, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.scalar, L.out0, L.out1, mask, L.geom);
-    else
+    else if (Model::kDecoupled && W == 3 && jac_bulk_enabled() && (reinterpret_cast<uintptr_t>(L.out0) & 15) == 0) {
+      if constexpr (Model::kDecoupled && W == 3)
+        jacobian_pair_kernel<Model, SCHEME, NV, W, false, true><<<g, dim3(32, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.scalar, L.out0, L.out1, mask, L.geom);
+    } else
       jacobian_pair_kernel<Model, SCHEME, NV, W, false><<<g, dim3(32, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.scalar, L.out0, L.out1, mask, L.geom);
   } else {
     dim3 g = grid_for(P.batch, P.nx, b);
