@@ -7,13 +7,21 @@ nx = 250, 3-variable advection-diffusion problem (benchmark/test_jac_benchmark.p
 One step = one assembly of every member's block-banded Jacobian (one kernel launch).
 
   value      assemblies/s, inputs resident in HBM, CUDA-event time, max over ranks
-  e2e        same metric through EnsembleSimulation.jacobian with HOST buffers (pinned H2D of the states and
-             D2H of the banded Jacobians inside the timed region)
-  roofline   the Jacobian kernel's algorithmic bytes / its CUDA-event duration vs the measured HBM peak
-  cpu_baseline  oracle port (NumPy, 1 core) on a bounded sample of the same members
+  e2e        same metric through EnsembleSimulation.jacobian_host with HOST buffers (pinned H2D of the states and
+             D2H of the banded Jacobians inside the timed region); e2e.pcie_probe: what the host link gives when all
+             ranks copy at once
+  roofline   the Jacobian kernel: bytes actually moved / its CUDA-event duration vs the measured HBM peak (`frac`),
+             the SURVEY 8(d) figure beside it, and the fraction of the FP64 pipe, which is the nearer bound
+  newton     BASELINE metric, second half: Split-Newton steady states/s of the same ensemble, on every rank
+             (value device-resident, e2e through host buffers)
+  slab       N > 1 only: BASELINE config 5 (one conservative Sod mesh of 1e7 cells slab-decomposed over the ranks,
+             halo exchange fused into the update kernel vs NCCL) and Newton on slabs - the collective paths
+  cpu_baseline  the UNMODIFIED reference (baseline/_ref) on ONE host core, bounded sample of the same members
+                (kind "reference"; the oracle port only if baseline/_ref is not installed)
+  extra      secondary rooflines (ensemble residual / solves, one-mesh kernels, AMR, RK45) - rank 0 only
 
-`--impl reference` times the reference's CPU algorithm (oracle port - the reference is Python and cannot
-travel to the GPU box) on all host cores.
+`--impl reference` times the unmodified reference's own `Simulation.jacobian` / `Simulation.steady_state` on all host
+cores (one member per core and step), same `config`, `metric`, `unit`.  Timed regions run with the cyclic GC off.
 """
 import argparse
 import json
@@ -476,10 +484,11 @@ def run_gpu(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": value / (1.0 / 0.6), "dtype": "f64", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": bench_config(B, world),
-                "vs_baseline_note": "BASELINE.md published sparse Jacobian ~0.6 s per assembly at N=250 (README.md:100-105, "
-                                    "hardware unstated)",
+                "vs_baseline_note": "BASELINE.json publishes nothing for this metric (published = {}); the reference's README "
+                                    "quotes ~0.6 s per sparse assembly at N=250 on unstated hardware (README.md:100-105), i.e. "
+                                    "%.3g x that figure - not a like-for-like baseline, hence null" % (value * 0.6),
                 "gpu_launches": launches, "roofline": roofline, "e2e": e2e, "newton": newton, "slab": slab,
                 "cpu_baseline": cpu_baseline(args.cpu_sample, args.cpu_newton_sample, total),
                 "clocks": sampler.summary() if sampler else None, "extra": extra}
@@ -800,6 +809,33 @@ def extras(torch, sf, ens, Y, dev, peak):
                                   "SURVEY 8(d): ~96 B per cell over both passes (1e6 cells = 96 MB: launch-latency-bound)"))
         out.setdefault("amr", []).append({"nx": nx, "device_pass_ms": ms_amr, "GBps": nx * 96 / ms_amr / 1e6,
                                           "cells_after": int(counts[0]), "refine_api_s": t_api})
+    # BASELINE config 3 in small: conservative Sod + AMR, the mesh growing from 60,000 cells past 1e5 (examples/sod_amr.py
+    # runs the full recipe), every call through the reference-shaped API, the Domain staying on the device in between
+    d = sf.Domain.from_size(60000, 1, 1, comps)
+    xs = d.interior_x()
+    d.interior_U()[:, 0] = np.where(xs < 0.5, 1.0, 0.125)
+    d.interior_U()[:, 2] = np.where(xs < 0.5, 2.5, 0.25)
+    sim = sf.Simulation(d, Euler1DConservative(1.4, "FVM"), {}, nbc, sf.FVSchemes.LAX_FRIEDRICHS)
+    sim._r.set_criteria(2.0, 2e-5, 2e-5, -0.001)
+    sim._r.set_max_points(400000)
+    sim.evolve(2.0e-4, split=True, split_locs=[1])
+    torch.cuda.synchronize()
+    cells, stale = [d._nx], []
+    before = _lib_mod.LAUNCHES[0]
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        for _ in range(6):
+            sim._r.refine(d)
+            cells.append(d._nx)
+            sim.evolve(1.0e-5, split=True, split_locs=[1])
+            stale.append(not d._host_ok)
+            if d._nx >= 100000:
+                break
+    torch.cuda.synchronize()
+    t_c3 = time.perf_counter() - t0
+    out["sod_amr_config3"] = {"cells": cells, "seconds": t_c3, "launches": _lib_mod.LAUNCHES[0] - before,
+                              "domain_stayed_on_device": bool(all(stale)), "finite": bool(np.isfinite(d.values()).all())}
+
     d = sf.Domain.from_size(100000, 1, 1, comps)
     xs = d.interior_x()
     d.interior_U()[:, 0] = np.where(xs < 0.5, 1.0, 0.125)

@@ -18,17 +18,4 @@ __device__ __forceinline__ void cp_async16(double2 *smem, const double2 *gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
 }
 
-// ---- bulk asynchronous copies (TMA, sm_90+; SASS UBLKCP): shared -> global ---------------------------------------------
-// One elected thread hands a contiguous row staged in shared memory to the copy engine; the stores leave the SM without
-// occupying the load/store path that the warp's own STG instructions use.  `bytes` and both addresses must be multiples
-// of 16.  The generic-proxy writes that filled the row must be fenced into the async proxy first (bulk_fence_smem), and
-// the CTA may not exit - or reuse the row - before bulk_wait_read().
-__device__ __forceinline__ void bulk_fence_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bulk_store(void *gmem, const void *smem, unsigned bytes) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem), "r"(sa), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-
 }  // namespace sfxm

@@ -593,11 +593,7 @@ jacobian_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restri
 // RESTRICT: only the columns of the requested segments are evaluated (sfxm_jacobian_segments).  A separate
 // instantiation, because the per-column branch ends the straight-line code in which the compiler interleaves the
 // independent column evaluations (measured: 0.57 -> 0.70 ms when the unrestricted kernel carried the test).
-// BULK (decoupled models, full 64-member tiles): the W * NV stored rows of the block row - 512 contiguous bytes each in
-// the member-fastest layout - are staged in shared memory and handed to the copy engine by one lane
-// (cp.async.bulk.global.shared::cta, SASS UBLKCP) instead of NV * W 16-byte STG per lane: ncu r1j showed the l1tex -> xbar
-// store path as the busiest unit after the FP64 pipe.
-template <class Model, int SCHEME, int NV, int W, bool RESTRICT, bool BULK = false>
+template <class Model, int SCHEME, int NV, int W, bool RESTRICT>
 __global__ void __launch_bounds__(32, SFXM_PAIR_MIN_CTAS)
 jacobian_pair_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restrict__ x_int,
                      const double *__restrict__ params, int64_t param_stride, const double *__restrict__ y,
@@ -662,8 +658,6 @@ jacobian_pair_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
     for (int j = 0; j < NV; ++j) *reinterpret_cast<double2 *>(r0_out + off[j]) = make_double2(r0[0][j], r0[1][j]);
   }
   double *p = J + (i * W) * (int64_t)(NV * NV) * B + m0;
-  __shared__ __align__(128) double2 stage[BULK ? W * NV : 1][32];
-  const bool bulk = BULK && (int64_t)(blockIdx.x + 1) * 64 <= B;      // a full tile of 64 members (warp-uniform)
 #pragma unroll
   for (int d = 0; d < W; ++d) {
     double cols[2][NV][NV];   // [member][c][r]
@@ -680,13 +674,6 @@ jacobian_pair_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
         upc[d] = u[v][d][c] + eps;                          // simulation.py:337
         jac_column<Model, SCHEME, NV, W, true>(prm[v], u[v], upc, c, geom, r0[v], eps, reps, cols[v][c]);
       }
-    if constexpr (BULK) {
-      if (bulk) {
-#pragma unroll
-        for (int c = 0; c < NV; ++c) stage[d * NV + c][threadIdx.x] = make_double2(cols[0][c][c], cols[1][c][c]);
-        continue;
-      }
-    }
 #pragma unroll
     for (int r = 0; r < NV; ++r)
 #pragma unroll
@@ -696,25 +683,13 @@ jacobian_pair_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
         p += B;
       }
   }
-  if constexpr (BULK) {
-    if (bulk) {
-      bulk_fence_smem();
-      __syncwarp();
-      if (threadIdx.x == 0) {
-        double *row0 = J + (i * W) * (int64_t)(NV * NV) * B + (int64_t)blockIdx.x * 64;
-#pragma unroll
-        for (int d = 0; d < W; ++d)
-#pragma unroll
-          for (int c = 0; c < NV; ++c)
-            if (entry_mask & (1u << (c * NV + c)))
-              bulk_store(row0 + ((int64_t)(d * NV + c) * NV + c) * B, &stage[d * NV + c][0], 512u);
-        bulk_commit();
-        bulk_wait_read();
-      }
-    }
-  }
 }
 
+// (Round 2: TMA bulk stores - the W * NV stored 512-byte rows of a 64-member tile staged in shared memory and handed to
+// the copy engine by one lane, cp.async.bulk.global.shared::cta / SASS UBLKCP, instead of 16-byte STG per lane, because
+// ncu r1j showed the l1tex -> xbar store path as the busiest unit after the FP64 pipe: 0.543 ms against 0.506 ms on the
+// bench shape, both of two runs (gpurun_out r2q) - the staging, the proxy fence and the wait before the one-cell CTA
+// exits cost more than the store path gives back; removed.)
 // (The ring / sliding-window structure of residual_ring_kernel was tried here too - one warp walking 4-32 cells, the
 // entering cell's rows prefetched by cp.async: the loop around the unrolled perturbations spills 500-800 bytes at 128
 // registers (276 at 168) and runs at 0.73-0.77 ms against 0.50 ms for one cell per CTA; removed.  The assembly kernel is
@@ -885,14 +860,6 @@ static bool pair_enabled() {
   }
   return v != 0;
 }
-static bool jac_bulk_enabled() {        // bulk (TMA) stores of the Jacobian block rows, see jacobian_pair_kernel
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("SFXM_JAC_BULK");
-    v = e ? atoi(e) : 0;
-  }
-  return v != 0;
-}
 static bool residual_ring_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -1010,10 +977,7 @@ static int launch_t(const Launch &L) {
     if (g.z > 65535) return set_error("mesh too large for one launch");
     if (restricted)
       jacobian_pair_kernel<Model, SCHEME, NV, W, true><<<g, dim3(32, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.scalar, L.out0, L.out1, mask, L.geom);
-    else if (Model::kDecoupled && W == 3 && jac_bulk_enabled() && (reinterpret_cast<uintptr_t>(L.out0) & 15) == 0) {
-      if constexpr (Model::kDecoupled && W == 3)
-        jacobian_pair_kernel<Model, SCHEME, NV, W, false, true><<<g, dim3(32, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.scalar, L.out0, L.out1, mask, L.geom);
-    } else
+    else
       jacobian_pair_kernel<Model, SCHEME, NV, W, false><<<g, dim3(32, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.scalar, L.out0, L.out1, mask, L.geom);
   } else {
     dim3 g = grid_for(P.batch, P.nx, b);
