@@ -238,6 +238,25 @@ int sfxm_rk_error_sumsq(const double *K, int64_t stage_stride, const double *E_h
                         const double *y, const double *y_new, double atol, double rtol, int64_t n, int64_t batch,
                         double *out, double *work, void *stream);
 
+/* RK45 with scipy's step-size controller (rk.py:124-187) on the device: ONE attempted step is a fixed launch sequence -
+ * sfxm_rk45_begin, six x (sfxm_rk_lincomb_dev + sfxm_residual), sfxm_rk_error_sumsq_dev, sfxm_rk45_control,
+ * sfxm_rk45_commit - with no host decision inside, so it is captured once in a CUDA graph and replayed.
+ *   ctl[8]  doubles: t, h_abs, h (this attempt), t_new, t_bound, max_step, sqrt(n_global), -
+ *   flag[16] int32:  done, step_rejected, need_begin, accept, final, failed, nfev, accepted, attempts
+ * begin: clamps h_abs for a new step, fails on a step below 10 ulp(t), clips the step to t_bound.  control: error norm
+ * sqrt(err_sumsq) / ctl[6], accept (factor min(10, 0.9 err^-0.2), <= 1 after a rejection) or reject (max(0.2, ...)).
+ * commit (accepted steps only): the final step writes the dense-output end value to `result`; y <- y_new, K_0 <- K_last.
+ * After `done` every kernel of the sequence is a no-op (the right-hand sides still run, on scratch). */
+int sfxm_rk45_begin(double *ctl, int32_t *flag, void *stream);
+int sfxm_rk45_control(double *ctl, int32_t *flag, const double *err_sumsq, void *stream);
+int sfxm_rk_lincomb_dev(const double *y, const double *K, int64_t stage_stride, const double *coef_host, int32_t nstage,
+                        const double *ctl, const int32_t *flag, double *out, int64_t total, void *stream);
+int sfxm_rk_error_sumsq_dev(const double *K, int64_t stage_stride, const double *E_host, int32_t nstage, const double *ctl,
+                            const double *y, const double *y_new, double atol, double rtol, int64_t n, int64_t batch,
+                            double *out, double *work, void *stream);
+int sfxm_rk45_commit(double *y, const double *y_new, double *K, int64_t stage_stride, const double *P_host, int32_t nstage,
+                     const double *ctl, const int32_t *flag, double *result, int64_t total, void *stream);
+
 /* ---- adaptive mesh refinement (one mesh, batch = 1): Refiner.refine + perform_changes (refine.py:90-282).
  * x[n], U[n * nv] cell-major interior.  mark: reductions (min/max of values and slopes per variable,
  * refine.py:136-153), slope / curvature / grid-ratio / prune flags (:159-227), the adjacent-deletion rule (:231-233)

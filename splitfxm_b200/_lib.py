@@ -80,6 +80,12 @@ SIGNATURES = {
     "sfxm_scaled_diff_sumsq": (ctypes.c_int, [c_vp, c_vp, c_vp, c_f64, c_f64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "sfxm_rk_error_sumsq": (ctypes.c_int, [c_vp, c_i64, ctypes.POINTER(c_f64), c_i32, c_f64, c_vp, c_vp, c_f64, c_f64,
                                            c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "sfxm_rk45_begin": (ctypes.c_int, [c_vp, c_vp, c_vp]),
+    "sfxm_rk45_control": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "sfxm_rk_lincomb_dev": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_f64), c_i32, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "sfxm_rk_error_sumsq_dev": (ctypes.c_int, [c_vp, c_i64, ctypes.POINTER(c_f64), c_i32, c_vp, c_vp, c_vp, c_f64, c_f64,
+                                               c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "sfxm_rk45_commit": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_f64), c_i32, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "sfxm_refine_workspace_bytes": (c_i64, [c_i64]),
     "sfxm_refine_mark": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_f64, c_f64, c_f64, c_f64, c_f64, c_f64, c_vp, c_vp, c_vp]),
     "sfxm_refine_flags": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -12,6 +12,7 @@ norm).  Single-mesh control (batch members advance in lock-step only for Euler).
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -121,9 +122,93 @@ class RK45Stepper:
             h1 = (0.01 / max(d1, d2)) ** (1 / 5)
         return min(100 * h0, h1, interval_length, self.max_step)
 
+    # -- step-size control on the device, attempted steps replayed from a CUDA graph -------------------------------
+    def device_control_ok(self):
+        """The graph path needs the plain engine right-hand side (no slab halo exchange / collective norms inside an
+        attempt) and no per-step host callback (bound warnings)."""
+        return (self._rhs is None and self._on_step is None and self.eng.device.type == "cuda"
+                and os.environ.get("SFXM_RK45_DEVICE", "1")[:1] != "0")
+
+    def _attempt(self):
+        """ONE attempted step as a fixed launch sequence (csrc/sfxm_ode.cu): begin, six x (stage combination + RHS),
+        error norm, control, commit.  No host decision inside: this is what the CUDA graph holds."""
+        eng, lib = self.eng, self.eng.lib
+        st = _lib.stream_ptr()
+        ctl, flag = _lib.ptr(self._ctl), _lib.ptr(self._flag)
+        _lib.check(lib.sfxm_rk45_begin(ctl, flag, st))
+        for s in range(1, 6):
+            _lib.check(lib.sfxm_rk_lincomb_dev(_lib.ptr(self._y), _lib.ptr(self.K), self.total, _dptr(self.A[s]), s, ctl, flag,
+                                               _lib.ptr(self.ytmp), self.total, st))
+            eng.residual(self.ytmp, self.K[s], self.split, self.split_locs)
+        _lib.check(lib.sfxm_rk_lincomb_dev(_lib.ptr(self._y), _lib.ptr(self.K), self.total, _dptr(self.Bc), 6, ctl, flag,
+                                           _lib.ptr(self._ynew), self.total, st))
+        eng.residual(self._ynew, self.K[6], self.split, self.split_locs)
+        _lib.check(lib.sfxm_rk_error_sumsq_dev(_lib.ptr(self.K), self.total, _dptr(self.E), 7, ctl, _lib.ptr(self._y),
+                                               _lib.ptr(self._ynew), self.atol, self.rtol, eng.n, eng.batch,
+                                               _lib.ptr(self.out1), _lib.ptr(self.work), st))
+        _lib.check(lib.sfxm_rk45_control(ctl, flag, _lib.ptr(self.out1), st))
+        _lib.check(lib.sfxm_rk45_commit(_lib.ptr(self._y), _lib.ptr(self._ynew), _lib.ptr(self.K), self.total, _dptr(self.P), 7,
+                                        ctl, flag, _lib.ptr(self._result), self.total, st))
+        _lib.count(17)
+
+    def integrate_device(self, y, t_bound):
+        """integrate() with scipy's controller running on the device: the host computes the initial step (two norms),
+        uploads the control block and replays the captured attempt; it reads the flags back once per batch of attempts
+        (estimated from the remaining time and the current step), not once per step.  Attempts replayed after the end
+        are no-ops on the state.  Same step sequence as integrate() up to the last bits of err ** -0.2."""
+        eng = self.eng
+        if t_bound <= 0:
+            raise ValueError("t_diff must be positive")
+        dev = eng.device
+        if not hasattr(self, "_y"):
+            self._y = torch.empty((eng.n, eng.batch), dtype=torch.float64, device=dev)
+            self._ynew = torch.empty_like(self._y)
+            self._result = torch.empty_like(self._y)
+            self._ctl = torch.zeros(8, dtype=torch.float64, device=dev)
+            self._flag = torch.zeros(16, dtype=torch.int32, device=dev)
+            self._ctl_host = torch.zeros(8, dtype=torch.float64).pin_memory()
+            self._flag_host = torch.zeros(16, dtype=torch.int32).pin_memory()
+            self._graph = None
+        self._y.copy_(y)
+        self.f(self._y, self.K[0])
+        h_abs = self.select_initial_step(self._y, t_bound)
+        nfev0 = self.nfev
+        self._ctl_host[:] = torch.tensor([0.0, h_abs, 0.0, 0.0, float(t_bound), min(self.max_step, 1.7e308), self._n_global ** 0.5,
+                                          0.0], dtype=torch.float64)
+        self._flag_host.zero_()
+        self._flag_host[2] = 1                      # need_begin
+        self._ctl.copy_(self._ctl_host, non_blocking=True)
+        self._flag.copy_(self._flag_host, non_blocking=True)
+        if self._graph is None:
+            self._attempt()                         # first attempt eagerly (lazy module loading must not happen in capture)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._attempt()
+            self._graph = g
+            _lib.LAUNCHES[0] -= 17                  # the captured sequence was recorded, not launched
+        while True:
+            self._flag_host.copy_(self._flag, non_blocking=True)
+            self._ctl_host.copy_(self._ctl, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            if int(self._flag_host[0]):
+                break
+            t, h = float(self._ctl_host[0]), float(self._ctl_host[1])
+            todo = int(min(max(math.ceil((t_bound - t) / h) if h > 0 else 1, 1), 8))      # the step may still grow: few at a time
+            for _ in range(todo):
+                self._graph.replay()
+            _lib.count(17 * todo)
+        if int(self._flag_host[5]):
+            raise SFXM("Required step size is less than spacing between numbers.")
+        self.nfev = nfev0 + int(self._flag_host[6])
+        self.last_rhs_state = self._y
+        return self._result
+
     def integrate(self, y, t_bound):
         """Advance y (device [n, 1]) from t = 0 to t_bound; returns the dense-output end value like
         solve_ivp(..., t_eval=[t_bound]).y[:, 0]."""
+        if self.device_control_ok():
+            return self.integrate_device(y, t_bound)
         eng = self.eng
         if t_bound <= 0:
             raise ValueError("t_diff must be positive")

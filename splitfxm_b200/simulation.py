@@ -64,6 +64,7 @@ class Simulation:
             raise SFXM("Stencil size does not match boundary conditions")
         self._eng = None
         self._eng_key = self._eng_rev = self._bc_sig = None
+        self._rk = None
 
     # -- device engine -----------------------------------------------------------------------------------
     def _engine(self):
@@ -233,7 +234,16 @@ class Simulation:
 
                 def on_step(yd, t):
                     checker.report(yd, t)
-            stepper = RK45Stepper(eng, split, split_locs, 1e-3, 1e-6, max_step, on_step=on_step)
+            # the stepper (stage vectors, control block, captured CUDA graph of one attempted step) is kept while the
+            # engine, its boundary conditions and parameters stay what they were when the graph was captured
+            dev_m = self._s._model._device
+            key = (id(eng), self._eng_rev, self._bc_sig, tuple(dev_m.params), bool(split), tuple(split_locs) if split_locs else None,
+                   float(max_step)) if (bounds is None and self._bc_sig is not None) else None
+            stepper = self._rk[1] if (key is not None and self._rk is not None and self._rk[0] == key) else None
+            if stepper is None:
+                stepper = RK45Stepper(eng, split, split_locs, 1e-3, 1e-6, max_step, on_step=on_step)
+                self._rk = (key, stepper) if key is not None else None
+            stepper.nfev = 0
             y = stepper.integrate(y, t_diff)
             ghost_state = stepper.last_rhs_state
         else:
