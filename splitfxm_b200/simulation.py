@@ -65,6 +65,7 @@ class Simulation:
         self._eng = None
         self._eng_key = self._eng_rev = self._bc_sig = None
         self._rk = None
+        self._nd = None
 
     # -- device engine -----------------------------------------------------------------------------------
     def _engine(self):
@@ -287,7 +288,13 @@ class Simulation:
                               "Split locations must be between 0 and nv-1")
         eng = self._engine()
         y = self._state(eng, split, split_locs)
-        drv = NewtonDriver(eng, split, split_locs, dt0, dtmax, armijo, ext_bounds)
+        # the driver (work vectors, per-level counters, events) is kept while the engine and the options stay the same
+        key = (id(eng), self._eng_rev, bool(split), tuple(split_locs) if split_locs else None, float(dt0), float(dtmax),
+               bool(armijo)) if bounds is None else None
+        drv = self._nd[1] if (key is not None and self._nd is not None and self._nd[0] == key) else None
+        if drv is None:
+            drv = NewtonDriver(eng, split, split_locs, dt0, dtmax, armijo, ext_bounds)
+            self._nd = (key, drv) if key is not None else None
         maxiter = self._ss.get("maxiter", math.inf) if isinstance(self._ss, dict) else math.inf
         it = drv.run(y, maxiter)
         self._store(eng, y, split, split_locs)
