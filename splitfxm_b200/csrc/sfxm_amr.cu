@@ -515,6 +515,10 @@ __device__ __forceinline__ unsigned long long tile_lookback(const unsigned long 
   return acc;
 }
 
+// Cell <-> (warp, item, lane): warp w of tile T owns the 128 contiguous cells from T * 1024 + w * 128; its item k of
+// lane L is cell base + k * 32 + L, so every load and store of a warp instruction touches 32 consecutive cells (the first
+// version gave each thread 4 consecutive cells: 32-byte strides between lanes, 4x the sectors - ncu r2m 420 us at 1e7
+// cells).  The scans run in cell order: a warp scan per item, the carry of item k - 1 entering item k.
 template <int NV>
 __global__ void __launch_bounds__(kScanThreads)
 amr_scan_apply_kernel(const double *__restrict__ z, const double *__restrict__ U, int64_t n,
@@ -522,62 +526,60 @@ amr_scan_apply_kernel(const double *__restrict__ z, const double *__restrict__ U
                       uint8_t *__restrict__ keepf, TileDesc *__restrict__ desc, unsigned int *__restrict__ tile_counter,
                       double *__restrict__ z_out, double *__restrict__ U_out, int64_t *__restrict__ counts) {
   constexpr unsigned long long kMask = (1ull << 62) - 1;
+  constexpr int kWarps = kScanThreads / 32;
   __shared__ int s_tile;
-  __shared__ unsigned long long s_warp[kScanThreads / 32];
+  __shared__ unsigned long long s_warp[kWarps];
   __shared__ unsigned long long s_prefix;
   if (threadIdx.x == 0) s_tile = (int)atomicAdd(tile_counter, 1u);     // tiles start in index order: look-back cannot deadlock
   __syncthreads();
   const int tile = s_tile;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t t0 = (int64_t)tile * kScanTile + threadIdx.x * kScanItems;
+  const int64_t wbase = (int64_t)tile * kScanTile + (int64_t)w * (32 * kScanItems);
   bool del0[kScanItems], lc[kScanItems];
-  static_assert(kScanItems == 4, "the flags of a thread's items are one 32-bit word");
-  // the flag arrays are 256-byte aligned and padded (fused_layout), t0 is a multiple of 4: one word per array
-  uint32_t wv = 0, wk = 0, wl = 0;
-  if (t0 < n) {
-    wv = *reinterpret_cast<const uint32_t *>(visited + t0);
-    wk = *reinterpret_cast<const uint32_t *>(keep1 + t0);
-    wl = *reinterpret_cast<const uint32_t *>(loc + t0);
-  }
-  bool prev = t0 > 0 && t0 - 1 < n && visited[t0 - 1] && !keep1[t0 - 1];
-  // the cells the thread will copy or average, requested now: their latency hides behind the two look-backs
-  double zc[kScanItems + 1], Uc[kScanItems + 1][NV];
-#pragma unroll
-  for (int k = 0; k <= kScanItems; ++k) {
-    const int64_t t = t0 + k;
-    zc[k] = t < n ? __ldg(z + t) : 0.0;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) Uc[k][i] = t < n ? __ldg(U + t * NV + i) : 0.0;
-  }
-  long long run[kScanItems];                              // 1 + latest run start <= t inside the thread's items (0 = none)
-  long long running = 0;
+  double zc[kScanItems], Uc[kScanItems][NV];
+  // flags and cells of the thread's items (coalesced); the cells are needed only at the end - requested now, their
+  // latency hides behind the two look-backs
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
-    const int64_t t = t0 + k;
+    const int64_t t = wbase + k * 32 + lane;
     const bool in = t < n;
-    del0[k] = in && ((wv >> (8 * k)) & 0xffu) && !((wk >> (8 * k)) & 0xffu);
-    lc[k] = in && ((wl >> (8 * k)) & 0xffu) && t + 1 < n;
-    if (del0[k] && !prev) running = t + 1;
-    run[k] = running;
-    prev = del0[k];
-  }
-  // ---- scan 1: inclusive max of the run starts -----------------------------------------------------------------
-  unsigned long long incl = (unsigned long long)running;
+    del0[k] = in && visited[t] && !keep1[t];
+    lc[k] = in && loc[t] && t + 1 < n;
+    zc[k] = in ? __ldg(z + t) : 0.0;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned long long other = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o && other > incl) incl = other;
+    for (int i = 0; i < NV; ++i) Uc[k][i] = in ? __ldg(U + t * NV + i) : 0.0;
   }
-  if (lane == 31) s_warp[w] = incl;
-  __syncthreads();
-  unsigned long long before = 0;                          // max over the threads before this one, inside the tile
+  // ---- scan 1: inclusive max of (1 + run start) in cell order ---------------------------------------------------
+  unsigned long long run[kScanItems];          // inclusive over the warp's cells up to this one
+  unsigned long long carry = 0;
   {
-    const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, 1);
-    if (lane > 0) before = up;
-    for (int q = 0; q < w; ++q) before = s_warp[q] > before ? s_warp[q] : before;
+    bool last_prev = wbase > 0 && wbase - 1 < n && visited[wbase - 1] && !keep1[wbase - 1];    // cell before the warp's first
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      const int64_t t = wbase + k * 32 + lane;
+      const bool up = __shfl_up_sync(0xffffffffu, del0[k] ? 1 : 0, 1) != 0;
+      const bool prev = lane == 0 ? last_prev : up;
+      unsigned long long v = (del0[k] && !prev) ? (unsigned long long)(t + 1) : 0ull;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long other = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o && other > v) v = other;
+      }
+      if (carry > v) v = carry;
+      run[k] = v;
+      carry = __shfl_sync(0xffffffffu, v, 31);
+      last_prev = __shfl_sync(0xffffffffu, del0[k] ? 1 : 0, 31) != 0;
+    }
   }
-  unsigned long long agg = 0;
-  for (int q = 0; q < kScanThreads / 32; ++q) agg = s_warp[q] > agg ? s_warp[q] : agg;
+  if (lane == 31) s_warp[w] = carry;           // the warp's aggregate
+  __syncthreads();
+  unsigned long long before = 0, agg = 0;      // max over the warps before this one / over the tile
+#pragma unroll
+  for (int q = 0; q < kWarps; ++q) {
+    const unsigned long long v = s_warp[q];
+    if (q < w && v > before) before = v;
+    if (v > agg) agg = v;
+  }
   if (threadIdx.x == 0) {
     *reinterpret_cast<volatile unsigned long long *>(&desc[tile].run) = (tile == 0 ? (2ull << 62) : (1ull << 62)) | agg;
   }
@@ -597,29 +599,38 @@ amr_scan_apply_kernel(const double *__restrict__ z, const double *__restrict__ U
   const unsigned long long base_run = s_prefix > before ? s_prefix : before;
   // final keep flags (refine.py:231-233: inside a run of deletions every odd offset is kept) and the counts
   bool kp[kScanItems];
-  unsigned long long mine = 0;
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
-    const int64_t t = t0 + k;
-    const unsigned long long rs1 = (unsigned long long)run[k] > base_run ? (unsigned long long)run[k] : base_run;   // 1 + run start
+    const int64_t t = wbase + k * 32 + lane;
+    const unsigned long long rs1 = run[k] > base_run ? run[k] : base_run;               // 1 + run start
     const bool del = del0[k] && (((t - ((int64_t)rs1 - 1)) & 1) == 0);
     kp[k] = (t < n) && !del;
-    mine += (kp[k] ? (1ull << 31) : 0ull) + (lc[k] ? 1ull : 0ull);
   }
   __syncthreads();                                        // s_warp / s_prefix are reused
-  // ---- scan 2: exclusive sums of (kept, inserted) ---------------------------------------------------------------
-  unsigned long long isum = mine;
+  // ---- scan 2: exclusive sums of (kept << 31 | inserted) in cell order -------------------------------------------
+  unsigned long long pos[kScanItems];          // exclusive over the warp's cells before this one
+  unsigned long long wsum = 0;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned long long other = __shfl_up_sync(0xffffffffu, isum, o);
-    if (lane >= o) isum += other;
+  for (int k = 0; k < kScanItems; ++k) {
+    const unsigned long long mine = (kp[k] ? (1ull << 31) : 0ull) + (lc[k] ? 1ull : 0ull);
+    unsigned long long v = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long other = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += other;
+    }
+    pos[k] = wsum + v - mine;
+    wsum += __shfl_sync(0xffffffffu, v, 31);
   }
-  if (lane == 31) s_warp[w] = isum;
+  if (lane == 31) s_warp[w] = wsum;
   __syncthreads();
-  unsigned long long tbefore = isum - mine;
-  for (int q = 0; q < w; ++q) tbefore += s_warp[q];
-  unsigned long long tagg = 0;
-  for (int q = 0; q < kScanThreads / 32; ++q) tagg += s_warp[q];
+  unsigned long long tbefore = 0, tagg = 0;
+#pragma unroll
+  for (int q = 0; q < kWarps; ++q) {
+    const unsigned long long v = s_warp[q];
+    if (q < w) tbefore += v;
+    tagg += v;
+  }
   if (threadIdx.x == 0) {
     *reinterpret_cast<volatile unsigned long long *>(&desc[tile].cnt) = (tile == 0 ? (2ull << 62) : (1ull << 62)) | tagg;
   }
@@ -635,33 +646,33 @@ amr_scan_apply_kernel(const double *__restrict__ z, const double *__restrict__ U
     if (lane == 0) s_prefix = excl;
   }
   __syncthreads();
-  unsigned long long pos = s_prefix + tbefore;             // kept << 31 | inserted, before the thread's first item
+  const unsigned long long tile_pos = s_prefix + tbefore;
   // ---- write the new mesh --------------------------------------------------------------------------------------
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
-    const int64_t t = t0 + k;
-    if (t >= n) break;
+    const int64_t t = wbase + k * 32 + lane;
+    if (t >= n) continue;
     keepf[t] = kp[k] ? 1 : 0;
-    const int64_t kb = (int64_t)(pos >> 31), ib = (int64_t)(pos & ((1ull << 31) - 1));
+    const unsigned long long p = tile_pos + pos[k];
+    const int64_t kb = (int64_t)(p >> 31), ib = (int64_t)(p & ((1ull << 31) - 1));
     if (kp[k]) {
       const int64_t o = kb + ib;
       z_out[o] = zc[k];
 #pragma unroll
       for (int i = 0; i < NV; ++i) U_out[o * NV + i] = Uc[k][i];
     }
-    if (lc[k]) {
+    if (lc[k]) {                                           // the next cell was loaded by the neighbouring lane: L1 hit
       const int64_t o = kb + (kp[k] ? 1 : 0) + ib;
-      z_out[o] = 0.5 * (zc[k + 1] + zc[k]);                                               // refine.py:268
+      z_out[o] = 0.5 * (__ldg(z + t + 1) + zc[k]);                                        // refine.py:268
 #pragma unroll
-      for (int i = 0; i < NV; ++i) U_out[o * NV + i] = 0.5 * (Uc[k + 1][i] + Uc[k][i]);   // :269
+      for (int i = 0; i < NV; ++i) U_out[o * NV + i] = 0.5 * (__ldg(U + (t + 1) * NV + i) + Uc[k][i]);   // :269
     }
-    pos += (kp[k] ? (1ull << 31) : 0ull) + (lc[k] ? 1ull : 0ull);
-  }
-  if (t0 <= n - 1 && n - 1 < t0 + kScanItems) {            // the thread that owns the last cell reports the totals
-    const int64_t kept = (int64_t)(pos >> 31), ins = (int64_t)(pos & ((1ull << 31) - 1));
-    counts[0] = kept + ins;
-    counts[1] = ins;
-    counts[2] = n - kept;
+    if (t == n - 1) {                                      // the thread that owns the last cell reports the totals
+      const int64_t kept = kb + (kp[k] ? 1 : 0), ins = ib + (lc[k] ? 1 : 0);
+      counts[0] = kept + ins;
+      counts[1] = ins;
+      counts[2] = n - kept;
+    }
   }
 }
 
