@@ -1,8 +1,9 @@
 """Diagnostic (not a test): is the custom Burgers model bit-identical to the oracle's NumPy evaluation?"""
 import json, os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 from nonlinear_cases import CASES, oracle_case, oracle_solve, product_case
 from oracle import core
 out = {}

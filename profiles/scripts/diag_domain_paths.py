@@ -1,7 +1,7 @@
 """Diagnostic: where do the device-resident and the host-synced sequences diverge?"""
 import contextlib, io, os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import splitfxm_b200 as sf
 from splitfxm_b200.models.advection_diffusion import AdvectionDiffusion
 comps = ["u", "v", "w"]
