@@ -127,66 +127,101 @@ amr_mark_kernel(const double *__restrict__ z, const double *__restrict__ U, cons
                 const Stats *__restrict__ st, uint8_t *__restrict__ keep1, uint8_t *__restrict__ visited,
                 uint8_t *__restrict__ loc, int32_t *__restrict__ comp, uint8_t *__restrict__ gridpt,
                 const MarkConst *__restrict__ mc) {
-  // t: index into the window arrays; j: the global cell index every rule of refine.py is written in
+  // t: index into the window arrays; j: the global cell index every rule of refine.py is written in.
+  // A rule evaluated at cell j flags cells j-2 .. j+2.  The flags are collected in a per-thread word - five offset bits
+  // per array: keep1 bits 0-4, visited 5-9, loc 10-14, gridpt 15-19 - exchanged between the lanes of the warp, and every
+  // cell is then written ONCE per array by its own lane (a dozen scattered, mostly duplicate byte stores per cell
+  // before: ncu r2m 294 us at 1e7 cells); flags for cells of a neighbouring warp are stored directly.
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= wd.ne) return;
-  const int64_t j = wd.g0 + t, n = wd.ng;
+  const int64_t n = wd.ng;
+  const int64_t j = wd.g0 + t;
+  bool eval = t < wd.ne;
   // cells of the overlap whose own stencil leaves the window are someone else's to evaluate
 #pragma unroll
   for (int o = -2; o <= 2; ++o)
-    if (j + o >= 0 && j + o < n && (t + o < 0 || t + o >= wd.ne)) return;
-  if (j == 0 || j == n - 1) keep1[t] = 1;                              // refine.py:120-121
-  const bool own = t >= wd.own_lo && t < wd.own_hi;                    // only own cells report the component
-  const double zj = __ldg(z + t);
-  const double dzj = j + 1 < n ? __ldg(z + t + 1) - zj : 0.0;          // dz[j]
-  const double dzj1 = j + 2 < n ? __ldg(z + t + 2) - __ldg(z + t + 1) : 0.0;   // dz[j+1]
-  // reciprocals shared by the NV slopes of an interval (mc == nullptr: the window path, plain divisions)
-  const bool z0_ok = mc != nullptr && divisor_ok(dzj), z1_ok = mc != nullptr && divisor_ok(dzj1);
-  const double rz0 = 1.0 / dzj, rz1 = 1.0 / dzj1;
-  const double ulp_dz = div_shared(kUlp, dzj, rz0, z0_ok);                    // kUlp / dz[j], refine.py:188
+    if (j + o >= 0 && j + o < n && (t + o < 0 || t + o >= wd.ne)) eval = false;
+  uint32_t M = 0;
+  constexpr int K1 = 0, VIS = 5, LOC = 10, GP = 15;
+  auto flag = [&](int arr, int o) { M |= 1u << (arr + o + 2); };
+  if (eval) {
+    if (j == 0 || j == n - 1) flag(K1, 0);                             // refine.py:120-121
+    const bool own = t >= wd.own_lo && t < wd.own_hi;                  // only own cells report the component
+    const double zj = __ldg(z + t);
+    const double dzj = j + 1 < n ? __ldg(z + t + 1) - zj : 0.0;        // dz[j]
+    const double dzj1 = j + 2 < n ? __ldg(z + t + 2) - __ldg(z + t + 1) : 0.0;   // dz[j+1]
+    // reciprocals shared by the NV slopes of an interval (mc == nullptr: the window path, plain divisions)
+    const bool z0_ok = mc != nullptr && divisor_ok(dzj), z1_ok = mc != nullptr && divisor_ok(dzj1);
+    const double rz0 = 1.0 / dzj, rz1 = 1.0 / dzj1;
+    const double ulp_dz = div_shared(kUlp, dzj, rz0, z0_ok);                  // kUlp / dz[j], refine.py:188
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const double vmin = st->vmin[i], vmax = st->vmax[i], smin = st->smin[i], smax = st->smax[i];
-    const double aa = fmax(fabs(vmin), fabs(vmax));
-    const double ss = fmax(fabs(smin), fabs(smax));
-    const double v0 = __ldg(U + t * NV + i);
-    const double v1 = j + 1 < n ? __ldg(U + (t + 1) * NV + i) : 0.0;
-    // slope criterion on interval j (refine.py:159-173)
-    if (j + 1 < n && (vmax - vmin) > cr.min_range * aa) {
-      const double dmax = cr.slope * (vmax - vmin) + kUlp;
-      const double r = mc != nullptr ? div_shared(fabs(v1 - v0), dmax, mc->rdmax_slope[i], mc->ok[i] != 0) : fabs(v1 - v0) / dmax;
-      if (r > 1.0 && dzj >= 2 * cr.min_grid) { loc[t] = 1; if (own) comp[i] = 1; }
-      if (r >= cr.prune) { keep1[t] = 1; keep1[t + 1] = 1; }
-      else visited[t] = 1;
+    for (int i = 0; i < NV; ++i) {
+      const double vmin = st->vmin[i], vmax = st->vmax[i], smin = st->smin[i], smax = st->smax[i];
+      const double aa = fmax(fabs(vmin), fabs(vmax));
+      const double ss = fmax(fabs(smin), fabs(smax));
+      const double v0 = __ldg(U + t * NV + i);
+      const double v1 = j + 1 < n ? __ldg(U + (t + 1) * NV + i) : 0.0;
+      // slope criterion on interval j (refine.py:159-173)
+      if (j + 1 < n && (vmax - vmin) > cr.min_range * aa) {
+        const double dmax = cr.slope * (vmax - vmin) + kUlp;
+        const double r = mc != nullptr ? div_shared(fabs(v1 - v0), dmax, mc->rdmax_slope[i], mc->ok[i] != 0) : fabs(v1 - v0) / dmax;
+        if (r > 1.0 && dzj >= 2 * cr.min_grid) { flag(LOC, 0); if (own) comp[i] = 1; }
+        if (r >= cr.prune) { flag(K1, 0); flag(K1, 1); }
+        else flag(VIS, 0);
+      }
+      // curvature criterion on the pair of intervals (j, j+1) (refine.py:179-197)
+      if (j + 2 < n && (smax - smin) > cr.min_range * ss) {
+        const double v2 = __ldg(U + (t + 2) * NV + i);
+        const double s0 = div_shared(v1 - v0, dzj, rz0, z0_ok);
+        const double s1 = div_shared(v2 - v1, dzj1, rz1, z1_ok);
+        const double dmax = cr.curve * (smax - smin);
+        const double r = fabs(s1 - s0) / (dmax + ulp_dz);
+        if (r > 1.0 && dzj >= 2 * cr.min_grid && dzj1 >= 2 * cr.min_grid) { if (own) comp[i] = 1; flag(LOC, 0); flag(LOC, 1); }
+        if (r >= cr.prune) flag(K1, 1);
+        else flag(VIS, 1);
+      }
     }
-    // curvature criterion on the pair of intervals (j, j+1) (refine.py:179-197)
-    if (j + 2 < n && (smax - smin) > cr.min_range * ss) {
-      const double v2 = __ldg(U + (t + 2) * NV + i);
-      const double s0 = div_shared(v1 - v0, dzj, rz0, z0_ok);
-      const double s1 = div_shared(v2 - v1, dzj1, rz1, z1_ok);
-      const double dmax = cr.curve * (smax - smin);
-      const double r = fabs(s1 - s0) / (dmax + ulp_dz);
-      if (r > 1.0 && dzj >= 2 * cr.min_grid && dzj1 >= 2 * cr.min_grid) { if (own) comp[i] = 1; loc[t] = 1; loc[t + 1] = 1; }
-      if (r >= cr.prune) keep1[t + 1] = 1;
-      else visited[t + 1] = 1;
+    // grid-ratio rules (refine.py:200-227), j = 1 .. n-2
+    if (j >= 1 && j <= n - 2) {
+      const double dzm1 = zj - __ldg(z + t - 1);                       // dz[j-1]
+      if (dzj > cr.ratio * dzm1) {
+        flag(LOC, 0); flag(GP, 0);
+        flag(K1, -1); flag(K1, 0); flag(K1, 1);
+        if (j + 2 < n) flag(K1, 2);
+      }
+      if (dzj < dzm1 / cr.ratio) {
+        flag(LOC, -1); flag(GP, -1);
+        if (j >= 2) flag(K1, -2);
+        flag(K1, -1); flag(K1, 0); flag(K1, 1);
+      }
+      const double span = __ldg(z + t + 1) - __ldg(z + t - 1);
+      if (j > 1 && span > cr.ratio * (__ldg(z + t - 1) - __ldg(z + t - 2))) flag(K1, 0);
+      if (j < n - 2 && span > cr.ratio * dzj1) flag(K1, 0);
     }
   }
-  // grid-ratio rules (refine.py:200-227), j = 1 .. n-2
-  if (j >= 1 && j <= n - 2) {
-    const double dzm1 = zj - __ldg(z + t - 1);                         // dz[j-1]
-    if (dzj > cr.ratio * dzm1) {
-      loc[t] = 1; gridpt[t] = 1;
-      keep1[t - 1] = 1; keep1[t] = 1; keep1[t + 1] = 1;
-      if (j + 2 < n) keep1[t + 2] = 1;
+  // what the neighbouring lanes flagged for this lane's cell
+  const int lane = threadIdx.x & 31;
+  uint8_t *const arrays[4] = {keep1, visited, loc, gridpt};
+  uint32_t mine = 0;                                                    // bit a: array a of this cell is set
+#pragma unroll
+  for (int o = -2; o <= 2; ++o) {
+    // lane L - o flagged offset o  ->  this lane's cell
+    const uint32_t from = o == 0 ? M : (o > 0 ? __shfl_up_sync(0xffffffffu, M, o) : __shfl_down_sync(0xffffffffu, M, -o));
+    const bool valid = o == 0 || (o > 0 ? lane >= o : lane + (-o) <= 31);
+    if (valid) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) mine |= ((from >> (5 * a + o + 2)) & 1u) << a;
     }
-    if (dzj < dzm1 / cr.ratio) {
-      loc[t - 1] = 1; gridpt[t - 1] = 1;
-      if (j >= 2) keep1[t - 2] = 1;
-      keep1[t - 1] = 1; keep1[t] = 1; keep1[t + 1] = 1;
+    // a flag for a cell outside this warp's 32 cells is stored by the lane that raised it
+    if (o != 0 && (lane + o < 0 || lane + o > 31)) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        if ((M >> (5 * a + o + 2)) & 1u) arrays[a][t + o] = 1;
     }
-    const double span = __ldg(z + t + 1) - __ldg(z + t - 1);
-    if (j > 1 && span > cr.ratio * (__ldg(z + t - 1) - __ldg(z + t - 2))) keep1[t] = 1;
-    if (j < n - 2 && span > cr.ratio * dzj1) keep1[t] = 1;
+  }
+  if (t < wd.ne) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+      if ((mine >> a) & 1u) arrays[a][t] = 1;
   }
 }
 
@@ -520,7 +555,7 @@ __device__ __forceinline__ unsigned long long tile_lookback(const unsigned long 
 // version gave each thread 4 consecutive cells: 32-byte strides between lanes, 4x the sectors - ncu r2m 420 us at 1e7
 // cells).  The scans run in cell order: a warp scan per item, the carry of item k - 1 entering item k.
 template <int NV>
-__global__ void __launch_bounds__(kScanThreads)
+__global__ void __launch_bounds__(kScanThreads, 5)
 amr_scan_apply_kernel(const double *__restrict__ z, const double *__restrict__ U, int64_t n,
                       const uint8_t *__restrict__ keep1, const uint8_t *__restrict__ visited, const uint8_t *__restrict__ loc,
                       uint8_t *__restrict__ keepf, TileDesc *__restrict__ desc, unsigned int *__restrict__ tile_counter,
@@ -536,18 +571,15 @@ amr_scan_apply_kernel(const double *__restrict__ z, const double *__restrict__ U
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t wbase = (int64_t)tile * kScanTile + (int64_t)w * (32 * kScanItems);
   bool del0[kScanItems], lc[kScanItems];
-  double zc[kScanItems], Uc[kScanItems][NV];
-  // flags and cells of the thread's items (coalesced); the cells are needed only at the end - requested now, their
-  // latency hides behind the two look-backs
+  // flags of the thread's items (coalesced).  The kernel is a chain of dependent memory round trips per tile (flags ->
+  // look-back 1 -> look-back 2 -> cells -> stores): what hides them is resident tiles, so registers are capped for five
+  // CTAs per SM and the cells are loaded where they are used
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
     const int64_t t = wbase + k * 32 + lane;
     const bool in = t < n;
     del0[k] = in && visited[t] && !keep1[t];
     lc[k] = in && loc[t] && t + 1 < n;
-    zc[k] = in ? __ldg(z + t) : 0.0;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) Uc[k][i] = in ? __ldg(U + t * NV + i) : 0.0;
   }
   // ---- scan 1: inclusive max of (1 + run start) in cell order ---------------------------------------------------
   unsigned long long run[kScanItems];          // inclusive over the warp's cells up to this one
@@ -655,17 +687,22 @@ amr_scan_apply_kernel(const double *__restrict__ z, const double *__restrict__ U
     keepf[t] = kp[k] ? 1 : 0;
     const unsigned long long p = tile_pos + pos[k];
     const int64_t kb = (int64_t)(p >> 31), ib = (int64_t)(p & ((1ull << 31) - 1));
+    if (!kp[k] && !lc[k]) continue;
+    const double zc = __ldg(z + t);
+    double Uc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) Uc[i] = __ldg(U + t * NV + i);
     if (kp[k]) {
       const int64_t o = kb + ib;
-      z_out[o] = zc[k];
+      z_out[o] = zc;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) U_out[o * NV + i] = Uc[k][i];
+      for (int i = 0; i < NV; ++i) U_out[o * NV + i] = Uc[i];
     }
-    if (lc[k]) {                                           // the next cell was loaded by the neighbouring lane: L1 hit
+    if (lc[k]) {                                           // the next cell is loaded by the neighbouring lane too: L1 hit
       const int64_t o = kb + (kp[k] ? 1 : 0) + ib;
-      z_out[o] = 0.5 * (__ldg(z + t + 1) + zc[k]);                                        // refine.py:268
+      z_out[o] = 0.5 * (__ldg(z + t + 1) + zc);                                           // refine.py:268
 #pragma unroll
-      for (int i = 0; i < NV; ++i) U_out[o * NV + i] = 0.5 * (__ldg(U + (t + 1) * NV + i) + Uc[k][i]);   // :269
+      for (int i = 0; i < NV; ++i) U_out[o * NV + i] = 0.5 * (__ldg(U + (t + 1) * NV + i) + Uc[i]);      // :269
     }
     if (t == n - 1) {                                      // the thread that owns the last cell reports the totals
       const int64_t kept = kb + (kp[k] ? 1 : 0), ins = ib + (lc[k] ? 1 : 0);
