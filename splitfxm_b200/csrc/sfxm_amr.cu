@@ -119,6 +119,9 @@ struct Criteria {
   double ratio, slope, curve, prune, min_range, min_grid;
 };
 
+// (Round 2: collecting a thread's flags in a word, exchanging the words between the lanes of the warp and storing every
+// cell once per array instead of a dozen scattered, mostly duplicate byte stores was measured SLOWER - 343 us against
+// 296 us at 1e7 cells (gpurun_out r2t): the kernel is bound by its instruction stream, not by the stores; removed.)
 // flags: keep1[j] / visited[j] / loc[j] (bytes, zero-initialised), comp[i] = component i asked for a point,
 // gridpt[j] = the grid-ratio rule named "point j" (refine.py:203,211)
 template <int NV>
@@ -127,101 +130,66 @@ amr_mark_kernel(const double *__restrict__ z, const double *__restrict__ U, cons
                 const Stats *__restrict__ st, uint8_t *__restrict__ keep1, uint8_t *__restrict__ visited,
                 uint8_t *__restrict__ loc, int32_t *__restrict__ comp, uint8_t *__restrict__ gridpt,
                 const MarkConst *__restrict__ mc) {
-  // t: index into the window arrays; j: the global cell index every rule of refine.py is written in.
-  // A rule evaluated at cell j flags cells j-2 .. j+2.  The flags are collected in a per-thread word - five offset bits
-  // per array: keep1 bits 0-4, visited 5-9, loc 10-14, gridpt 15-19 - exchanged between the lanes of the warp, and every
-  // cell is then written ONCE per array by its own lane (a dozen scattered, mostly duplicate byte stores per cell
-  // before: ncu r2m 294 us at 1e7 cells); flags for cells of a neighbouring warp are stored directly.
+  // t: index into the window arrays; j: the global cell index every rule of refine.py is written in
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t n = wd.ng;
-  const int64_t j = wd.g0 + t;
-  bool eval = t < wd.ne;
+  if (t >= wd.ne) return;
+  const int64_t j = wd.g0 + t, n = wd.ng;
   // cells of the overlap whose own stencil leaves the window are someone else's to evaluate
 #pragma unroll
   for (int o = -2; o <= 2; ++o)
-    if (j + o >= 0 && j + o < n && (t + o < 0 || t + o >= wd.ne)) eval = false;
-  uint32_t M = 0;
-  constexpr int K1 = 0, VIS = 5, LOC = 10, GP = 15;
-  auto flag = [&](int arr, int o) { M |= 1u << (arr + o + 2); };
-  if (eval) {
-    if (j == 0 || j == n - 1) flag(K1, 0);                             // refine.py:120-121
-    const bool own = t >= wd.own_lo && t < wd.own_hi;                  // only own cells report the component
-    const double zj = __ldg(z + t);
-    const double dzj = j + 1 < n ? __ldg(z + t + 1) - zj : 0.0;        // dz[j]
-    const double dzj1 = j + 2 < n ? __ldg(z + t + 2) - __ldg(z + t + 1) : 0.0;   // dz[j+1]
-    // reciprocals shared by the NV slopes of an interval (mc == nullptr: the window path, plain divisions)
-    const bool z0_ok = mc != nullptr && divisor_ok(dzj), z1_ok = mc != nullptr && divisor_ok(dzj1);
-    const double rz0 = 1.0 / dzj, rz1 = 1.0 / dzj1;
-    const double ulp_dz = div_shared(kUlp, dzj, rz0, z0_ok);                  // kUlp / dz[j], refine.py:188
+    if (j + o >= 0 && j + o < n && (t + o < 0 || t + o >= wd.ne)) return;
+  if (j == 0 || j == n - 1) keep1[t] = 1;                              // refine.py:120-121
+  const bool own = t >= wd.own_lo && t < wd.own_hi;                    // only own cells report the component
+  const double zj = __ldg(z + t);
+  const double dzj = j + 1 < n ? __ldg(z + t + 1) - zj : 0.0;          // dz[j]
+  const double dzj1 = j + 2 < n ? __ldg(z + t + 2) - __ldg(z + t + 1) : 0.0;   // dz[j+1]
+  // reciprocals shared by the NV slopes of an interval (mc == nullptr: the window path, plain divisions)
+  const bool z0_ok = mc != nullptr && divisor_ok(dzj), z1_ok = mc != nullptr && divisor_ok(dzj1);
+  const double rz0 = 1.0 / dzj, rz1 = 1.0 / dzj1;
+  const double ulp_dz = div_shared(kUlp, dzj, rz0, z0_ok);                    // kUlp / dz[j], refine.py:188
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const double vmin = st->vmin[i], vmax = st->vmax[i], smin = st->smin[i], smax = st->smax[i];
-      const double aa = fmax(fabs(vmin), fabs(vmax));
-      const double ss = fmax(fabs(smin), fabs(smax));
-      const double v0 = __ldg(U + t * NV + i);
-      const double v1 = j + 1 < n ? __ldg(U + (t + 1) * NV + i) : 0.0;
-      // slope criterion on interval j (refine.py:159-173)
-      if (j + 1 < n && (vmax - vmin) > cr.min_range * aa) {
-        const double dmax = cr.slope * (vmax - vmin) + kUlp;
-        const double r = mc != nullptr ? div_shared(fabs(v1 - v0), dmax, mc->rdmax_slope[i], mc->ok[i] != 0) : fabs(v1 - v0) / dmax;
-        if (r > 1.0 && dzj >= 2 * cr.min_grid) { flag(LOC, 0); if (own) comp[i] = 1; }
-        if (r >= cr.prune) { flag(K1, 0); flag(K1, 1); }
-        else flag(VIS, 0);
-      }
-      // curvature criterion on the pair of intervals (j, j+1) (refine.py:179-197)
-      if (j + 2 < n && (smax - smin) > cr.min_range * ss) {
-        const double v2 = __ldg(U + (t + 2) * NV + i);
-        const double s0 = div_shared(v1 - v0, dzj, rz0, z0_ok);
-        const double s1 = div_shared(v2 - v1, dzj1, rz1, z1_ok);
-        const double dmax = cr.curve * (smax - smin);
-        const double r = fabs(s1 - s0) / (dmax + ulp_dz);
-        if (r > 1.0 && dzj >= 2 * cr.min_grid && dzj1 >= 2 * cr.min_grid) { if (own) comp[i] = 1; flag(LOC, 0); flag(LOC, 1); }
-        if (r >= cr.prune) flag(K1, 1);
-        else flag(VIS, 1);
-      }
+  for (int i = 0; i < NV; ++i) {
+    const double vmin = st->vmin[i], vmax = st->vmax[i], smin = st->smin[i], smax = st->smax[i];
+    const double aa = fmax(fabs(vmin), fabs(vmax));
+    const double ss = fmax(fabs(smin), fabs(smax));
+    const double v0 = __ldg(U + t * NV + i);
+    const double v1 = j + 1 < n ? __ldg(U + (t + 1) * NV + i) : 0.0;
+    // slope criterion on interval j (refine.py:159-173)
+    if (j + 1 < n && (vmax - vmin) > cr.min_range * aa) {
+      const double dmax = cr.slope * (vmax - vmin) + kUlp;
+      const double r = mc != nullptr ? div_shared(fabs(v1 - v0), dmax, mc->rdmax_slope[i], mc->ok[i] != 0) : fabs(v1 - v0) / dmax;
+      if (r > 1.0 && dzj >= 2 * cr.min_grid) { loc[t] = 1; if (own) comp[i] = 1; }
+      if (r >= cr.prune) { keep1[t] = 1; keep1[t + 1] = 1; }
+      else visited[t] = 1;
     }
-    // grid-ratio rules (refine.py:200-227), j = 1 .. n-2
-    if (j >= 1 && j <= n - 2) {
-      const double dzm1 = zj - __ldg(z + t - 1);                       // dz[j-1]
-      if (dzj > cr.ratio * dzm1) {
-        flag(LOC, 0); flag(GP, 0);
-        flag(K1, -1); flag(K1, 0); flag(K1, 1);
-        if (j + 2 < n) flag(K1, 2);
-      }
-      if (dzj < dzm1 / cr.ratio) {
-        flag(LOC, -1); flag(GP, -1);
-        if (j >= 2) flag(K1, -2);
-        flag(K1, -1); flag(K1, 0); flag(K1, 1);
-      }
-      const double span = __ldg(z + t + 1) - __ldg(z + t - 1);
-      if (j > 1 && span > cr.ratio * (__ldg(z + t - 1) - __ldg(z + t - 2))) flag(K1, 0);
-      if (j < n - 2 && span > cr.ratio * dzj1) flag(K1, 0);
+    // curvature criterion on the pair of intervals (j, j+1) (refine.py:179-197)
+    if (j + 2 < n && (smax - smin) > cr.min_range * ss) {
+      const double v2 = __ldg(U + (t + 2) * NV + i);
+      const double s0 = div_shared(v1 - v0, dzj, rz0, z0_ok);
+      const double s1 = div_shared(v2 - v1, dzj1, rz1, z1_ok);
+      const double dmax = cr.curve * (smax - smin);
+      const double r = fabs(s1 - s0) / (dmax + ulp_dz);
+      if (r > 1.0 && dzj >= 2 * cr.min_grid && dzj1 >= 2 * cr.min_grid) { if (own) comp[i] = 1; loc[t] = 1; loc[t + 1] = 1; }
+      if (r >= cr.prune) keep1[t + 1] = 1;
+      else visited[t + 1] = 1;
     }
   }
-  // what the neighbouring lanes flagged for this lane's cell
-  const int lane = threadIdx.x & 31;
-  uint8_t *const arrays[4] = {keep1, visited, loc, gridpt};
-  uint32_t mine = 0;                                                    // bit a: array a of this cell is set
-#pragma unroll
-  for (int o = -2; o <= 2; ++o) {
-    // lane L - o flagged offset o  ->  this lane's cell
-    const uint32_t from = o == 0 ? M : (o > 0 ? __shfl_up_sync(0xffffffffu, M, o) : __shfl_down_sync(0xffffffffu, M, -o));
-    const bool valid = o == 0 || (o > 0 ? lane >= o : lane + (-o) <= 31);
-    if (valid) {
-#pragma unroll
-      for (int a = 0; a < 4; ++a) mine |= ((from >> (5 * a + o + 2)) & 1u) << a;
+  // grid-ratio rules (refine.py:200-227), j = 1 .. n-2
+  if (j >= 1 && j <= n - 2) {
+    const double dzm1 = zj - __ldg(z + t - 1);                         // dz[j-1]
+    if (dzj > cr.ratio * dzm1) {
+      loc[t] = 1; gridpt[t] = 1;
+      keep1[t - 1] = 1; keep1[t] = 1; keep1[t + 1] = 1;
+      if (j + 2 < n) keep1[t + 2] = 1;
     }
-    // a flag for a cell outside this warp's 32 cells is stored by the lane that raised it
-    if (o != 0 && (lane + o < 0 || lane + o > 31)) {
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-        if ((M >> (5 * a + o + 2)) & 1u) arrays[a][t + o] = 1;
+    if (dzj < dzm1 / cr.ratio) {
+      loc[t - 1] = 1; gridpt[t - 1] = 1;
+      if (j >= 2) keep1[t - 2] = 1;
+      keep1[t - 1] = 1; keep1[t] = 1; keep1[t + 1] = 1;
     }
-  }
-  if (t < wd.ne) {
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-      if ((mine >> a) & 1u) arrays[a][t] = 1;
+    const double span = __ldg(z + t + 1) - __ldg(z + t - 1);
+    if (j > 1 && span > cr.ratio * (__ldg(z + t - 1) - __ldg(z + t - 2))) keep1[t] = 1;
+    if (j < n - 2 && span > cr.ratio * dzj1) keep1[t] = 1;
   }
 }
 

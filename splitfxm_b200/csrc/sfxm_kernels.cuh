@@ -747,19 +747,13 @@ __device__ __forceinline__ void jacobian_scalar_cell(const sfxm_problem_t &P, co
   // see stored_entry).
   const int64_t B = P.batch;
   const double reps = 1.0 / eps;
-  // One mesh (B == 1): the whole row j of the block is written - the diagonal entry and the structural zeros around it -
-  // because the three threads of a cell then store 72 contiguous bytes per slot.  Writing the diagonal alone touches one
-  // 8-byte word in each 32-byte sector, which L2 has to complete from DRAM: ncu r2s showed 459 MB of traffic for the 152
-  // algorithmic MB of a 1e6-cell assembly (3.4 TB/s for 0.137 ms).  Cross-segment entries of the row are zeros nobody
-  // reads (solves and the sparse export take same-segment entries only).
+  // (Round 2: for one mesh, writing the whole row j - diagonal plus structural zeros, 72 contiguous bytes per slot from
+  // the three threads of a cell - so that no 32-byte sector is written partially: ncu r2s shows 459 MB of DRAM traffic for
+  // the 152 algorithmic MB of a 1e6-cell assembly, but the kernel is latency-bound at 25 % occupancy (98 registers, IPC
+  // 1.4), not DRAM-bound: 0.147 ms with full rows against 0.139 ms; removed.)
   auto emit = [&](int d, double val) {
     double *q = p + (int64_t)d * (nv * nv) * B;
-    if (!(row_mask & (1u << j))) return;
-    if (B == 1) {
-      for (int c = 0; c < nv; ++c) q[c] = (c == j) ? val : 0.0;
-    } else {
-      q[(int64_t)j * B] = val;
-    }
+    if (row_mask & (1u << j)) q[(int64_t)j * B] = val;
   };
   if (interior) {
 #pragma unroll
