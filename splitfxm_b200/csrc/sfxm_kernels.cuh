@@ -800,8 +800,11 @@ __device__ __forceinline__ void jacobian_scalar_cell(const sfxm_problem_t &P, co
   }
 }
 
+#ifndef SFXM_SCALAR_JAC_MIN_CTAS
+#define SFXM_SCALAR_JAC_MIN_CTAS 1      // resident CTAs per SM the compiler must allow (register cap); see build notes
+#endif
 template <class Model, int SCHEME, int NV, int W>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, SFXM_SCALAR_JAC_MIN_CTAS)
 jacobian_scalar_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restrict__ x_int,
                        const double *__restrict__ params, int64_t param_stride, const double *__restrict__ y,
                        double eps, double *__restrict__ J, double *__restrict__ r0_out, uint32_t entry_mask,
