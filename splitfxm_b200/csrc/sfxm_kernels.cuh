@@ -801,7 +801,10 @@ __device__ __forceinline__ void jacobian_scalar_cell(const sfxm_problem_t &P, co
 }
 
 #ifndef SFXM_SCALAR_JAC_MIN_CTAS
-#define SFXM_SCALAR_JAC_MIN_CTAS 1      // resident CTAs per SM the compiler must allow (register cap); see build notes
+// resident 256-thread CTAs per SM the compiler must allow (register cap).  Measured at nx = 1e6 (gpurun_out r2u): no cap
+// (98 registers, 2 CTAs) 0.132 ms; 3 CTAs (80 registers, 12 bytes spilled) 0.109 ms; 4 (64 registers) 0.111 ms; 6 (40
+// registers, 624 bytes spilled) 0.166 ms - the kernel is latency-bound, occupancy pays until the spills do.
+#define SFXM_SCALAR_JAC_MIN_CTAS 3
 #endif
 template <class Model, int SCHEME, int NV, int W>
 __global__ void __launch_bounds__(256, SFXM_SCALAR_JAC_MIN_CTAS)
