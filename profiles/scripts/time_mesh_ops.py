@@ -33,5 +33,18 @@ def timed(fn, reps=20):
     return a.elapsed_time(b) / reps
 
 
-print(os.environ.get("SFXM_LIB", "default"), "nx", nx, "jacobian_ms %.4f residual_ms %.4f" % (
-    timed(lambda: e1.jacobian(y, True, [1], J=Jb)), timed(lambda: e1.residual(y, rr, True, [1]))))
+ss = torch.zeros_like(y)
+st1 = torch.zeros(1, dtype=torch.int32, device=y.device)
+
+
+def newton_iteration(split, locs):
+    def it():
+        e1.jacobian(y, split, locs, J=Jb, r0=rr)
+        e1.solve(Jb, rr, ss, split, locs, status=st1)
+        e1.update_norms(y, ss, update=False)
+    return it
+
+
+print(os.environ.get("SFXM_LIB", "default"), "nx", nx, "jacobian_ms %.4f residual_ms %.4f newton_it_split1_ms %.4f newton_it_unsplit_ms %.4f" % (
+    timed(lambda: e1.jacobian(y, True, [1], J=Jb)), timed(lambda: e1.residual(y, rr, True, [1])),
+    timed(newton_iteration(True, [1]), 10), timed(newton_iteration(False, None), 10)))

@@ -196,8 +196,11 @@ static inline SepMap make_sepmap(int64_t n, bool want_last) {
 }
 
 // rows[((cell * S + r) * (1 + 2 S) + c) * B + m]: (q | V | W) of a chunk cell
+#ifndef SFXM_CHUNK_MIN_CTAS
+#define SFXM_CHUNK_MIN_CTAS 1
+#endif
 template <int NV, int S>
-__global__ void __launch_bounds__(kChunkPeriod)
+__global__ void __launch_bounds__(kChunkPeriod, SFXM_CHUNK_MIN_CTAS)
 chunk_reduce_kernel(const __grid_constant__ sfxm_problem_t P, const SepMap sp, int o, const double *__restrict__ J,
                     const double *__restrict__ f, const double *__restrict__ shift, double *__restrict__ rows,
                     int32_t *__restrict__ status) {
