@@ -196,11 +196,14 @@ static inline SepMap make_sepmap(int64_t n, bool want_last) {
 }
 
 // rows[((cell * S + r) * (1 + 2 S) + c) * B + m]: (q | V | W) of a chunk cell
+// Register cap per block size (measured at nx = 1e6, gpurun_out r2v): the 2 x 2 kernel needs 150 registers uncapped
+// (one 256-thread CTA per SM); capped at 128 (two CTAs, 74 bytes spilled) a split [1] Newton iteration takes 0.557
+// instead of 0.596 ms.  The 3 x 3 kernel spills 1.1 KB under the same cap and doubles its time (1.09 -> 2.07 ms): uncapped.
 #ifndef SFXM_CHUNK_MIN_CTAS
-#define SFXM_CHUNK_MIN_CTAS 1
+#define SFXM_CHUNK_MIN_CTAS(S) ((S) == 2 ? 2 : 1)
 #endif
 template <int NV, int S>
-__global__ void __launch_bounds__(kChunkPeriod, SFXM_CHUNK_MIN_CTAS)
+__global__ void __launch_bounds__(kChunkPeriod, SFXM_CHUNK_MIN_CTAS(S))
 chunk_reduce_kernel(const __grid_constant__ sfxm_problem_t P, const SepMap sp, int o, const double *__restrict__ J,
                     const double *__restrict__ f, const double *__restrict__ shift, double *__restrict__ rows,
                     int32_t *__restrict__ status) {

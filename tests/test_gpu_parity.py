@@ -83,6 +83,37 @@ def test_evolve_matches_reference(name):
     err = rel_err(d.values(), z["U_all"])
     print(name, method, "rel err", err)
     assert err <= tol
+    if method == "RK45":
+        # the step-size controller runs on the device (csrc/sfxm_ode.cu): same number of right-hand-side evaluations as
+        # scipy's in the reference run (2 for the initial step + 6 per attempted step)
+        assert s._rk is not None and s._rk[1].nfev == int(z["nfev"])
+
+
+def test_rk45_device_and_host_controllers_agree():
+    """The graph-replayed device controller against the host-controlled loop on a problem with rejected steps (a stiff
+    diffusion coefficient) and a max_step clamp: same attempts, same result to round-off (err ** -0.2: CUDA pow vs libm)."""
+    import os
+    import splitfxm_b200 as sf
+    from splitfxm_b200.models.advection_diffusion import AdvectionDiffusion
+    from splitfxm_b200.ode import RK45Stepper
+    comps = ["u", "v"]
+    bcs = {"u": {"left": "periodic", "right": "periodic"}, "v": {"left": {"dirichlet": 1.0}, "right": {"neumann": 0.0}}}
+    out = []
+    for device in ("1", "0"):
+        os.environ["SFXM_RK45_DEVICE"] = device
+        try:
+            d = sf.Domain.from_size(200, 1, 1, comps)
+            sim = sf.Simulation(d, AdvectionDiffusion(0.5, 0.2, "FVM"), {"u": "sine", "v": "tophat"}, bcs, sf.FVSchemes.LAX_FRIEDRICHS)
+            eng = sim._engine()
+            st = RK45Stepper(eng, False, None, 1e-3, 1e-6, 2e-4)
+            assert st.device_control_ok() == (device == "1")
+            y = st.integrate(sim._state(eng, False, None), 0.003)
+            out.append((st.nfev, y.cpu().numpy().copy()))
+        finally:
+            os.environ.pop("SFXM_RK45_DEVICE", None)
+    (n1, y1), (n0, y0) = out
+    assert n1 == n0 and n1 > 50
+    assert rel_err(y1, y0) < 1e-13
 
 
 @pytest.mark.parametrize("name", ["sod_cons_nx100_t0p05", "sod_cons_nx60_unsplit_t0p02", "sod_prim_nx60_t0p02"])
