@@ -124,8 +124,11 @@ struct Criteria {
 // 296 us at 1e7 cells (gpurun_out r2t): the kernel is bound by its instruction stream, not by the stores; removed.)
 // flags: keep1[j] / visited[j] / loc[j] (bytes, zero-initialised), comp[i] = component i asked for a point,
 // gridpt[j] = the grid-ratio rule named "point j" (refine.py:203,211)
+#ifndef SFXM_AMR_MARK_MIN_CTAS
+#define SFXM_AMR_MARK_MIN_CTAS 1
+#endif
 template <int NV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, SFXM_AMR_MARK_MIN_CTAS)
 amr_mark_kernel(const double *__restrict__ z, const double *__restrict__ U, const Window wd, const Criteria cr,
                 const Stats *__restrict__ st, uint8_t *__restrict__ keep1, uint8_t *__restrict__ visited,
                 uint8_t *__restrict__ loc, int32_t *__restrict__ comp, uint8_t *__restrict__ gridpt,

@@ -291,8 +291,11 @@ residual_ring_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
 // divisions each) of the one-thread-does-everything kernel.  Lanes [nbl, 32 - nbr) of a warp produce residuals, the
 // outer lanes only feed their neighbours.  Warps that touch a domain end use the general per-thread path.
 // ------------------------------------------------------------------------------------------------
+#ifndef SFXM_WARP_RES_MIN_CTAS
+#define SFXM_WARP_RES_MIN_CTAS 1
+#endif
 template <class Model, int SCHEME, int NV, int W>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, SFXM_WARP_RES_MIN_CTAS)
 residual_warp_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restrict__ x_int,
                      const double *__restrict__ params, int64_t param_stride, const double *__restrict__ y,
                      double *__restrict__ r_out, double *__restrict__ y_out, double dt) {
@@ -708,8 +711,11 @@ jacobian_pair_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
 // 21 % occupancy, profiles/README.md r1f), and with batch = 1 consecutive threads touch consecutive unknowns of
 // the cell-major vector.  threadIdx.y / blockIdx walk t = cell * NV + variable.
 // ------------------------------------------------------------------------------------------------
+#ifndef SFXM_SCALAR_RES_MIN_CTAS
+#define SFXM_SCALAR_RES_MIN_CTAS 1
+#endif
 template <class Model, int SCHEME, int NV, int W>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, SFXM_SCALAR_RES_MIN_CTAS)
 residual_scalar_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restrict__ x_int,
                        const double *__restrict__ params, int64_t param_stride, const double *__restrict__ y,
                        double *__restrict__ r_out, double *__restrict__ y_out, double dt,
