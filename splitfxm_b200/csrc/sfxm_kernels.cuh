@@ -291,8 +291,11 @@ residual_ring_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
 // divisions each) of the one-thread-does-everything kernel.  Lanes [nbl, 32 - nbr) of a warp produce residuals, the
 // outer lanes only feed their neighbours.  Warps that touch a domain end use the general per-thread path.
 // ------------------------------------------------------------------------------------------------
+// resident 256-thread CTAs per SM the compiler must allow (register cap).  Conservative Sod, nx = 1e7, explicit Euler step
+// (gpurun_out r2w): uncapped (80 registers, 3 CTAs) 0.420 ms; 4 CTAs (64 registers, 16 bytes spilled) 0.314 ms; 5 (48
+// registers) 0.348 ms; 6 (40 registers) 0.412 ms.
 #ifndef SFXM_WARP_RES_MIN_CTAS
-#define SFXM_WARP_RES_MIN_CTAS 1
+#define SFXM_WARP_RES_MIN_CTAS 4
 #endif
 template <class Model, int SCHEME, int NV, int W>
 __global__ void __launch_bounds__(256, SFXM_WARP_RES_MIN_CTAS)
@@ -711,8 +714,10 @@ jacobian_pair_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
 // 21 % occupancy, profiles/README.md r1f), and with batch = 1 consecutive threads touch consecutive unknowns of
 // the cell-major vector.  threadIdx.y / blockIdx walk t = cell * NV + variable.
 // ------------------------------------------------------------------------------------------------
+// (register cap, as above) one mesh, nx = 1e6: uncapped (60 registers, 4 CTAs) 0.0417 ms; 5 CTAs (48 registers) 0.0356 ms;
+// 6 (40 registers) 0.0393 ms; 8 (32 registers) 0.0436 ms.
 #ifndef SFXM_SCALAR_RES_MIN_CTAS
-#define SFXM_SCALAR_RES_MIN_CTAS 1
+#define SFXM_SCALAR_RES_MIN_CTAS 5
 #endif
 template <class Model, int SCHEME, int NV, int W>
 __global__ void __launch_bounds__(256, SFXM_SCALAR_RES_MIN_CTAS)
