@@ -53,7 +53,9 @@ __device__ __noinline__ void fused_row_general(const sfxm_problem_t &P, const Fu
 // Resident one-warp CTAs per SM the register allocation must allow.  Measured on the 65,536 x nx 250 ensemble
 // (gpurun_out/fused_time_variants.log): scalar segments run 0.64 -> 0.49 ms when capped at 128 registers (14 CTAs per SM:
 // all 2048 warps resident in one wave, the spills are cheaper than a second wave); 2x2 and 3x3 segments spill too much
-// under the cap and are left at 255 registers (8 CTAs per SM).
+// under the cap and are left at 255 registers (8 CTAs per SM).  Re-measured in round 2 after the update was folded into the
+// back substitution (gpurun_out r2x, 2x2 segment of the bench ensemble): uncapped 0.756 ms; 10 or 12 CTAs (168 registers,
+// ~220 bytes spilled) 0.93 / 0.90 ms; 14 CTAs (128 registers) 1.05 ms.
 #ifndef SFXM_FUSED_MIN_CTAS
 #define SFXM_FUSED_MIN_CTAS(S) ((S) == 1 ? 14 : 1)
 #endif
