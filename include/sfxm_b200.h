@@ -93,7 +93,8 @@ int sfxm_residual(const sfxm_problem_t *prob, const double *x_int, const double 
 
 /* Per-cell geometry table geom[SFXM_GEOM_ROWS * nx] (the divisors of the scheme, their reciprocals, 1/dx): it
  * depends on the mesh and the ghost-position rule only, so an ensemble computes it once per mesh instead of once
- * per member.  Optional everywhere: pass geom = NULL and each thread derives it from x_int. */
+ * per member.  One record of SFXM_GEOM_ROWS doubles per cell (geom[i * SFXM_GEOM_ROWS + k]); the buffer must be 16-byte
+ * aligned.  Optional everywhere: pass geom = NULL and each thread derives it from x_int. */
 #define SFXM_GEOM_ROWS 10
 int sfxm_geometry(const sfxm_problem_t *prob, const double *x_int, double *geom, void *stream);
 

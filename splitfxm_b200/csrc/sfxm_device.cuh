@@ -298,14 +298,22 @@ struct ModelEulerCons {   // tutorials/conservative_sod_shock/euler1d.py:28-63 ;
 // parity target is the correctly rounded IEEE quotient.  nvcc expands a/b into ~35 FP64-pipe instructions
 // (reciprocal seed + Newton iterations + fix-up); the divisors here are mesh spacings and the FD epsilon,
 // shared by every perturbation of a cell, so their correctly rounded reciprocals rb = RN(1/b) are computed
-// once and each quotient costs five FMAs: two Markstein correction steps
-//      q1 = RN(q0 + RN(a - q0 b) rb),   q2 = RN(q1 + RN(a - q1 b) rb)
-// The first makes the quotient faithful, the second makes it correctly rounded (Markstein 1990; the residuals
-// a - q b are exact in an FMA).  This holds while nothing under- or overflows, so each thread checks ONCE that
-// its inputs are "sane" - stencil values and parameters zero or within 2^+-120, divisors within 2^+-120: then
-// every numerator (a difference of such values: zero or >= 2^-173) and every quotient stays far inside the
-// normal range - and otherwise (FAST = false instantiation) all its quotients use the IEEE division.
-// sfxm_selftest_div compares the two on random and adversarial operands (tests/test_gpu_div.py).
+// once and each quotient costs one multiplication and two FMAs:
+//      q0 = RN(a rb),   r = RN(a - q0 b) (exact),   q = RN(q0 + r rb)
+// Why one correction step is enough (round 2; rounds 1-2a ran two).  Scale so that b, a/b are in [1, 2)
+// (u = 2^-52).  With e = 1 - b rb, |e| < b 2^-54, the FMA's argument is exactly  q0 + r rb = a/b - (a/b - q0) e.
+//  * a/b within u/4 of a rounding boundary m (midpoint of two doubles): a rb = (a/b)(1 - e) lies within
+//    (a/b) b 2^-54 < u of a/b, so q0 is one of m +- u/2, |a/b - q0| <= u/2 + |a/b - m| and r (a multiple of
+//    2^-104 below 1.5 2^-52) is exact.  a/b cannot BE a midpoint: a - m b is a non-zero multiple of 2^-105, so
+//    |a/b - m| >= 2^-105 / b, while the perturbation is below (u/2) b 2^-54 (1 + 2^-52) = b 2^-107 (1 + ..),
+//    smaller because b^2 < 4 (1 - 2^-53): the argument stays on a/b's side of m and rounds like a/b.
+//  * elsewhere |a/b - q0| <= 1.5 u, the perturbation (with a possibly inexact r) is below 2^-51 u << u/4.
+// This holds while nothing under- or overflows, so each thread checks ONCE that its inputs are "sane" -
+// stencil values and parameters zero or within 2^+-120, divisors within 2^+-120: then every numerator (a
+// difference of such values: zero or >= 2^-173) and every quotient stays far inside the normal range - and
+// otherwise (FAST = false instantiation) all its quotients use the IEEE division.  sfxm_selftest_div compares
+// the two on random, adversarial and nearest-to-midpoint operands (tests/test_gpu_div.py); tests/test_div_known.py
+// checks the same three operations in exact rational arithmetic on the CPU.
 // ------------------------------------------------------------------------------------------------
 // out of line on purpose: inlined, the compiler if-converts the rare path and executes the full IEEE division
 // (MUFU.RCP64H + ~10 DFMA + fix-up) for every quotient, which is what div_known exists to avoid
@@ -314,16 +322,21 @@ static __device__ __noinline__ double div_ieee(double a, double b) { return a / 
 template <bool FAST>
 __device__ __forceinline__ double div_known(double a, double b, double rb) {
   if constexpr (!FAST) return div_ieee(a, b);
+#ifdef SFXM_DIV_TWO_CORRECTIONS
   const double q0 = a * rb;
   const double q1 = __fma_rn(__fma_rn(-q0, b, a), rb, q0);
   return __fma_rn(__fma_rn(-q1, b, a), rb, q1);
+#else
+  const double q0 = a * rb;
+  return __fma_rn(__fma_rn(-q0, b, a), rb, q0);
+#endif
 }
 
-// exponent of v within 2^+-span, or v == 0
+// exponent of v within 2^+-span, or v == 0 (four integer instructions: mask, subtract, or-with-low-word, compare)
 __device__ __forceinline__ bool sane(double v, unsigned span) {
-  const unsigned e = ((unsigned)__double2hiint(v) >> 20) & 0x7ffu;
+  const unsigned a = (unsigned)__double2hiint(v) & 0x7fffffffu;
   // bitwise, not short-circuit: keeps the check branch-free (integer pipe only)
-  return ((e - (1023u - span)) < 2u * span) | ((((unsigned)__double2hiint(v) << 1) | (unsigned)__double2loint(v)) == 0u);
+  return ((a - ((1023u - span) << 20)) < ((2u * span) << 20)) | ((a | (unsigned)__double2loint(v)) == 0u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -364,24 +377,23 @@ struct Geom {
       fast = fast & sane(d[k], 120) & (d[k] != 0.0);
     }
   }
-  // from the per-cell table written by geometry_kernel: tab[k * nx + i], k = d0..d3, rd0..rd3, inv, fast
-  __device__ __forceinline__ Geom(const double *__restrict__ tab, int64_t nx, int64_t i) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      d[k] = __ldg(tab + k * nx + i);
-      rd[k] = __ldg(tab + (4 + k) * nx + i);
-    }
-    inv = __ldg(tab + 8 * nx + i);
-    fast = __ldg(tab + 9 * nx + i) != 0.0;
+  // from the per-cell table written by geometry_kernel: one 80-byte record per cell, tab[i * 10 + k], k = d0..d3,
+  // rd0..rd3, inv, fast - five 16-byte loads from one address (the table must be 16-byte aligned)
+  __device__ __forceinline__ Geom(const double *__restrict__ tab, int64_t, int64_t i) {
+    const double2 *__restrict__ rec = reinterpret_cast<const double2 *>(tab + i * 10);
+    const double2 a = __ldg(rec), b = __ldg(rec + 1), c = __ldg(rec + 2), e = __ldg(rec + 3), f = __ldg(rec + 4);
+    d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y;
+    rd[0] = c.x; rd[1] = c.y; rd[2] = e.x; rd[3] = e.y;
+    inv = f.x;
+    fast = f.y != 0.0;
   }
-  __device__ __forceinline__ void store(double *__restrict__ tab, int64_t nx, int64_t i) const {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      tab[k * nx + i] = d[k];
-      tab[(4 + k) * nx + i] = rd[k];
-    }
-    tab[8 * nx + i] = inv;
-    tab[9 * nx + i] = fast ? 1.0 : 0.0;
+  __device__ __forceinline__ void store(double *__restrict__ tab, int64_t, int64_t i) const {
+    double2 *__restrict__ rec = reinterpret_cast<double2 *>(tab + i * 10);
+    rec[0] = make_double2(d[0], d[1]);
+    rec[1] = make_double2(d[2], d[3]);
+    rec[2] = make_double2(rd[0], rd[1]);
+    rec[3] = make_double2(rd[2], rd[3]);
+    rec[4] = make_double2(inv, fast ? 1.0 : 0.0);
   }
   template <int NV, int NP>
   __device__ __forceinline__ void and_inputs(const double (&u)[W][NV], const double (&prm)[NP]) {

@@ -599,71 +599,116 @@ jacobian_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restri
 // RESTRICT: only the columns of the requested segments are evaluated (sfxm_jacobian_segments).  A separate
 // instantiation, because the per-column branch ends the straight-line code in which the compiler interleaves the
 // independent column evaluations (measured: 0.57 -> 0.70 ms when the unrestricted kernel carried the test).
+// Host-prepared arguments (round 2, second half): everything that is the same for every CTA is formed once on the
+// host - row bases with the split permutation folded in, 32-bit row lengths - so that a CTA's address arithmetic is a
+// handful of 32 x 32 -> 64-bit multiply-adds instead of ~25 64-bit products of sfxm_problem_t fields (SASS of the
+// previous kernel: 177 IMAD + 48 LEA + 41 IADD3 of 1199 instructions per warp, more than a third of its non-FP64 work).
+template <int NV>
+struct PairArgs {
+  const double *yv[NV];   // y + (var_base[j] + var_off[j]) * batch: variable j of cell 0, member 0
+  double *r0v[NV];        // the same rows of r0_out (null: not wanted)
+  uint32_t row[NV];       // var_stride[j] * batch: elements from one cell to the next
+  uint32_t batch, nx, nbl;
+  uint32_t pstride;       // parameter k of member m at params[k * pstride + m] (0: shared by all members)
+  uint32_t eps_sane;      // the finite-difference step passes the range check of div_known (sfxm_device.cuh)
+  double reps;            // RN(1 / eps), formed on the host (IEEE division: the same bits as on the device)
+};
+
 template <class Model, int SCHEME, int NV, int W, bool RESTRICT>
 __global__ void __launch_bounds__(32, SFXM_PAIR_MIN_CTAS)
-jacobian_pair_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restrict__ x_int,
-                     const double *__restrict__ params, int64_t param_stride, const double *__restrict__ y,
-                     double eps, double *__restrict__ J, double *__restrict__ r0_out, uint32_t entry_mask,
-                     const double *__restrict__ geom_tab) {
-  const int64_t i = (int64_t)blockIdx.z * gridDim.y + blockIdx.y;
-  const int64_t m0 = ((int64_t)blockIdx.x * 32 + threadIdx.x) * 2;
-  if (m0 >= P.batch || i >= P.nx) return;
-  const int64_t B = P.batch;
-  const int nbl = (W == 3) ? 1 : P.nbl;
-  const bool interior = (i >= nbl) && (i + (W - 1 - nbl) < P.nx);
-  if (!interior || geom_tab == nullptr) {   // warp-uniform: boundary cells take the general path
+jacobian_pair_kernel(const __grid_constant__ sfxm_problem_t P, const __grid_constant__ PairArgs<NV> A,
+                     const double *__restrict__ x_int, const double *__restrict__ params, int64_t param_stride,
+                     const double *__restrict__ y, double eps, double *__restrict__ J, double *__restrict__ r0_out,
+                     uint32_t entry_mask, const double *__restrict__ geom_tab) {
+  const uint32_t i = blockIdx.z * gridDim.y + blockIdx.y;
+  const uint32_t m0 = (blockIdx.x * 32 + threadIdx.x) * 2;
+  if (m0 >= A.batch || i >= A.nx) return;
+  const uint32_t nbl = (W == 3) ? 1u : A.nbl;
+  const bool interior = (i >= nbl) && (i + (W - 1 - nbl) < A.nx);
+  if (!interior) {   // warp-uniform: boundary cells take the general path
     jacobian_member_noinline<Model, SCHEME, NV, W>(P, x_int, params, param_stride, y, eps, J, r0_out, entry_mask, geom_tab, i, m0);
     jacobian_member_noinline<Model, SCHEME, NV, W>(P, x_int, params, param_stride, y, eps, J, r0_out, entry_mask, geom_tab, i, m0 + 1);
     return;
   }
-  bool vector_ok = true;
+  const uint32_t B = A.batch;
   double prm[2][Model::kParams];
   double u[2][W][NV];
-  int64_t off[NV];
-  const Geom<SCHEME, W> geom(geom_tab, P.nx, i);
-  {
+  const Geom<SCHEME, W> geom(geom_tab, A.nx, i);
 #pragma unroll
-    for (int k = 0; k < Model::kParams; ++k) {
-      if (param_stride) {
-        const double2 t = __ldg(reinterpret_cast<const double2 *>(params + k * param_stride + m0));
-        prm[0][k] = t.x;
-        prm[1][k] = t.y;
-      } else {
-        prm[0][k] = prm[1][k] = __ldg(params + k);
-      }
+  for (int k = 0; k < Model::kParams; ++k) {
+    const double2 t = A.pstride ? __ldg(reinterpret_cast<const double2 *>(params + ((uint64_t)((uint32_t)k * A.pstride) + m0)))
+                                : make_double2(__ldg(params + k), __ldg(params + k));
+    prm[0][k] = t.x;
+    prm[1][k] = t.y;
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const double *q = A.yv[j] + ((uint64_t)(i - nbl) * A.row[j] + m0);
+#pragma unroll
+    for (int s = 0; s < W; ++s) {
+      const double2 t = __ldg(reinterpret_cast<const double2 *>(q + (uint64_t)((uint32_t)s * A.row[j])));
+      u[0][s][j] = t.x;
+      u[1][s][j] = t.y;
     }
+  }
+  bool vector_ok = geom.fast & (A.eps_sane != 0u);
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int64_t rs = (int64_t)P.var_stride[j] * B;
-      off[j] = (P.var_base[j] + P.var_off[j]) * B + m0 + i * rs;
-      const double *q = y + (off[j] - nbl * rs);
+  for (int v = 0; v < 2; ++v) {
 #pragma unroll
-      for (int s = 0; s < W; ++s) {
-        const double2 t = __ldg(reinterpret_cast<const double2 *>(q));
-        u[0][s][j] = t.x;
-        u[1][s][j] = t.y;
-        q += rs;
-      }
-    }
-    Geom<SCHEME, W> g0 = geom, g1 = geom;
-    g0.and_inputs(u[0], prm[0]);
-    g1.and_inputs(u[1], prm[1]);
-    vector_ok = g0.fast & g1.fast & sane(eps, 120);
+    for (int s = 0; s < W; ++s)
+#pragma unroll
+      for (int j = 0; j < NV; ++j) vector_ok = vector_ok & sane(u[v][s][j], 120);
+#pragma unroll
+    for (int k = 0; k < Model::kParams; ++k) vector_ok = vector_ok & sane(prm[v][k], 120);
   }
   if (!vector_ok) {
     jacobian_member_noinline<Model, SCHEME, NV, W>(P, x_int, params, param_stride, y, eps, J, r0_out, entry_mask, geom_tab, i, m0);
     jacobian_member_noinline<Model, SCHEME, NV, W>(P, x_int, params, param_stride, y, eps, J, r0_out, entry_mask, geom_tab, i, m0 + 1);
     return;
   }
-  const double reps = 1.0 / eps;
+  const double reps = A.reps;
+  double *const Jc = J + ((uint64_t)i * ((uint32_t)(W * NV * NV) * B) + m0);   // entry (d, r, c) at Jc + ((d NV + r) NV + c) B
+  if constexpr (Model::kDecoupled) {
+    // one scalar equation per variable (only row c of column c can be non-zero, see stored_entry): variable by variable,
+    // so that a variable's stencil values and residual die as soon as its W entries are stored
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      if constexpr (RESTRICT) {
+        if (!(entry_mask & column_bits<NV>(c))) continue;   // variable outside the requested segments
+      }
+      double us[2][W][1], r0[2][1];
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+#pragma unroll
+        for (int s = 0; s < W; ++s) us[v][s][0] = u[v][s][c];
+        cell_residual<typename Model::Scalar, SCHEME, 1, W, true>(prm[v], us[v], geom, r0[v]);   // simulation.py:320
+      }
+      if (A.r0v[c])
+        *reinterpret_cast<double2 *>(A.r0v[c] + ((uint64_t)i * A.row[c] + m0)) = make_double2(r0[0][0], r0[1][0]);
+#pragma unroll
+      for (int d = 0; d < W; ++d) {
+        double e[2];
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          double up[W][1], r1[1];
+#pragma unroll
+          for (int s = 0; s < W; ++s) up[s][0] = us[v][s][0];
+          up[d][0] = us[v][d][0] + eps;                                                          // simulation.py:337
+          cell_residual<typename Model::Scalar, SCHEME, 1, W, true>(prm[v], up, geom, r1);       // simulation.py:345
+          e[v] = div_known<true>(r1[0] - r0[v][0], eps, reps);                                   // simulation.py:354
+        }
+        if (entry_mask & (1u << (c * NV + c)))
+          *reinterpret_cast<double2 *>(Jc + (uint64_t)((uint32_t)((d * NV + c) * NV + c) * B)) = make_double2(e[0], e[1]);
+      }
+    }
+  } else {
   double r0[2][NV];
 #pragma unroll
   for (int v = 0; v < 2; ++v) cell_residual<Model, SCHEME, NV, W, true>(prm[v], u[v], geom, r0[v]);   // simulation.py:320
-  if (r0_out) {
 #pragma unroll
-    for (int j = 0; j < NV; ++j) *reinterpret_cast<double2 *>(r0_out + off[j]) = make_double2(r0[0][j], r0[1][j]);
-  }
-  double *p = J + (i * W) * (int64_t)(NV * NV) * B + m0;
+  for (int j = 0; j < NV; ++j)
+    if (A.r0v[j])
+      *reinterpret_cast<double2 *>(A.r0v[j] + ((uint64_t)i * A.row[j] + m0)) = make_double2(r0[0][j], r0[1][j]);
 #pragma unroll
   for (int d = 0; d < W; ++d) {
     double cols[2][NV][NV];   // [member][c][r]
@@ -683,11 +728,11 @@ jacobian_pair_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
 #pragma unroll
     for (int r = 0; r < NV; ++r)
 #pragma unroll
-      for (int c = 0; c < NV; ++c) {
+      for (int c = 0; c < NV; ++c)
         if (stored_entry<Model>(r, c) && (entry_mask & (1u << (r * NV + c))))
-          *reinterpret_cast<double2 *>(p) = make_double2(cols[0][c][r], cols[1][c][r]);
-        p += B;
-      }
+          *reinterpret_cast<double2 *>(Jc + (uint64_t)((uint32_t)((d * NV + r) * NV + c) * B)) =
+              make_double2(cols[0][c][r], cols[1][c][r]);
+  }
   }
 }
 
@@ -934,6 +979,24 @@ struct Launch {
   int seg_lo, seg_hi;   // Jacobian: assemble the entries of segments [seg_lo, seg_hi) only
 };
 
+// host twin of sane() (sfxm_device.cuh)
+static bool host_sane(double v, unsigned span) {
+  uint64_t bits;
+  std::memcpy(&bits, &v, sizeof bits);
+  const uint32_t a = (uint32_t)(bits >> 32) & 0x7fffffffu;
+  return ((uint32_t)(a - ((1023u - span) << 20)) < ((2u * span) << 20)) || ((a | (uint32_t)bits) == 0u);
+}
+
+// the ensemble Jacobian kernel addresses with 32-bit row lengths (PairArgs)
+template <int NV, int W>
+static bool pair_args_fit(const sfxm_problem_t &P) {
+  if (P.nx >= (int64_t)1 << 31 || P.batch * (int64_t)(W * NV * NV) >= (int64_t)1 << 32) return false;
+  if (P.batch * (int64_t)SFXM_MAX_PARAMS >= (int64_t)1 << 32) return false;   // parameter rows (stride <= batch)
+  for (int j = 0; j < NV; ++j)
+    if (P.var_stride[j] * P.batch >= (int64_t)1 << 32) return false;
+  return true;
+}
+
 template <class Model, int SCHEME, int NV, int W>
 static int launch_t(const Launch &L) {
   const sfxm_problem_t &P = *L.P;
@@ -992,14 +1055,27 @@ static int launch_t(const Launch &L) {
     dim3 g = grid_for(P.batch, P.nx, b, strip);
     if (g.z > 65535) return set_error("mesh too large for one launch");
     residual_kernel<Model, SCHEME, NV, W><<<g, b, 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.out0, L.out1, L.scalar, L.geom, strip);
-  } else if (P.batch >= 64 && P.batch % 2 == 0 && L.geom != nullptr && pair_enabled()) {
+  } else if (P.batch >= 64 && P.batch % 2 == 0 && L.geom != nullptr && pair_enabled() && pair_args_fit<NV, W>(P)) {
     const int64_t gy = P.nx < 65535 ? P.nx : 65535;
     dim3 g((unsigned)((P.batch / 2 + 31) / 32), (unsigned)gy, (unsigned)((P.nx + gy - 1) / gy));
     if (g.z > 65535) return set_error("mesh too large for one launch");
+    PairArgs<NV> A;
+    for (int j = 0; j < NV; ++j) {
+      const int64_t base = (P.var_base[j] + P.var_off[j]) * P.batch;
+      A.yv[j] = L.y + base;
+      A.r0v[j] = L.out1 ? L.out1 + base : nullptr;
+      A.row[j] = (uint32_t)(P.var_stride[j] * P.batch);
+    }
+    A.batch = (uint32_t)P.batch;
+    A.nx = (uint32_t)P.nx;
+    A.nbl = (uint32_t)P.nbl;
+    A.pstride = (uint32_t)L.pstride;
+    A.eps_sane = host_sane(L.scalar, 120) ? 1u : 0u;
+    A.reps = 1.0 / L.scalar;
     if (restricted)
-      jacobian_pair_kernel<Model, SCHEME, NV, W, true><<<g, dim3(32, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.scalar, L.out0, L.out1, mask, L.geom);
+      jacobian_pair_kernel<Model, SCHEME, NV, W, true><<<g, dim3(32, 1, 1), 0, L.st>>>(P, A, L.x, L.params, L.pstride, L.y, L.scalar, L.out0, L.out1, mask, L.geom);
     else
-      jacobian_pair_kernel<Model, SCHEME, NV, W, false><<<g, dim3(32, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.scalar, L.out0, L.out1, mask, L.geom);
+      jacobian_pair_kernel<Model, SCHEME, NV, W, false><<<g, dim3(32, 1, 1), 0, L.st>>>(P, A, L.x, L.params, L.pstride, L.y, L.scalar, L.out0, L.out1, mask, L.geom);
   } else {
     dim3 g = grid_for(P.batch, P.nx, b);
     if (g.z > 65535) return set_error("mesh too large for one launch");

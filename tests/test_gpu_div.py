@@ -5,7 +5,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("mode,n", [(0, 1 << 28), (1, 1 << 28)])
+@pytest.mark.parametrize("mode,n", [(0, 1 << 28), (1, 1 << 28), (2, 1 << 28)])
 def test_division_by_known_reciprocal_is_correctly_rounded(mode, n):
     import torch
     from splitfxm_b200 import _lib
