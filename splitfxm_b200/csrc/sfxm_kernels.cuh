@@ -599,6 +599,8 @@ jacobian_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restri
 // RESTRICT: only the columns of the requested segments are evaluated (sfxm_jacobian_segments).  A separate
 // instantiation, because the per-column branch ends the straight-line code in which the compiler interleaves the
 // independent column evaluations (measured: 0.57 -> 0.70 ms when the unrestricted kernel carried the test).
+__device__ __forceinline__ void prefetch_l1_row(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // Host-prepared arguments (round 2, second half): everything that is the same for every CTA is formed once on the
 // host - row bases with the split permutation folded in, 32-bit row lengths - so that a CTA's address arithmetic is a
 // handful of 32 x 32 -> 64-bit multiply-adds instead of ~25 64-bit products of sfxm_problem_t fields (SASS of the
@@ -614,15 +616,15 @@ struct PairArgs {
   double reps;            // RN(1 / eps), formed on the host (IEEE division: the same bits as on the device)
 };
 
+#ifndef SFXM_PAIR_CELLS
+#define SFXM_PAIR_CELLS 1           // consecutive cells per one-warp CTA of the ensemble Jacobian kernel
+#endif
+
 template <class Model, int SCHEME, int NV, int W, bool RESTRICT>
-__global__ void __launch_bounds__(32, SFXM_PAIR_MIN_CTAS)
-jacobian_pair_kernel(const __grid_constant__ sfxm_problem_t P, const __grid_constant__ PairArgs<NV> A,
+__device__ __forceinline__ void jacobian_pair_cell(const sfxm_problem_t &P, const PairArgs<NV> &A,
                      const double *__restrict__ x_int, const double *__restrict__ params, int64_t param_stride,
                      const double *__restrict__ y, double eps, double *__restrict__ J, double *__restrict__ r0_out,
-                     uint32_t entry_mask, const double *__restrict__ geom_tab) {
-  const uint32_t i = blockIdx.z * gridDim.y + blockIdx.y;
-  const uint32_t m0 = (blockIdx.x * 32 + threadIdx.x) * 2;
-  if (m0 >= A.batch || i >= A.nx) return;
+                     uint32_t entry_mask, const double *__restrict__ geom_tab, const uint32_t i, const uint32_t m0) {
   const uint32_t nbl = (W == 3) ? 1u : A.nbl;
   const bool interior = (i >= nbl) && (i + (W - 1 - nbl) < A.nx);
   if (!interior) {   // warp-uniform: boundary cells take the general path
@@ -733,6 +735,35 @@ jacobian_pair_kernel(const __grid_constant__ sfxm_problem_t P, const __grid_cons
           *reinterpret_cast<double2 *>(Jc + (uint64_t)((uint32_t)((d * NV + r) * NV + c) * B)) =
               make_double2(cols[0][c][r], cols[1][c][r]);
   }
+  }
+}
+
+template <class Model, int SCHEME, int NV, int W, bool RESTRICT>
+__global__ void __launch_bounds__(32, SFXM_PAIR_MIN_CTAS)
+jacobian_pair_kernel(const __grid_constant__ sfxm_problem_t P, const __grid_constant__ PairArgs<NV> A,
+                     const double *__restrict__ x_int, const double *__restrict__ params, int64_t param_stride,
+                     const double *__restrict__ y, double eps, double *__restrict__ J, double *__restrict__ r0_out,
+                     uint32_t entry_mask, const double *__restrict__ geom_tab) {
+  const uint32_t m0 = (blockIdx.x * 32 + threadIdx.x) * 2;
+  if (m0 >= A.batch) return;
+  if constexpr (SFXM_PAIR_CELLS == 1) {
+    const uint32_t i = blockIdx.z * gridDim.y + blockIdx.y;
+    if (i >= A.nx) return;
+    jacobian_pair_cell<Model, SCHEME, NV, W, RESTRICT>(P, A, x_int, params, param_stride, y, eps, J, r0_out, entry_mask, geom_tab, i, m0);
+  } else {
+    // consecutive cells share W - 1 of their W stencil rows (L1 hits for the later cell); the one new row of the next
+    // cell is requested before this cell's arithmetic starts
+    const uint32_t i0 = (blockIdx.z * gridDim.y + blockIdx.y) * SFXM_PAIR_CELLS;
+#pragma unroll 1
+    for (uint32_t i = i0; i < i0 + SFXM_PAIR_CELLS && i < A.nx; ++i) {
+      const uint32_t nbl = (W == 3) ? 1u : A.nbl;
+      const uint32_t inext = i + 1 - nbl + (W - 1);
+      if (i + 1 < i0 + SFXM_PAIR_CELLS && inext < A.nx) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) prefetch_l1_row(A.yv[j] + ((uint64_t)inext * A.row[j] + m0));
+      }
+      jacobian_pair_cell<Model, SCHEME, NV, W, RESTRICT>(P, A, x_int, params, param_stride, y, eps, J, r0_out, entry_mask, geom_tab, i, m0);
+    }
   }
 }
 
@@ -1056,8 +1087,9 @@ static int launch_t(const Launch &L) {
     if (g.z > 65535) return set_error("mesh too large for one launch");
     residual_kernel<Model, SCHEME, NV, W><<<g, b, 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.out0, L.out1, L.scalar, L.geom, strip);
   } else if (P.batch >= 64 && P.batch % 2 == 0 && L.geom != nullptr && pair_enabled() && pair_args_fit<NV, W>(P)) {
-    const int64_t gy = P.nx < 65535 ? P.nx : 65535;
-    dim3 g((unsigned)((P.batch / 2 + 31) / 32), (unsigned)gy, (unsigned)((P.nx + gy - 1) / gy));
+    const int64_t ctas = (P.nx + SFXM_PAIR_CELLS - 1) / SFXM_PAIR_CELLS;
+    const int64_t gy = ctas < 65535 ? ctas : 65535;
+    dim3 g((unsigned)((P.batch / 2 + 31) / 32), (unsigned)gy, (unsigned)((ctas + gy - 1) / gy));
     if (g.z > 65535) return set_error("mesh too large for one launch");
     PairArgs<NV> A;
     for (int j = 0; j < NV; ++j) {
