@@ -15,7 +15,8 @@
 #include "sfxm_cpasync.cuh"
 
 #ifndef SFXM_PAIR_MIN_CTAS
-#define SFXM_PAIR_MIN_CTAS 16       // Jacobian pair kernel: 128 registers (20 / 24 CTAs spill and are slower)
+#define SFXM_PAIR_MIN_CTAS 16       // Jacobian pair kernel: 128 registers (20 / 24 CTAs spill and are slower; re-measured on the
+                                    // round-2 kernel, bench shape: 12 CTAs 0.387 ms, 16 0.339, 20 0.357, 24 0.391)
 #endif
 #ifndef SFXM_RES_PAIR_MIN_CTAS
 #define SFXM_RES_PAIR_MIN_CTAS 16   // residual pair kernel: 128 registers (24 CTAs spill: 0.39 ms; 12: 0.28; 16: 0.26)
@@ -617,7 +618,9 @@ struct PairArgs {
 };
 
 #ifndef SFXM_PAIR_CELLS
-#define SFXM_PAIR_CELLS 1           // consecutive cells per one-warp CTA of the ensemble Jacobian kernel
+#define SFXM_PAIR_CELLS 1           // consecutive cells per one-warp CTA of the ensemble Jacobian kernel (2 / 4 cells with the
+                                    // next cell's new row prefetched: 0.343 / 0.339 ms against 0.341 - the load phase is not what
+                                    // binds the kernel; kept at 1)
 #endif
 
 template <class Model, int SCHEME, int NV, int W, bool RESTRICT>

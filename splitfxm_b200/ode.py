@@ -282,6 +282,7 @@ class RK45Stepper:
 class _DeviceJacobian:
     """Stands for the constant Jacobian at y0 (simulation.py:441-443) inside scipy's BDF: `I - c * J` evaluates to a
     token that remembers c, nothing is formed on the host."""
+    __array_ufunc__ = None
 
     def __rmul__(self, c):
         return _ScaledJacobian(float(c))
@@ -303,8 +304,30 @@ class _ShiftedSystem:       # I - c J
 
 
 class _Identity:
+    __array_ufunc__ = None      # numpy scalars defer to __rmul__ instead of broadcasting over the token
+
     def __sub__(self, other):
         return other.__rsub__(self)
+
+    def __rmul__(self, mu):     # Radau: MU / h * I
+        return _ScaledIdentity(mu)
+
+    __mul__ = __rmul__
+
+
+class _ScaledIdentity:          # mu I
+    def __init__(self, mu):
+        self.mu = complex(mu) if np.iscomplexobj(mu) else float(mu)
+
+    def __sub__(self, other):
+        if not isinstance(other, _DeviceJacobian):
+            raise SFXM("device Radau: unexpected linear system")
+        return _MuSystem(self.mu)
+
+
+class _MuSystem:                # mu I - J, mu real or complex
+    def __init__(self, mu):
+        self.mu = mu
 
 
 def device_bdf(eng, y0_dev, split, split_locs, eps=1e-8):
@@ -342,3 +365,105 @@ def device_bdf(eng, y0_dev, split, split_locs, eps=1e-8):
             self.LU = None
 
     return DeviceBDF
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Implicit Radau IIA: scipy's step control, the real and the COMPLEX shifted systems on the device
+# ---------------------------------------------------------------------------------------------------------------------
+def device_radau(eng, y0_dev, split, split_locs, eps=1e-8):
+    """-> a scipy.integrate.Radau subclass for solve_ivp(method=...), or None when a segment is too wide (below).
+
+    scipy's Radau (radau.py `_step_impl`, `solve_collocation_system`) factorises two matrices per step size with the
+    constant Jacobian at y0 the reference hands it (simulation.py:441-443, 468-469): MU_REAL / h I - J (real) and
+    MU_COMPLEX / h I - J (complex), and solves with them in every simplified-Newton iteration.  Here J stays in the banded
+    device layout and both are solved by the block-tridiagonal kernels:
+      * real:    (mu I - J) x = b        <=>  (J - mu I) x = -b                    (the solver's shifted form, shift = -mu);
+      * complex: mu = a + i b, z = x + i y, rhs = p + i q.  Interleaving (x, y) per cell turns every s x s block B of a
+        segment into the 2s x 2s real block [[B, 0], [0, B]] and the diagonal block into [[B_d, b I], [-b I, B_d]] with
+        shift -a: still block-tridiagonal (cyclic wrap blocks included), solved by the same kernel with 2s unknowns per cell.
+    The kernels hold blocks up to 4 x 4, so segments of 1 or 2 variables are served (any split run of <= 2-variable
+    segments, unsplit runs of <= 2 variables); wider segments keep scipy's host factorisation (the caller falls back).
+    Only right-hand sides and solutions cross PCIe."""
+    import ctypes
+    from scipy.integrate import Radau
+    from . import _lib
+    P, segs = eng.problem(split, split_locs)
+    if eng.W != 3 or eng.batch != 1 or any(2 * s > _lib.MAX_NV for _, s in segs):
+        return None
+    dev, nx = eng.device, eng.nx
+    Jb = eng.jacobian(y0_dev, split, split_locs, eps).clone()          # [nx, 3, nv, nv, 1]
+    shift = torch.empty(1, dtype=torch.float64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    sol = torch.zeros((eng.n, 1), dtype=torch.float64, device=dev)
+    lib = eng.lib
+
+    class _ComplexSegment:
+        """One segment's 2s-unknowns-per-cell real form: descriptor, J2 / rhs / solution buffers, workspace."""
+
+        def __init__(self, o, s):
+            self.o, self.s = o, s
+            P2 = _lib.Problem.from_buffer_copy(P)
+            P2.nv = 2 * s
+            for j in range(2 * s):
+                src = o + (j % s)
+                P2.var_base[j], P2.var_stride[j], P2.var_off[j], P2.var_seg[j] = 0, 2 * s, j, 0
+                P2.bc_ltype[j], P2.bc_rtype[j] = P.bc_ltype[src], P.bc_rtype[src]
+            self.P2 = P2
+            self.J2 = torch.zeros((nx, 3, 2 * s, 2 * s, 1), dtype=torch.float64, device=dev)
+            B = Jb[:, :, o:o + s, o:o + s, 0]
+            self.J2[:, :, :s, :s, 0] = B
+            self.J2[:, :, s:, s:, 0] = B
+            self.f2 = torch.empty((nx * 2 * s, 1), dtype=torch.float64, device=dev)
+            self.s2 = torch.zeros((nx * 2 * s, 1), dtype=torch.float64, device=dev)
+            self.work = torch.empty(max(lib.sfxm_pcr_workspace_bytes(ctypes.byref(P2)) // 8, 1), dtype=torch.float64, device=dev)
+            self.beta = 0.0
+
+        def solve(self, mu, rhs_seg):
+            """rhs_seg: complex [nx, s] device tensor -> complex [nx, s] with (mu I - J_seg) z = rhs."""
+            s = self.s
+            if mu.imag != self.beta:                              # the coupling entries of the diagonal blocks
+                r = torch.arange(s, device=dev)
+                self.J2[:, 1, r, s + r, 0] += mu.imag - self.beta
+                self.J2[:, 1, s + r, r, 0] -= mu.imag - self.beta
+                self.beta = mu.imag
+            # (J2 + shift I) v = -f2 with f2 = (Re rhs, Im rhs) per cell, shift = -Re mu
+            self.f2.copy_(torch.cat([rhs_seg.real, rhs_seg.imag], dim=1).reshape(-1, 1))
+            shift.fill_(-mu.real)
+            _lib.check(lib.sfxm_block_tridiag_solve_pcr(ctypes.byref(self.P2), _lib.ptr(self.J2), _lib.ptr(self.f2), _lib.ptr(shift),
+                                                        None, 0, 1, _lib.ptr(self.s2), _lib.ptr(self.work), _lib.ptr(status),
+                                                        _lib.stream_ptr()))
+            _lib.count()
+            v = self.s2.reshape(nx, 2 * s)
+            return torch.complex(v[:, :s], v[:, s:])
+
+    csegs = [_ComplexSegment(o, s) for (o, s) in segs]
+
+    def solve_lu(LU, b):
+        if isinstance(LU.mu, complex):
+            bd = torch.from_numpy(np.ascontiguousarray(b, dtype=np.complex128)).to(dev)
+            out = torch.empty(eng.n, dtype=torch.complex128, device=dev)
+            for c in csegs:       # segment k occupies rows [o nx, (o + s) nx) of the flat vector, cell-major inside
+                lo, hi = c.o * nx, (c.o + c.s) * nx
+                out[lo:hi] = c.solve(LU.mu, bd[lo:hi].reshape(nx, c.s)).reshape(-1)
+            return out.cpu().numpy()
+        f = eng.to_device(np.ascontiguousarray(b, dtype=np.float64))
+        shift.fill_(-LU.mu)
+        eng.solve(Jb, f, sol, split, split_locs, shift=shift, status=status)
+        return sol.cpu().numpy().reshape(-1)
+
+    class DeviceRadau(Radau):
+        def __init__(self, fun, t0, y0, t_bound, **kw):
+            super().__init__(fun, t0, y0, t_bound, **kw)
+            self.J = _DeviceJacobian()
+            self.I = _Identity()
+
+            def lu(A):                      # nothing to factorise: the shifted solve takes mu itself
+                if not isinstance(A, _MuSystem):
+                    raise SFXM("device Radau: unexpected linear system")
+                self.nlu += 1
+                return A
+            self.lu = lu
+            self.solve_lu = solve_lu
+            self.LU_real = self.LU_complex = None
+
+    return DeviceRadau

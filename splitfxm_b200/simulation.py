@@ -269,6 +269,18 @@ class Simulation:
                 from .ode import device_bdf
                 solver = device_bdf(eng, y, split, split_locs)
                 jac = identity(y0.shape[0], format="csc")      # placeholder of the right shape: replaced by the device J
+            elif method == "Radau" and eng.W == 3:
+                # the real and the complex shifted systems of every simplified-Newton iteration on the device
+                # (ode.device_radau); segments wider than two variables keep scipy's host factorisation
+                from scipy.sparse import identity
+                from .ode import device_radau
+                solver = device_radau(eng, y, split, split_locs)
+                if solver is None:
+                    solver = method
+                    jac = self.jacobian(y0, split, split_locs)
+                    eng = self._engine()
+                else:
+                    jac = identity(y0.shape[0], format="csc")
             elif method in JAC_REQUIRED:
                 jac = self.jacobian(y0, split, split_locs)
                 eng = self._engine()

@@ -96,7 +96,12 @@ README_BCS = {
 NEUMANN0 = lambda names: {n: {"left": {"neumann": 0.}, "right": {"neumann": 0.}} for n in names}
 
 
+ONLY = [t for t in os.environ.get("SFXM_GOLDEN_ONLY", "").split(",") if t]   # regenerate just these fixtures
+
+
 def save(name, **kw):
+    if ONLY and name not in ONLY:
+        return
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **kw)
     print(f"wrote {name}.npz ({os.path.getsize(path)} B)")
@@ -270,6 +275,8 @@ evolve_case("evolve_readme_rk45_split", "RK45", 0.25, np.inf, split=True, locs=[
 evolve_case("evolve_rk45_maxstep", "RK45", 0.3, 0.05, nx=40, fv=False)
 evolve_case("evolve_readme_radau", "Radau", 0.1, np.inf)
 evolve_case("evolve_readme_bdf_split", "BDF", 0.2, np.inf, split=True, locs=[1, 2], fv=False)
+evolve_case("evolve_readme_radau_split", "Radau", 0.2, np.inf, split=True, locs=[1, 2])
+evolve_case("evolve_radau_split1_fd", "Radau", 0.2, np.inf, nx=24, split=True, locs=[1], fv=False)
 evolve_case("evolve_readme_rk23", "RK23", 0.1, np.inf)
 evolve_case("evolve_euler", "Euler", 1.0, 0.03, nx=30)
 evolve_case("evolve_euler_split_fd", "Euler", 0.5, 0.01, nx=25, split=True, locs=[1], fv=False)
