@@ -160,6 +160,8 @@ static int newton_fused_common(const sfxm_problem_t *prob, const double *x_int, 
   if (!(eps > 0.0)) return set_error("sfxm_newton_solve_fused: epsilon must be positive");
   if (int e = validate(*prob)) return e;
   if (!sfxm_newton_fused_supported(prob)) return set_error("sfxm_newton_solve_fused: no fused kernel for this model / scheme");
+  if (prob->nx >= ((int64_t)1 << 32) || prob->batch * (int64_t)(SFXM_MAX_NV * (1 + SFXM_MAX_NV) * 8) >= ((int64_t)1 << 32))
+    return set_error("sfxm_newton_solve_fused: batch too large for 32-bit row strides (> 2^24 members)");
   FusedLaunch L{prob, FusedArgs{x_int, params, param_stride, y, eps, geom, 0u, r0}, seg, shift, active, s, work, status,
                 (cudaStream_t)stream, StepUpd{y_upd, norms}};
   int e = -2;

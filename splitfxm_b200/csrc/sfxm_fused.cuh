@@ -84,11 +84,20 @@ struct FusedSrc {
   int64_t seq_next;         // the cell the forward ring expects next (-1: ring not primed)
   double Jseg[3][S][S];
   double rseg[S];
+  static constexpr int KV = Model::kDecoupled ? S : NV;   // state variables this source reads per cell
+  int64_t ybase[KV];        // flat index of (cell 0, variable k, this member); + cell * ystride[k]  (sfxm_thomas.cuh: Rows)
+  uint32_t ystride[KV];
 
   __device__ __forceinline__ FusedSrc(const FusedArgs &args, const sfxm_problem_t &P, int64_t m) : a(args), o(first_var(P, args.mask)) {
     prm_ok = sane(a.eps, 120);
     reps = 1.0 / a.eps;
     seq_next = -1;
+#pragma unroll
+    for (int k = 0; k < KV; ++k) {
+      const int j = Model::kDecoupled ? o + k : k;
+      ybase[k] = (P.var_base[j] + P.var_off[j]) * P.batch + m;
+      ystride[k] = (uint32_t)(P.var_stride[j] * P.batch);
+    }
 #pragma unroll
     for (int k = 0; k < Model::kParams; ++k) {
       prm[k] = __ldg(a.params + (a.pstride ? k * a.pstride + m : k));
@@ -110,11 +119,12 @@ struct FusedSrc {
   // decoupled models, all of them otherwise.  The sweep visits consecutive cells, so every cell is copied from HBM
   // ONCE, kDF - 2 cells ahead of its first use, by cp.async into a per-thread ring in shared memory (slot = cell mod
   // kDF); a jump in the cell sequence drains and re-primes the ring.
-  static constexpr int KV = Model::kDecoupled ? S : NV;
   static constexpr int kDF = 8;
-  __device__ __forceinline__ const double *cell_ptr(const sfxm_problem_t &P, int64_t cell, int k, int64_t m) const {
-    const int j = Model::kDecoupled ? o + k : k;
-    return a.y + (P.var_base[j] + P.var_off[j] + cell * (int64_t)P.var_stride[j]) * P.batch + m;
+  __device__ __forceinline__ int64_t cell_idx(int64_t cell, int k) const {
+    return ybase[k] + (int64_t)((uint64_t)(uint32_t)cell * ystride[k]);
+  }
+  __device__ __forceinline__ const double *cell_ptr(const sfxm_problem_t &, int64_t cell, int k, int64_t) const {
+    return a.y + cell_idx(cell, k);
   }
   __device__ __forceinline__ void window(const sfxm_problem_t &P, int64_t i, int64_t m, double (&w)[3][KV]) {
     __shared__ double ring[kDF][KV][kThomasThreads];
@@ -157,7 +167,7 @@ struct FusedSrc {
         window(P, i, m, w);
 #pragma unroll
         for (int cc = 0; cc < S; ++cc) {
-          off[cc] = (P.var_base[o + cc] + P.var_off[o + cc] + i * (int64_t)P.var_stride[o + cc]) * B + m;
+          off[cc] = cell_idx(i, cc);
 #pragma unroll
           for (int sl = 0; sl < 3; ++sl) {
             us[cc][sl][0] = w[sl][cc];
@@ -191,7 +201,7 @@ struct FusedSrc {
         window(P, i, m, u);
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-          off[j] = (P.var_base[j] + P.var_off[j] + i * (int64_t)P.var_stride[j]) * B + m;
+          off[j] = cell_idx(i, j);
 #pragma unroll
           for (int sl = 0; sl < 3; ++sl) ok = ok & sane(u[sl][j], 120);
         }

@@ -120,6 +120,7 @@ extern "C" int sfxm_block_tridiag_solve(const sfxm_problem_t *prob, const double
   const sfxm_problem_t &P = *prob;
   if (P.nbl != 1 || P.nbr != 1) return set_error("sfxm_block_tridiag_solve: needs a 3-cell stencil (nb 1/1)");
   if (P.nx < 3) return set_error("sfxm_block_tridiag_solve: nx < 3");
+  if (!thomas_rows_fit(P)) return set_error("sfxm_block_tridiag_solve: batch too large for 32-bit row strides (> 2^24 members)");
   cudaStream_t st = (cudaStream_t)stream;
   // segments are runs of equal var_seg
   for (int seg = seg_lo; seg < seg_hi; ++seg) {
