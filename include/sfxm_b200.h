@@ -216,6 +216,36 @@ int sfxm_newton_end(int64_t batch, const int32_t *run, const double *ss, const d
                     double rel_tol, double *crit, int64_t *it, double *dt, const double *r_old_sq, const double *r_new_sq,
                     double dtmax, double *keep_ss, double *keep_yy, void *stream);
 
+/* The whole Newton / Split-Newton loop nest of Simulation.steady_state (simulation.py:474-526; the reference hands it to
+ * the third-party splitnewton: splitnewton.newton / split_newton at :515-523; specification oracle/newton.py) for the
+ * plain configuration - full steps, no pseudo-transient term, no Armijo back-tracking, no bounds - driven from inside the
+ * library: the calls above in the order of splitfxm_b200/newton.py (begin; Jacobian of the segment + block solve +
+ * update/norms, or the fused sweep; end), so that no interpreter sits between the launches.  All buffers are the
+ * caller's.  Loop levels: l = k for the Newton loop of segment k, l = nseg + k0 for the Split-Newton loop over segments
+ * k0.. ; it / crit / run hold one [batch] row per level (2 * nseg rows), any_host one pinned int32 per level.
+ * *result_level receives the level whose `it` row is the iteration count of the run. */
+enum { SFXM_NEWTON_THOMAS = 0, SFXM_NEWTON_PCR = 1, SFXM_NEWTON_BAND4 = 2, SFXM_NEWTON_FUSED_STEP = 3 };
+typedef struct sfxm_newton_plan {
+  const sfxm_problem_t *prob;
+  const double *x_int, *params;
+  int64_t param_stride;
+  const double *geom;
+  double eps, abs_tol, rel_tol;
+  int32_t nseg, solver;                       /* SFXM_NEWTON_* */
+  int64_t row_lo[SFXM_MAX_NV], row_hi[SFXM_MAX_NV]; /* flat rows of segment k */
+  int32_t solve_launches[SFXM_MAX_NV];        /* kernel launches of one solve of segment k (for the launch count only) */
+  double *y, *s, *r, *J;                      /* state (in place), step, residual, banded Jacobian (unfused path) */
+  double *work_solve, *work_norms, *norms2;   /* solver workspace, 2 * sfxm_sumsq_workspace_bytes, [2 * batch] */
+  int32_t *status;
+  int64_t *it;                                /* [2 * nseg, batch] */
+  double *crit;                               /* [2 * nseg, batch] */
+  int32_t *run;                               /* [2 * nseg, batch] */
+  double *seg_ss, *seg_yy;                    /* [nseg, batch] */
+  int32_t *any_dev;                           /* one device word */
+  volatile int32_t *any_host;                 /* [2 * nseg] pinned host words */
+} sfxm_newton_plan_t;
+int sfxm_newton_run(const sfxm_newton_plan_t *plan, double maxiter, int32_t *result_level, int64_t *launches, void *stream);
+
 /* y[q, m] += alpha[m] * s[q, m] for q in [lo, hi) and members with active[m] != 0. */
 int sfxm_axpy_masked(double *y, const double *s, const double *alpha, const int32_t *active, int64_t lo, int64_t hi,
                      int64_t batch, void *stream);

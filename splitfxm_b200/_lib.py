@@ -41,6 +41,29 @@ class Problem(ctypes.Structure):
     ]
 
 
+NEWTON_THOMAS, NEWTON_PCR, NEWTON_BAND4, NEWTON_FUSED_STEP = 0, 1, 2, 3
+
+
+class NewtonPlan(ctypes.Structure):
+    """struct sfxm_newton_plan (include/sfxm_b200.h): the buffers of one Newton / Split-Newton run (sfxm_newton_run)."""
+    _fields_ = [
+        ("prob", ctypes.POINTER(Problem)),
+        ("x_int", c_vp), ("params", c_vp),
+        ("param_stride", c_i64),
+        ("geom", c_vp),
+        ("eps", c_f64), ("abs_tol", c_f64), ("rel_tol", c_f64),
+        ("nseg", c_i32), ("solver", c_i32),
+        ("row_lo", c_i64 * MAX_NV), ("row_hi", c_i64 * MAX_NV),
+        ("solve_launches", c_i32 * MAX_NV),
+        ("y", c_vp), ("s", c_vp), ("r", c_vp), ("J", c_vp),
+        ("work_solve", c_vp), ("work_norms", c_vp), ("norms2", c_vp),
+        ("status", c_vp),
+        ("it", c_vp), ("crit", c_vp), ("run", c_vp),
+        ("seg_ss", c_vp), ("seg_yy", c_vp),
+        ("any_dev", c_vp), ("any_host", c_vp),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/sfxm_b200.h declares
 _PP = ctypes.POINTER(Problem)
 SIGNATURES = {
@@ -73,6 +96,7 @@ SIGNATURES = {
     "sfxm_newton_begin": (ctypes.c_int, [c_i64, c_vp, c_vp, c_vp, c_f64, c_vp, c_f64, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_newton_end": (ctypes.c_int, [c_i64, c_vp, c_vp, c_vp, c_i32, c_f64, c_f64, c_vp, c_vp, c_vp, c_vp, c_vp, c_f64,
                                        c_vp, c_vp, c_vp]),
+    "sfxm_newton_run": (ctypes.c_int, [ctypes.POINTER(NewtonPlan), c_f64, ctypes.POINTER(c_i32), ctypes.POINTER(c_i64), c_vp]),
     "sfxm_axpy_masked": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "sfxm_rk_lincomb": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_f64), c_i32, c_f64, c_vp, c_i64, c_vp]),
     "sfxm_rk_dense_end": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_f64), c_i32, c_f64, c_vp, c_i64, c_vp]),

@@ -18,7 +18,7 @@ if [ -f libsfxm_b200.so ] && [ -z "${SFXM_NVCC_EXTRA}" ]; then
     exit 0
   fi
 fi
-SRCS="sfxm_host sfxm_dispatch sfxm_inst_ad1 sfxm_inst_ad2 sfxm_inst_ad3 sfxm_inst_ad4 sfxm_inst_euler_prim sfxm_inst_euler_cons sfxm_fused_ad3 sfxm_fused_euler sfxm_solve sfxm_newton_ctl sfxm_ode sfxm_selftest sfxm_amr sfxm_pcr sfxm_pcr4 sfxm_spike sfxm_stencil_api"
+SRCS="sfxm_host sfxm_dispatch sfxm_inst_ad1 sfxm_inst_ad2 sfxm_inst_ad3 sfxm_inst_ad4 sfxm_inst_euler_prim sfxm_inst_euler_cons sfxm_fused_ad3 sfxm_fused_euler sfxm_solve sfxm_newton_ctl sfxm_newton_driver sfxm_ode sfxm_selftest sfxm_amr sfxm_pcr sfxm_pcr4 sfxm_spike sfxm_stencil_api"
 for f in $SRCS; do
   if [ ! -f "$f.o" ] || [ "$f.cu" -nt "$f.o" ] || [ sfxm_device.cuh -nt "$f.o" ] || [ sfxm_kernels.cuh -nt "$f.o" ] || [ sfxm_reduce.cuh -nt "$f.o" ] || [ sfxm_pcr.cuh -nt "$f.o" ] || [ sfxm_thomas.cuh -nt "$f.o" ] || [ sfxm_cpasync.cuh -nt "$f.o" ] || [ sfxm_fused.cuh -nt "$f.o" ] || [ ../../include/sfxm_b200.h -nt "$f.o" ] || [ sfxm_host.h -nt "$f.o" ]; then
     "$NVCC" $FLAGS -c "$f.cu" -o "$f.o" &

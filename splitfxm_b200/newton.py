@@ -19,7 +19,9 @@ all masked by the per-member run flags, so an iteration nobody needs is a no-op 
 does the host look at the flag (``_peek`` before, ``_wait`` after).  When the device is already idle the flag is known
 at once and nothing is launched speculatively.
 """
+import ctypes
 import math
+import os
 
 import torch
 
@@ -32,7 +34,7 @@ BOUND_FAC = 0.8
 
 class NewtonDriver:
     def __init__(self, eng, split=False, split_locs=None, dt0=0.0, dtmax=1.0, armijo=False, bounds=None,
-                 bound_fac=BOUND_FAC, eps=1e-8, fused=True):
+                 bound_fac=BOUND_FAC, eps=1e-8, fused=True, native=True):
         if dt0 < 0 or dtmax < 0:
             raise ValueError("Must specify positive dt0 and dtmax")
         self.eng = eng
@@ -72,6 +74,12 @@ class NewtonDriver:
             self._any_host = torch.zeros(4 * (len(self.segs) + 1), dtype=torch.int32).pin_memory()
             self._states, self._reset, self._slots = {}, False, {}
             self._shift = torch.empty(B, dtype=torch.float64, device=dev) if dt0 > 0 else None
+        # plain runs (full steps, no pseudo-transient term / Armijo / bounds) on one process: the whole loop nest is driven
+        # from inside the library (sfxm_newton_run, csrc/sfxm_newton_driver.cu) - the same calls in the same order, without
+        # the interpreter between the launches
+        self.native = bool(native and self._lib is not None and self._speculate and self.dt0 == 0 and not self.armijo
+                           and self.lb is None and os.environ.get("SFXM_NEWTON_NATIVE", "1")[:1] != "0")
+        self._plan = None
 
     def rows(self, k):
         o, s = self.segs[k]
@@ -269,9 +277,71 @@ class NewtonDriver:
                 break
         return it
 
+    # -- the same loop nest inside the library ------------------------------------------------------------
+    def _native_plan(self):
+        from . import _lib
+        eng, B, dev = self.eng, self.eng.batch, self.eng.device
+        P, segs = eng.problem(self.split, self.split_locs)
+        K = len(segs)
+        pl = _lib.NewtonPlan()
+        pl.prob = ctypes.pointer(P)
+        pl.x_int, pl.params, pl.param_stride = _lib.ptr(eng.x_int), _lib.ptr(eng.params), eng.param_stride
+        pl.geom = _lib.ptr(eng._geom)
+        pl.eps, pl.abs_tol, pl.rel_tol = float(self.eps), ABS_TOL, REL_TOL
+        pl.nseg = K
+        keep = {"P": P}
+        if self.fused:
+            pl.solver = _lib.NEWTON_FUSED_STEP
+            keep["work"] = eng._scratch("solve", eng.lib.sfxm_solve_workspace_bytes(ctypes.byref(P)) // 8)
+        else:
+            if eng.W == 4:
+                pl.solver, nbytes = _lib.NEWTON_BAND4, eng.lib.sfxm_band4_workspace_bytes(ctypes.byref(P))
+                keep["work"] = eng._scratch("band4", nbytes // 8)
+            elif B >= 2048:
+                pl.solver, nbytes = _lib.NEWTON_THOMAS, eng.lib.sfxm_solve_workspace_bytes(ctypes.byref(P))
+                keep["work"] = eng._scratch("solve", nbytes // 8)
+            else:
+                pl.solver, nbytes = _lib.NEWTON_PCR, eng.lib.sfxm_pcr_workspace_bytes(ctypes.byref(P))
+                keep["work"] = eng._scratch("pcr", nbytes // 8)
+            keep["J"] = eng.jacobian_buffer()
+            keep["wn"] = eng._scratch("norms2", 2 * eng.lib.sfxm_sumsq_workspace_bytes(eng.n, B) // 8)
+            pl.J, pl.work_norms, pl.r = _lib.ptr(keep["J"]), _lib.ptr(keep["wn"]), _lib.ptr(self.r)
+        for k in range(K):
+            pl.row_lo[k], pl.row_hi[k] = self.rows(k)
+            if pl.solver == _lib.NEWTON_BAND4:
+                pl.solve_launches[k] = 2 + max((eng.nx + 1) // 2 - 1, 1).bit_length()
+            elif pl.solver == _lib.NEWTON_PCR:
+                pl.solve_launches[k] = eng._pcr_launches(P, segs[k])
+            else:
+                pl.solve_launches[k] = 1
+        keep["it"] = torch.zeros((2 * K, B), dtype=torch.int64, device=dev)
+        keep["crit"] = torch.zeros((2 * K, B), dtype=torch.float64, device=dev)
+        keep["run"] = torch.zeros((2 * K, B), dtype=torch.int32, device=dev)
+        keep["norms2"] = torch.zeros(2 * B, dtype=torch.float64, device=dev)
+        keep["any_host"] = torch.zeros(2 * K, dtype=torch.int32).pin_memory()
+        pl.work_solve, pl.norms2, pl.status, pl.s = _lib.ptr(keep["work"]), _lib.ptr(keep["norms2"]), _lib.ptr(self.status), _lib.ptr(self.s)
+        pl.it, pl.crit, pl.run = _lib.ptr(keep["it"]), _lib.ptr(keep["crit"]), _lib.ptr(keep["run"])
+        pl.seg_ss, pl.seg_yy = _lib.ptr(self.seg_ss), _lib.ptr(self.seg_yy)
+        pl.any_dev, pl.any_host = _lib.ptr(self._any), keep["any_host"].data_ptr()
+        return pl, keep
+
+    def _run_native(self, y, maxiter):
+        from . import _lib
+        if self._plan is None:
+            self._plan = self._native_plan()
+        pl, keep = self._plan
+        pl.y = _lib.ptr(y)
+        level, launches = ctypes.c_int32(0), ctypes.c_int64(0)
+        _lib.check(self._lib.sfxm_newton_run(ctypes.byref(pl), float(min(maxiter, 1e300)), ctypes.byref(level),
+                                             ctypes.byref(launches), _lib.stream_ptr()))
+        _lib.count(int(launches.value))
+        return keep["it"][level.value].clone()
+
     def run(self, y, maxiter=math.inf):
         """In place on y [n, batch]; returns per-member iteration counts (int64 [batch])."""
         self.check_initial(y)
+        if self.native:
+            return self._run_native(y, maxiter)
         if len(self.segs) == 1:
             return self.newton_segment(y, 0, maxiter, None).clone()
         return self.split_newton(y, 0, maxiter, None).clone()
