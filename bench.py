@@ -534,22 +534,35 @@ def newton_leg(args, torch, dist, ens, Y_host, dev, world, total, barrier, peak)
     ms = float(t[0]) / steps
     res = float(torch.max(torch.abs(eng.residual(Yf, None, SPLIT, LOCS))))
     it_lo, it_hi = int(its.min()), int(its.max())
-    out_host = torch.empty((eng.n, B), dtype=torch.float64).pin_memory()
-    its_host = torch.empty(B, dtype=torch.int64).pin_memory()
-    for _ in range(2):
-        ens.steady_state_host(Y_host, out_host, its_host, SPLIT, LOCS)
+    # end to end: two slots (device state buffers + pinned result buffers); the download of a step overlaps the upload and
+    # the solve of the next one, and the next step's upload runs while this step's Newton iterations do
+    outs = [torch.empty((eng.n, B), dtype=torch.float64).pin_memory() for _ in range(2)]
+    itss = [torch.empty(B, dtype=torch.int64).pin_memory() for _ in range(2)]
+    out_host, its_host = outs[0], itss[0]
+    esteps = max(steps, 12)
+
+    def e2e_pass(n):
+        for k in range(n):
+            ens.steady_state_host(Y_host, outs[k % 2], itss[k % 2], SPLIT, LOCS, slot=k % 2,
+                                  next_Y_host=Y_host if k + 1 < n else None)
+        ens.sync_host()
+
+    e2e_pass(3)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with quiet_host():
         e0.record()
-        for _ in range(steps):
-            ens.steady_state_host(Y_host, out_host, its_host, SPLIT, LOCS)
+        w0 = time.perf_counter()
+        e2e_pass(esteps)
+        wall_ms = (time.perf_counter() - w0) * 1e3
         e1.record()
         barrier()
-    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    # the pass ends with sync_host() (all three streams drained): wall clock and the event pair bracket the same work;
+    # take the larger of the two, then the max over ranks
+    te = torch.tensor([max(e0.elapsed_time(e1), wall_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    ms_e = float(te[0]) / steps
+    ms_e = float(te[0]) / esteps
     # linear-solve sweeps actually run: per outer iteration the inner segment is solved to convergence, then one step
     # on the outer segment; fused algorithmic bytes per cell-member per sweep: s = 1 -> 48, s = 2 -> 128
     return {"metric": NEWTON_METRIC, "value": total / (ms * 1e-3), "unit": NEWTON_UNIT, "steps": steps, "ms_per_step": ms,
@@ -557,8 +570,11 @@ def newton_leg(args, torch, dist, ens, Y_host, dev, world, total, barrier, peak)
             "per_step_ms_rank0": [round(v, 3) for v in per_step], "host_ms_per_call_rank0": [round(1e3 * v, 3) for v in host_s],
             "e2e": {"value": total / (ms_e * 1e-3), "unit": NEWTON_UNIT, "ms_per_step": ms_e,
                     "h2d_bytes_per_step": int(Y_host.numel() * 8), "d2h_bytes_per_step": int(out_host.numel() * 8 + B * 8),
+                    "steps": esteps,
                     "api": "EnsembleSimulation.steady_state_host(pinned host states -> pinned host steady states + "
-                           "iteration counts)", "checksum": float(out_host[:, 0].sum())}}
+                           "iteration counts), 2 slots over 3 streams: the download of a step overlaps the upload and the "
+                           "solve of the next, the next upload runs during this step's Newton iterations",
+                    "checksum": float(out_host[:, 0].sum())}}
 
 
 def slab_leg(args, torch, dist, sf, dev, rank, world, peak):

@@ -107,6 +107,8 @@ class EnsembleSimulation:
         return out_host
 
     def sync_host(self):
+        if hasattr(self, "_ss_up"):
+            self._ss_up.synchronize()
         if hasattr(self, "_copy_stream"):
             self._copy_stream.synchronize()
         torch.cuda.current_stream().synchronize()
@@ -126,24 +128,71 @@ class EnsembleSimulation:
         return y, its
 
     def steady_state_host(self, Y_host, out_host, its_host, split=False, split_locs=None, dt0=0.0, dtmax=1.0,
-                          armijo=False, bounds=None, maxiter=math.inf):
+                          armijo=False, bounds=None, maxiter=math.inf, slot=None, next_Y_host=None):
         """Host buffers in, host buffers out: Y_host [n, batch] (pinned) is uploaded, every member is Newton-solved on
         the device, and the final states / iteration counts are downloaded into out_host [n, batch] / its_host [batch]
-        (pinned).  Synchronous: returns when the results are in host memory."""
+        (pinned).
+
+        slot = None: synchronous - returns when the results are in host memory.
+        slot = 0 / 1: pipelined over three streams (upload, solve, download) and two device state buffers: the download
+        of one step overlaps the upload and the solve of the next, and `next_Y_host` (the input of the NEXT call, which
+        must use the other slot) is uploaded while this call's Newton iterations run.  Call `sync_host()` before reading
+        `out_host` / `its_host`."""
         eng = self.eng
-        if not hasattr(self, "_ss_state"):
-            self._ss_state = torch.empty((eng.n, eng.batch), dtype=torch.float64, device=eng.device)
-        y = self._ss_state
-        y.copy_(Y_host, non_blocking=True)
         key = (bool(split), tuple(split_locs) if split_locs else None, float(dt0), float(dtmax), bool(armijo), bounds is None)
         drv = getattr(self, "_ss_driver", None)
         if drv is None or self._ss_key != key or bounds is not None:
             drv = NewtonDriver(eng, split, split_locs, dt0, dtmax, armijo, bounds)
             self._ss_driver, self._ss_key = drv, key
-        its = drv.run(y, maxiter)
-        out_host.copy_(y, non_blocking=True)
-        its_host.copy_(its, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        if slot is None:
+            if not hasattr(self, "_ss_state"):
+                self._ss_state = torch.empty((eng.n, eng.batch), dtype=torch.float64, device=eng.device)
+            y = self._ss_state
+            y.copy_(Y_host, non_blocking=True)
+            its = drv.run(y, maxiter)
+            out_host.copy_(y, non_blocking=True)
+            its_host.copy_(its, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return out_host, its_host
+        if not hasattr(self, "_ss_slots"):
+            self._ss_slots = {}
+            self._ss_up = torch.cuda.Stream(device=eng.device)
+            if not hasattr(self, "_copy_stream"):
+                self._copy_stream = torch.cuda.Stream(device=eng.device)
+
+        def slot_state(k):
+            st = self._ss_slots.get(k)
+            if st is None:
+                st = {"y": torch.empty((eng.n, eng.batch), dtype=torch.float64, device=eng.device),
+                      "its": torch.empty(eng.batch, dtype=torch.int64, device=eng.device),
+                      "up": torch.cuda.Event(), "done": torch.cuda.Event(), "free": torch.cuda.Event(), "loaded": None}
+                st["free"].record()
+                self._ss_slots[k] = st
+            return st
+
+        def upload(st, src):
+            with torch.cuda.stream(self._ss_up):
+                self._ss_up.wait_event(st["free"])       # the previous download from this slot has finished
+                st["y"].copy_(src, non_blocking=True)
+                st["up"].record(self._ss_up)
+            st["loaded"] = src
+
+        st = slot_state(slot)
+        if st["loaded"] is not Y_host:
+            upload(st, Y_host)
+        if next_Y_host is not None:
+            upload(slot_state(1 - slot), next_Y_host)    # overlaps this call's Newton iterations
+        main = torch.cuda.current_stream()
+        main.wait_event(st["up"])
+        its = drv.run(st["y"], maxiter)
+        st["its"].copy_(its)
+        st["done"].record(main)
+        st["loaded"] = None
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(st["done"])
+            out_host.copy_(st["y"], non_blocking=True)
+            its_host.copy_(st["its"], non_blocking=True)
+            st["free"].record(self._copy_stream)
         return out_host, its_host
 
     def evolve_euler(self, Y, t_diff, max_step, split=False, split_locs=None):

@@ -97,3 +97,40 @@ def test_ensemble_fused_sweeps_members_with_different_counts():
     from splitfxm_b200.newton import NewtonDriver
     assert NewtonDriver(ens.eng, True, [1]).fused
     _both(ens.eng, Y0, True, [1])
+
+
+def test_pipelined_host_steady_states_equal_the_synchronous_call():
+    """EnsembleSimulation.steady_state_host with slots (upload / solve / download on three streams, the next input
+    prefetched during the Newton iterations) against the synchronous call, alternating two different inputs."""
+    import torch
+    import splitfxm_b200 as sf
+    from splitfxm_b200.ensemble import EnsembleSimulation
+    B = 2048
+    d = sf.Domain.from_size(40, 1, 1, ["u", "v", "w"])
+    bcs = {"u": {"left": {"dirichlet": 1.0}, "right": {"dirichlet": 0.0}},
+           "v": {"left": {"dirichlet": 3}, "right": {"dirichlet": 4}},
+           "w": {"left": {"dirichlet": 2}, "right": {"neumann": 0.0}}}
+    ens = EnsembleSimulation(d, "ad", {"c": np.linspace(0.05, 0.5, B), "nu": np.logspace(-2, -1, B)}, bcs,
+                             sf.FDSchemes.CENTRAL, method="FDM")
+    rng = np.random.default_rng(11)
+    n = ens.eng.n
+    inputs = [torch.from_numpy(rng.random((n, B))).pin_memory() for _ in range(2)]
+    refs = []
+    for Y in inputs:
+        out = torch.empty((n, B), dtype=torch.float64).pin_memory()
+        its = torch.empty(B, dtype=torch.int64).pin_memory()
+        ens.steady_state_host(Y, out, its, True, [1])
+        refs.append((out.clone(), its.clone()))
+    outs = [torch.empty((n, B), dtype=torch.float64).pin_memory() for _ in range(2)]
+    itss = [torch.empty(B, dtype=torch.int64).pin_memory() for _ in range(2)]
+    steps = 5
+    for k in range(steps):
+        nxt = inputs[(k + 1) % 2] if k + 1 < steps else None
+        ens.steady_state_host(inputs[k % 2], outs[k % 2], itss[k % 2], True, [1], slot=k % 2, next_Y_host=nxt)
+        if k >= 1:                       # the other slot's result: complete once its download event has passed
+            ens._ss_slots[(k - 1) % 2]["free"].synchronize()
+            assert torch.equal(outs[(k - 1) % 2], refs[(k - 1) % 2][0])
+            assert torch.equal(itss[(k - 1) % 2], refs[(k - 1) % 2][1])
+    ens.sync_host()
+    assert torch.equal(outs[(steps - 1) % 2], refs[(steps - 1) % 2][0])
+    assert torch.equal(itss[(steps - 1) % 2], refs[(steps - 1) % 2][1])
