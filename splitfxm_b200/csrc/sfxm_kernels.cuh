@@ -327,7 +327,8 @@ residual_warp_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
   double uc[NV], Fc[NV], Dc[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
-    off[j] = (P.var_base[j] + P.var_off[j] + i * (int64_t)P.var_stride[j]) * B + m;
+    // (32-bit row lengths: one multiply-add per address; nx * nv * batch < 2^32 is checked by the launcher)
+    off[j] = (P.var_base[j] + P.var_off[j]) * B + m + (int64_t)((uint64_t)(uint32_t)i * (uint32_t)(P.var_stride[j] * (int32_t)B));
     uc[j] = __ldg(y + off[j]);
   }
   const double xc = __ldg(x_int + i);
@@ -340,25 +341,34 @@ residual_warp_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
   }
   double sigma_c = 0.0;
   if constexpr (SCHEME == SFXM_FV_LAX_FRIEDRICHS) sigma_c = Model::sigma(prm, uc);
-  // stencil slot s of lane l is lane l - nbl + s
+  // stencil slot s of lane l is lane l - nbl + s; the lane's own slot needs no exchange
   double u[W][NV], Fv[W][NV], Dv[W][NV], xs[W];
 #pragma unroll
   for (int s = 0; s < W; ++s) {
     const int src = lane - nbl + s;
-    xs[s] = __shfl_sync(0xffffffffu, xc, src);
+    const bool own = (W == 3) && s == 1;                  // (4-cell stencils: the own slot is nbl, a run-time value)
+    xs[s] = own ? xc : __shfl_sync(0xffffffffu, xc, src);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      u[s][j] = __shfl_sync(0xffffffffu, uc[j], src);
-      Fv[s][j] = __shfl_sync(0xffffffffu, Fc[j], src);
-      Dv[s][j] = Model::kHasDiffusion ? __shfl_sync(0xffffffffu, Dc[j], src) : 0.0;
+      u[s][j] = own ? uc[j] : __shfl_sync(0xffffffffu, uc[j], src);
+      Fv[s][j] = own ? Fc[j] : __shfl_sync(0xffffffffu, Fc[j], src);
+      Dv[s][j] = Model::kHasDiffusion ? (own ? Dc[j] : __shfl_sync(0xffffffffu, Dc[j], src)) : 0.0;
     }
   }
   if (lane < nbl || lane >= 32 - nbr) return;             // feeder lanes are done
   Geom<SCHEME, W> geom(xs);
-  geom.and_inputs(u, prm);
   double r[NV];
-  if (geom.fast) cell_combine<Model, SCHEME, NV, W, true>(prm, u, Fv, Dv, sigma_c, geom, r);
-  else cell_combine<Model, SCHEME, NV, W, false>(prm, u, Fv, Dv, sigma_c, geom, r);
+  // the range check guards div_known; a finite-volume scheme without diffusion has no quotient by a known divisor at all
+  // (fv_transport.py:58 multiplies by 1 / dx), so both instantiations are the same arithmetic
+  constexpr bool kNoKnownDivision = !Model::kHasDiffusion && (SCHEME == SFXM_FV_LAX_FRIEDRICHS || SCHEME == SFXM_FV_CENTRAL ||
+                                                              SCHEME == SFXM_FV_UPWIND);
+  if constexpr (kNoKnownDivision) {
+    cell_combine<Model, SCHEME, NV, W, false>(prm, u, Fv, Dv, sigma_c, geom, r);
+  } else {
+    geom.and_inputs(u, prm);
+    if (geom.fast) cell_combine<Model, SCHEME, NV, W, true>(prm, u, Fv, Dv, sigma_c, geom, r);
+    else cell_combine<Model, SCHEME, NV, W, false>(prm, u, Fv, Dv, sigma_c, geom, r);
+  }
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     if (r_out) r_out[off[j]] = r[j];
@@ -1079,7 +1089,7 @@ static int launch_t(const Launch &L) {
       residual_pair_kernel<Model, SCHEME, NV, W, true><<<g, dim3(32, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.out0, L.out1, L.scalar, L.geom, strip);
     else
       residual_pair_kernel<Model, SCHEME, NV, W, false><<<g, dim3(32, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.out0, L.out1, L.scalar, L.geom, strip);
-  } else if (L.op == OP_RESIDUAL && P.batch < 32 && !Model::kDecoupled && warp_enabled()) {
+  } else if (L.op == OP_RESIDUAL && P.batch < 32 && !Model::kDecoupled && warp_enabled() && P.nx < ((int64_t)1 << 32)) {
     const int per_warp = 32 - (W - 1);
     const int64_t warps = (P.nx + per_warp - 1) / per_warp;
     dim3 g((unsigned)((warps + 7) / 8), (unsigned)P.batch);
