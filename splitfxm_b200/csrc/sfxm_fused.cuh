@@ -85,7 +85,7 @@ struct FusedSrc {
   double Jseg[3][S][S];
   double rseg[S];
   static constexpr int KV = Model::kDecoupled ? S : NV;   // state variables this source reads per cell
-  int64_t ybase[KV];        // flat index of (cell 0, variable k, this member); + cell * ystride[k]  (sfxm_thomas.cuh: Rows)
+  int64_t ybase[KV];        // flat index of (cell 0, variable k, this member); + cell * ystride[k] (32-bit row length)
   uint32_t ystride[KV];
 
   __device__ __forceinline__ FusedSrc(const FusedArgs &args, const sfxm_problem_t &P, int64_t m) : a(args), o(first_var(P, args.mask)) {

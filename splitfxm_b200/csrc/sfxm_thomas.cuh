@@ -15,49 +15,14 @@ namespace sfxm {
 // ahead into L1 (profile r1h: without it each iteration costs ~1500 cycles, one exposed HBM latency).
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// Addresses inside the sweeps.  Every array here is member-fastest with rows that are a fixed number of elements apart:
-// address(row i, entry e) = base + i * row + e * batch + m.  The part that does not change along a sweep (array base,
-// first entry, member) is folded into `base` once and the row length is kept as a 32-bit byte count, so that an address
-// costs ONE 32 x 32 -> 64-bit multiply-add (IMAD.WIDE.U32) instead of a chain of 64-bit products of descriptor fields
-// (SASS of the round-2a kernels: 217 UIMAD + 212 IMAD + 141 UIADD3 + 106 LEA of 1575 instructions, 136 of them FP64).
-// Needs nx < 2^32 and row bytes < 2^32 (checked on the host, thomas_rows_fit).
-struct Rows {
-  char *base;
-  uint32_t row;   // bytes from one row to the next
-  __device__ __forceinline__ Rows() : base(nullptr), row(0) {}
-  __device__ __forceinline__ Rows(const double *p, int64_t first_elem, int64_t row_elems)
-      : base(reinterpret_cast<char *>(const_cast<double *>(p)) + first_elem * 8), row((uint32_t)(row_elems * 8)) {}
-  __device__ __forceinline__ double *at(int64_t i) const {
-    return reinterpret_cast<double *>(base + (uint64_t)(uint32_t)i * row);
-  }
-};
-// entry e (compile-time) of a row: e * batch elements further
-__device__ __forceinline__ double *entry(double *row, int e, uint32_t B) { return row + (size_t)((uint32_t)e * B); }
-__device__ __forceinline__ const double *entry(const double *row, int e, uint32_t B) { return row + (size_t)((uint32_t)e * B); }
+// (Round 2, second half: the addresses inside the sweeps were rewritten as base + i * row with 32-bit row lengths - one
+// IMAD.WIDE.U32 per address, 1575 -> 1147 and 2017 -> 1476 static instructions for the fused s = 1 / s = 2 kernels.  Times:
+// fused sweeps 0.42 + 0.65 ms either way, assembled-J sweeps (MemSrc) 0.944 -> 1.003 ms: the sweeps are bound by their
+// dependent chains at 8-14 resident warps per SM, not by instruction count, and the extra live registers cost more than
+// the integer work they save; removed.  The fused row source keeps its 32-bit row strides, sfxm_fused.cuh.)
 inline bool thomas_rows_fit(const sfxm_problem_t &P) {
   return P.nx < ((int64_t)1 << 32) && P.batch * (int64_t)(SFXM_MAX_NV * (1 + SFXM_MAX_NV) * 8) < ((int64_t)1 << 32);
 }
-
-// flat index of unknown (row i, variable o + r) of the segment, per r: base + i * stride (elements)
-template <int S>
-struct FlatRows {
-  int64_t base[S];
-  uint32_t stride[S];
-  __device__ __forceinline__ FlatRows(const sfxm_problem_t &P, int o, int64_t m) {
-#pragma unroll
-    for (int r = 0; r < S; ++r) {
-      base[r] = (P.var_base[o + r] + P.var_off[o + r]) * P.batch + m;
-      stride[r] = (uint32_t)(P.var_stride[o + r] * P.batch);
-    }
-  }
-  __device__ __forceinline__ int64_t operator()(int64_t i, int r) const {
-    int64_t b = base[0];
-    uint32_t st = stride[0];
-#pragma unroll
-    for (int k = 1; k < S; ++k) { b = (k == r) ? base[k] : b; st = (k == r) ? stride[k] : st; }
-    return b + (int64_t)((uint64_t)(uint32_t)i * st);
-  }
-};
 // The back substitution re-reads the C' / rhs' rows the forward sweep wrote; its iterations are short (s^2 FMAs), so the
 // rows are fetched kRingDepth iterations ahead with cp.async into a per-thread ring in shared memory (thread-private
 // columns: no barrier needed, cp.async.wait_group orders the thread's own copies).  One-warp CTAs only.
@@ -113,6 +78,17 @@ __device__ __forceinline__ bool gj_solve(double (&A)[S][S], double (&R)[S][NC]) 
   return ok;
 }
 
+// J block (i, slot d) restricted to rows/cols [o, o+S)
+template <int NV, int S>
+__device__ __forceinline__ void load_block(const double *__restrict__ J, int64_t i, int d, int o, int64_t B, int64_t m,
+                                           double (&blk)[S][S]) {
+  const double *p = J + ((i * 3 + d) * (int64_t)(NV * NV)) * B + m;
+#pragma unroll
+  for (int r = 0; r < S; ++r)
+#pragma unroll
+    for (int c = 0; c < S; ++c) blk[r][c] = __ldg(p + (int64_t)((o + r) * NV + (o + c)) * B);
+}
+
 // Row source that reads an assembled banded Jacobian and residual from memory (sfxm_jacobian's layout).
 template <int NV>
 struct MemSrc {
@@ -120,38 +96,29 @@ struct MemSrc {
   struct Args {
     const double *J, *f;
   };
-  Rows Jrows;                // block row i of this member: J + (i * 3 NV^2) * batch + m
-  const double *f;
-  uint32_t B;
-  __device__ __forceinline__ MemSrc(const Args &a, const sfxm_problem_t &P, int64_t m)
-      : Jrows(a.J, m, (int64_t)(3 * NV * NV) * P.batch), f(a.f), B((uint32_t)P.batch) {}
+  const double *J, *f;
+  __device__ __forceinline__ MemSrc(const Args &a, const sfxm_problem_t &, int64_t) : J(a.J), f(a.f) {}
   __device__ __forceinline__ void prepare(const sfxm_problem_t &, int64_t, int64_t) {}
-  __device__ __forceinline__ int64_t fidx(const sfxm_problem_t &P, int64_t i, int v, int64_t m) const {
-    return (P.var_base[v] + P.var_off[v]) * P.batch + m + (int64_t)((uint64_t)(uint32_t)i * (uint32_t)(P.var_stride[v] * P.batch));
-  }
   // request the blocks and the right-hand side of block row i (a row the sweep reaches a few iterations later)
   template <int S>
   __device__ __forceinline__ void prefetch(const sfxm_problem_t &P, int64_t i, int o, int64_t m) const {
-    const double *p = Jrows.at(i);
+    const double *p = J + (i * 3) * (int64_t)(NV * NV) * P.batch + m;
 #pragma unroll
     for (int d = 0; d < 3; ++d)
 #pragma unroll
       for (int r = 0; r < S; ++r)
 #pragma unroll
-        for (int c = 0; c < S; ++c) prefetch_l1(p + (size_t)((uint32_t)((d * NV + o + r) * NV + (o + c)) * B));
-#pragma unroll
-    for (int r = 0; r < S; ++r) prefetch_l1(f + fidx(P, i, o + r, m));
-  }
-  template <int S>
-  __device__ __forceinline__ void block(const sfxm_problem_t &, int64_t i, int d, int o, int64_t, double (&blk)[S][S]) const {
-    const double *p = Jrows.at(i);
+        for (int c = 0; c < S; ++c) prefetch_l1(p + (int64_t)((d * NV + o + r) * NV + (o + c)) * P.batch);
 #pragma unroll
     for (int r = 0; r < S; ++r)
-#pragma unroll
-      for (int c = 0; c < S; ++c) blk[r][c] = __ldg(p + (size_t)((uint32_t)((d * NV + o + r) * NV + (o + c)) * B));
+      prefetch_l1(f + (P.var_base[o + r] + i * (int64_t)P.var_stride[o + r] + P.var_off[o + r]) * P.batch + m);
+  }
+  template <int S>
+  __device__ __forceinline__ void block(const sfxm_problem_t &P, int64_t i, int d, int o, int64_t m, double (&blk)[S][S]) const {
+    load_block<NV, S>(J, i, d, o, P.batch, m, blk);
   }
   __device__ __forceinline__ double rhs(const sfxm_problem_t &P, int64_t i, int o, int r, int64_t m) const {
-    return __ldg(f + fidx(P, i, o + r, m));
+    return __ldg(f + (P.var_base[o + r] + i * (int64_t)P.var_stride[o + r] + P.var_off[o + r]) * P.batch + m);
   }
 };
 
@@ -219,10 +186,7 @@ block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __gri
   bool ok = true;
   StepSink sink(s_out, upd);
   double Cp[S][S], Rp[S][NR];   // C'_{i-1}, rhs'_{i-1}
-  const uint32_t B32 = (uint32_t)B;
-  const FlatRows<S> fidx(P, o, m);
-  const Rows wC(workC, (int64_t)(o * NV + o) * B + m, (int64_t)(NV * NV) * B);                 // entry (r, c): + (r NV + c) batch
-  const Rows wR(workR, (int64_t)(o * (1 + NV)) * B + m, (int64_t)(NV * (1 + NV)) * B);         // entry (r, k): + (r (1 + NV) + k) batch
+  auto fidx = [&](int64_t i, int r) { return (P.var_base[o + r] + i * (int64_t)P.var_stride[o + r] + P.var_off[o + r]) * B + m; };
   for (int64_t i = 0; i < ne; ++i) {
     double A[S][S], Bd[S][S], R[S][NC];
     if (i + PrefetchDist<S>::value < n) src.template prefetch<S>(P, i + PrefetchDist<S>::value, o, m);
@@ -266,18 +230,17 @@ block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __gri
       }
     }
     ok = gj_solve<S, NC>(Bd, R) && ok;
-    double *const pC = wC.at(i), *const pR = wR.at(i);
 #pragma unroll
     for (int r = 0; r < S; ++r) {
 #pragma unroll
       for (int c = 0; c < S; ++c) {
         Cp[r][c] = R[r][c];
-        *entry(pC, r * NV + c, B32) = R[r][c];
+        workC[(i * (int64_t)(NV * NV) + (o + r) * NV + (o + c)) * B + m] = R[r][c];
       }
 #pragma unroll
       for (int c = 0; c < NR; ++c) {
         Rp[r][c] = R[r][S + c];
-        if (CYCLIC || i < ne - 1) *entry(pR, r * (1 + NV) + c, B32) = R[r][S + c];
+        if (CYCLIC || i < ne - 1) workR[((i * NV + (o + r)) * (int64_t)(1 + NV) + c) * B + m] = R[r][S + c];
       }
     }
   }
@@ -294,7 +257,7 @@ block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __gri
 #pragma unroll
     for (int r = 0; r < S; ++r)
 #pragma unroll
-      for (int c = 0; c < NR; ++c) *entry(wR.at(ne - 1), r * (1 + NV) + c, B32) = X[r][c];
+      for (int c = 0; c < NR; ++c) workR[(((ne - 1) * NV + (o + r)) * (int64_t)(1 + NV) + c) * B + m] = X[r][c];
   }
   double Xfirst[S][NR];   // X_0 (needed by the last row in the cyclic case)
 #pragma unroll
@@ -314,13 +277,14 @@ block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __gri
   auto issue = [&](int64_t row) {     // one commit group per call, empty past the first row: uniform group count
     if (row >= 0) {
       const int slot = (int)(row & (DB - 1));
-      const double *const qC = wC.at(row), *const qR = wR.at(row);
 #pragma unroll
       for (int r = 0; r < S; ++r) {
 #pragma unroll
-        for (int c = 0; c < S; ++c) cp_async8(&ring[slot][r * S + c][tx], entry(qC, r * NV + c, B32));
+        for (int c = 0; c < S; ++c)
+          cp_async8(&ring[slot][r * S + c][tx], workC + (row * (int64_t)(NV * NV) + (o + r) * NV + (o + c)) * B + m);
 #pragma unroll
-        for (int c = 0; c < NR; ++c) cp_async8(&ring[slot][S * S + r * NR + c][tx], entry(qR, r * (1 + NV) + c, B32));
+        for (int c = 0; c < NR; ++c)
+          cp_async8(&ring[slot][S * S + r * NR + c][tx], workR + ((row * NV + (o + r)) * (int64_t)(1 + NV) + c) * B + m);
         if (upd_y) cp_async8(&ring[slot][KB + r][tx], upd.y + fidx(row, r));
       }
     }
@@ -362,7 +326,7 @@ block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __gri
 #pragma unroll
       for (int r = 0; r < S; ++r)
 #pragma unroll
-        for (int c = 0; c < NR; ++c) *entry(wR.at(i), r * (1 + NV) + c, B32) = X[r][c];
+        for (int c = 0; c < NR; ++c) workR[((i * NV + (o + r)) * (int64_t)(1 + NV) + c) * B + m] = X[r][c];
       if (i == 0) {
 #pragma unroll
         for (int r = 0; r < S; ++r)
@@ -406,7 +370,7 @@ block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __gri
         for (int r = 0; r < S; ++r)
 #pragma unroll
           for (int c = 0; c < NR; ++c)
-            prefetch_l1(entry(wR.at(i + PrefetchDist<S>::value), r * (1 + NV) + c, B32));
+            prefetch_l1(workR + (((i + PrefetchDist<S>::value) * NV + (o + r)) * (int64_t)(1 + NV) + c) * B + m);
         if (upd.y) {
 #pragma unroll
           for (int r = 0; r < S; ++r) prefetch_l1(upd.y + fidx(i + PrefetchDist<S>::value, r));
@@ -414,10 +378,10 @@ block_thomas_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __gri
       }
 #pragma unroll
       for (int r = 0; r < S; ++r) {
-        const double *w = entry(wR.at(i), r * (1 + NV), B32);
+        const double *w = workR + ((i * NV + (o + r)) * (int64_t)(1 + NV)) * B + m;
         double xv = w[0];
 #pragma unroll
-        for (int c = 0; c < S; ++c) xv -= w[(size_t)((uint32_t)(1 + c) * B32)] * rhs[c][0];
+        for (int c = 0; c < S; ++c) xv -= w[(int64_t)(1 + c) * B] * rhs[c][0];
         sink.put(fidx(i, r), xv);
       }
     }
@@ -446,10 +410,7 @@ block_thomas_ll_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __
   const int64_t n = P.nx;
   bool ok = true;
   StepSink sink(s_out, upd);
-  const uint32_t B32 = (uint32_t)B;
-  const FlatRows<S> fidx(P, o, m);
-  const Rows wC(workC, (int64_t)(o * NV + o) * B + m, (int64_t)(NV * NV) * B);                 // entry (r, c): + (r NV + c) batch
-  const Rows wR(workR, (int64_t)(o * (1 + NV)) * B + m, (int64_t)(NV * (1 + NV)) * B);         // entry (r, k): + (r (1 + NV) + k) batch
+  auto fidx = [&](int64_t i, int r) { return (P.var_base[o + r] + i * (int64_t)P.var_stride[o + r] + P.var_off[o + r]) * B + m; };
   double G[S][S], Alast[S][S], Blast[S][S], dl[S];
   src.prepare(P, n - 1, m);
   src.template block<S>(P, n - 1, 0, o, m, Alast);
@@ -490,16 +451,15 @@ block_thomas_ll_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __
         }
     }
     ok = gj_solve<S, S + 1>(Bd, R) && ok;
-    double *const pC = wC.at(i), *const pR = wR.at(i);
 #pragma unroll
     for (int r = 0; r < S; ++r) {
 #pragma unroll
       for (int c = 0; c < S; ++c) {
         Cp[r][c] = R[r][c];
-        *entry(pC, r * NV + c, B32) = R[r][c];
+        workC[(i * (int64_t)(NV * NV) + (o + r) * NV + (o + c)) * B + m] = R[r][c];
       }
       Rp[r] = R[r][S];
-      *entry(pR, r * (1 + NV), B32) = R[r][S];
+      workR[((i * NV + (o + r)) * (int64_t)(1 + NV)) * B + m] = R[r][S];
     }
     // carry the last row's fill
     if (i == n - 2) {
@@ -543,13 +503,13 @@ block_thomas_ll_kernel(const __grid_constant__ sfxm_problem_t P, int o, const __
   auto issue = [&](int64_t row) {
     if (row >= 0) {
       const int slot = (int)(row & (DB - 1));
-      const double *const qC = wC.at(row), *const qR = wR.at(row);
 #pragma unroll
       for (int r = 0; r < S; ++r) {
         if (upd_y) cp_async8(&ring[slot][KB + r][tx], upd.y + fidx(row, r));
-        cp_async8(&ring[slot][S * S + r][tx], entry(qR, r * (1 + NV), B32));
+        cp_async8(&ring[slot][S * S + r][tx], workR + ((row * NV + (o + r)) * (int64_t)(1 + NV)) * B + m);
 #pragma unroll
-        for (int c = 0; c < S; ++c) cp_async8(&ring[slot][r * S + c][tx], entry(qC, r * NV + c, B32));
+        for (int c = 0; c < S; ++c)
+          cp_async8(&ring[slot][r * S + c][tx], workC + (row * (int64_t)(NV * NV) + (o + r) * NV + (o + c)) * B + m);
       }
     }
     cp_async_commit();
