@@ -91,6 +91,15 @@ const char *sfxm_last_error(void);
 int sfxm_residual(const sfxm_problem_t *prob, const double *x_int, const double *params, int64_t param_stride,
                   const double *geom, const double *y, double *r, double *y_out, double dt, void *stream);
 
+/* sfxm_residual for a PIECE of one mesh: batches below 32 of the coupled models (Euler) evaluate the residual with one warp
+ * per 32 - (nbl + nbr) consecutive cells (fluxes once per cell, neighbours by shuffle); this entry point launches warps
+ * [warp_lo, warp_hi) of the sfxm_residual_warp_count() warps only.  A slab-decomposed mesh sends its interior warps out
+ * before the neighbours' halos have arrived and the two end warps - the only ones that read halo values and feed the
+ * neighbours' - afterwards (splitfxm_b200/distributed.py).  Other models / batch sizes: error. */
+int64_t sfxm_residual_warp_count(const sfxm_problem_t *prob);
+int sfxm_residual_warps(const sfxm_problem_t *prob, const double *x_int, const double *params, int64_t param_stride,
+                        const double *y, double *r, double *y_out, double dt, int64_t warp_lo, int64_t warp_hi, void *stream);
+
 /* Per-cell geometry table geom[SFXM_GEOM_ROWS * nx] (the divisors of the scheme, their reciprocals, 1/dx): it
  * depends on the mesh and the ghost-position rule only, so an ensemble computes it once per mesh instead of once
  * per member.  One record of SFXM_GEOM_ROWS doubles per cell (geom[i * SFXM_GEOM_ROWS + k]); the buffer must be 16-byte

@@ -70,6 +70,8 @@ SIGNATURES = {
     "sfxm_abi_version": (ctypes.c_int, []),
     "sfxm_last_error": (ctypes.c_char_p, []),
     "sfxm_residual": (ctypes.c_int, [_PP, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_f64, c_vp]),
+    "sfxm_residual_warp_count": (c_i64, [_PP]),
+    "sfxm_residual_warps": (ctypes.c_int, [_PP, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_f64, c_i64, c_i64, c_vp]),
     "sfxm_geometry": (ctypes.c_int, [_PP, c_vp, c_vp, c_vp]),
     "sfxm_fill_domain": (ctypes.c_int, [_PP, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "sfxm_jacobian": (ctypes.c_int, [_PP, c_vp, c_vp, c_i64, c_vp, c_vp, c_f64, c_vp, c_vp, c_vp]),

@@ -71,6 +71,22 @@ extern "C" int sfxm_residual(const sfxm_problem_t *prob, const double *x_int, co
   return dispatch(L);
 }
 
+extern "C" int64_t sfxm_residual_warp_count(const sfxm_problem_t *prob) {
+  if (!prob) return 0;
+  const int per_warp = 32 - (prob->nbl + prob->nbr);
+  return (prob->nx + per_warp - 1) / per_warp;
+}
+
+extern "C" int sfxm_residual_warps(const sfxm_problem_t *prob, const double *x_int, const double *params,
+                                   int64_t param_stride, const double *y, double *r, double *y_out, double dt,
+                                   int64_t warp_lo, int64_t warp_hi, void *stream) {
+  if (!prob || !x_int || !params || !y || (!r && !y_out)) return set_error("sfxm_residual_warps: null argument");
+  if (warp_lo < 0 || warp_hi <= warp_lo) return set_error("sfxm_residual_warps: empty warp range");
+  Launch L{OP_RESIDUAL, prob, x_int, params, param_stride, y, r, y_out, dt, (cudaStream_t)stream, nullptr, 0, SFXM_MAX_NV + 1,
+           warp_lo, warp_hi};
+  return dispatch(L);
+}
+
 extern "C" int sfxm_jacobian(const sfxm_problem_t *prob, const double *x_int, const double *params,
                              int64_t param_stride, const double *geom, const double *y, double eps, double *J,
                              double *r0, void *stream) {

@@ -302,15 +302,17 @@ template <class Model, int SCHEME, int NV, int W>
 __global__ void __launch_bounds__(256, SFXM_WARP_RES_MIN_CTAS)
 residual_warp_kernel(const __grid_constant__ sfxm_problem_t P, const double *__restrict__ x_int,
                      const double *__restrict__ params, int64_t param_stride, const double *__restrict__ y,
-                     double *__restrict__ r_out, double *__restrict__ y_out, double dt) {
+                     double *__restrict__ r_out, double *__restrict__ y_out, double dt, int64_t warp0, int64_t warp_end) {
+  // warps [warp0, warp_end) of the mesh's ceil(nx / per_warp): the whole mesh, or a piece of it (sfxm_residual_warps: a
+  // slab's interior goes out before its neighbours' halos have arrived, the two end warps after)
   const int64_t m = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int nbl = (W == 3) ? 1 : P.nbl;
   const int nbr = W - 1 - nbl;
   const int per_warp = 32 - (W - 1);
-  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t warp = warp0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t first = warp * per_warp;                  // first cell this warp produces
-  if (first >= P.nx) return;
+  if (warp >= warp_end || first >= P.nx) return;
   const int64_t i = first - nbl + lane;                   // this lane's cell
   double prm[Model::kParams];
 #pragma unroll
@@ -1021,6 +1023,7 @@ struct Launch {
   cudaStream_t st;
   const double *geom;
   int seg_lo, seg_hi;   // Jacobian: assemble the entries of segments [seg_lo, seg_hi) only
+  int64_t warp_lo, warp_hi;   // residual, warp-cooperative kernel only: warps [warp_lo, warp_hi) (warp_hi == 0: all)
 };
 
 // host twin of sane() (sfxm_device.cuh)
@@ -1052,6 +1055,8 @@ static int launch_t(const Launch &L) {
         if (P.var_seg[r] >= L.seg_lo && P.var_seg[r] < L.seg_hi) mask |= 1u << (r * NV + c);
         else restricted = true;
       }
+  if (L.warp_hi > 0 && !(L.op == OP_RESIDUAL && P.batch < 32 && !Model::kDecoupled && warp_enabled() && P.nx < ((int64_t)1 << 32)))
+    return set_error("sfxm_residual_warps: this model / batch does not use the warp-cooperative residual kernel");
   if constexpr (Model::kDecoupled) {
    if (P.batch < 32) {
     // (ensembles keep one thread per cell: the per-thread overhead - addresses, parameters, geometry, sanity check -
@@ -1092,8 +1097,12 @@ static int launch_t(const Launch &L) {
   } else if (L.op == OP_RESIDUAL && P.batch < 32 && !Model::kDecoupled && warp_enabled() && P.nx < ((int64_t)1 << 32)) {
     const int per_warp = 32 - (W - 1);
     const int64_t warps = (P.nx + per_warp - 1) / per_warp;
-    dim3 g((unsigned)((warps + 7) / 8), (unsigned)P.batch);
-    residual_warp_kernel<Model, SCHEME, NV, W><<<g, dim3(256, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.out0, L.out1, L.scalar);
+    const int64_t w0 = L.warp_hi > 0 ? L.warp_lo : 0, w1 = L.warp_hi > 0 ? (L.warp_hi < warps ? L.warp_hi : warps) : warps;
+    if (w0 < 0 || w0 > w1) return set_error("bad warp range");
+    if (w1 > w0) {
+      dim3 g((unsigned)((w1 - w0 + 7) / 8), (unsigned)P.batch);
+      residual_warp_kernel<Model, SCHEME, NV, W><<<g, dim3(256, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.out0, L.out1, L.scalar, w0, w1);
+    }
   } else if (L.op == OP_RESIDUAL) {
     const int strip = strip_for(b);
     dim3 g = grid_for(P.batch, P.nx, b, strip);

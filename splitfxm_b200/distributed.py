@@ -9,6 +9,8 @@ variables wrap rank 0 <-> G-1): ``nb * nv`` doubles per side, i.e. latency-bound
 boundary conditions are applied by the kernels on the ranks that own a domain end, exactly as on one GPU, so
 the slab residuals concatenated are bit-identical to the single-mesh residual.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -307,7 +309,7 @@ class SlabSimulation:
     def _flag(self, rank, which):  # which: 0 = "from left", 1 = "from right"
         return self._peer_base[rank] + 8 * (2 * self._n_l + 2 * self._n_r + which)
 
-    def evolve_euler_fused(self, y, t_diff, max_step, split=False, split_locs=None, use_graph=True):
+    def evolve_euler_fused(self, y, t_diff, max_step, split=False, split_locs=None, use_graph=True, overlap=True):
         """The explicit Euler loop of evolve_euler with the halo exchange fused into the update kernel.
 
         Step k reads ghost buffers of parity k % 2 and stores its updated boundary cells into the neighbours' buffers
@@ -345,12 +347,48 @@ class SlabSimulation:
         bufs = [y, torch.empty_like(y)]
         keep = (P.halo_left, P.halo_right)
 
-        def one_step(k, dt):
-            st = _lib.stream_ptr()
+        # Overlap (second half of round 2): only the two end warps of the warp-cooperative residual kernel read halo values
+        # and feed the neighbours' (sfxm_residual_warps); the interior warps go out on the main stream at once, while a
+        # second stream waits for the neighbours' counters, runs the end warps and publishes this rank's counter.  The
+        # critical path of a step is then max(interior, wait + ends + signal) instead of their sum.
+        nw = 0
+        if overlap and eng.batch < 32 and not eng.decoupled and eng.W == 3:
+            nw = int(lib.sfxm_residual_warp_count(ctypes.byref(P)))
+        overlap = nw > 2
+        # high priority: the one-block kernels of the wait / end warps / signal chain must not queue behind the interior
+        # kernel's pending CTAs (CUPTI timeline, profiles/scripts/trace_slab.py: at default priority the end warps only
+        # started in the interior kernel's last wave, which made the step interior + chain again)
+        aux = torch.cuda.Stream(device=eng.device, priority=-1) if overlap else None
+
+        def set_step(k):
             par, nxt = k % 2, (k + 1) % 2
             P.halo_left, P.halo_right = self._hl(me, par), self._hr(me, par)
             P.peer_left_dst = self._hr(L, nxt) if L is not None else None
             P.peer_right_dst = self._hl(R, nxt) if R is not None else None
+            return par, nxt
+
+        def warps(par, nxt, dt, lo, hi):
+            _lib.check(lib.sfxm_residual_warps(ctypes.byref(P), _lib.ptr(eng.x_int), _lib.ptr(eng.params), eng.param_stride,
+                                               _lib.ptr(bufs[par]), None, _lib.ptr(bufs[nxt]), float(dt), lo, hi,
+                                               _lib.stream_ptr()))
+            _lib.count()
+
+        def one_step(k, dt):
+            par, nxt = set_step(k)
+            if overlap:
+                main = torch.cuda.current_stream()
+                aux.wait_stream(main)                         # fork: the previous step is complete on both streams
+                warps(par, nxt, dt, 1, nw - 1)                # interior: no halo value enters
+                with torch.cuda.stream(aux):
+                    st = _lib.stream_ptr()
+                    _lib.check(lib.sfxm_halo_wait_counter(counter, from_l, from_r, self._timeout.data_ptr(), st))
+                    warps(par, nxt, dt, 0, 1)
+                    warps(par, nxt, dt, nw - 1, nw)
+                    _lib.check(lib.sfxm_halo_signal_counter(counter, to_l, to_r, st))
+                    _lib.count(2)
+                main.wait_stream(aux)                         # join
+                return
+            st = _lib.stream_ptr()
             _lib.check(lib.sfxm_halo_wait_counter(counter, from_l, from_r, self._timeout.data_ptr(), st))
             eng.euler_step(bufs[par], bufs[nxt], dt, split, split_locs)
             _lib.check(lib.sfxm_halo_signal_counter(counter, to_l, to_r, st))
