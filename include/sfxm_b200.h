@@ -95,7 +95,8 @@ int sfxm_residual(const sfxm_problem_t *prob, const double *x_int, const double 
  * per 32 - (nbl + nbr) consecutive cells (fluxes once per cell, neighbours by shuffle); this entry point launches warps
  * [warp_lo, warp_hi) of the sfxm_residual_warp_count() warps only.  A slab-decomposed mesh sends its interior warps out
  * before the neighbours' halos have arrived and the two end warps - the only ones that read halo values and feed the
- * neighbours' - afterwards (splitfxm_b200/distributed.py).  Other models / batch sizes: error. */
+ * neighbours' - afterwards (splitfxm_b200/distributed.py); warp_lo = -1 launches exactly those two end warps together
+ * (warp_hi is then ignored beyond being positive).  Other models / batch sizes: error. */
 int64_t sfxm_residual_warp_count(const sfxm_problem_t *prob);
 int sfxm_residual_warps(const sfxm_problem_t *prob, const double *x_int, const double *params, int64_t param_stride,
                         const double *y, double *r, double *y_out, double dt, int64_t warp_lo, int64_t warp_hi, void *stream);

@@ -81,7 +81,7 @@ extern "C" int sfxm_residual_warps(const sfxm_problem_t *prob, const double *x_i
                                    int64_t param_stride, const double *y, double *r, double *y_out, double dt,
                                    int64_t warp_lo, int64_t warp_hi, void *stream) {
   if (!prob || !x_int || !params || !y || (!r && !y_out)) return set_error("sfxm_residual_warps: null argument");
-  if (warp_lo < 0 || warp_hi <= warp_lo) return set_error("sfxm_residual_warps: empty warp range");
+  if (warp_lo < -1 || warp_hi <= warp_lo || warp_hi < 1) return set_error("sfxm_residual_warps: empty warp range");
   Launch L{OP_RESIDUAL, prob, x_int, params, param_stride, y, r, y_out, dt, (cudaStream_t)stream, nullptr, 0, SFXM_MAX_NV + 1,
            warp_lo, warp_hi};
   return dispatch(L);

@@ -310,7 +310,10 @@ residual_warp_kernel(const __grid_constant__ sfxm_problem_t P, const double *__r
   const int nbl = (W == 3) ? 1 : P.nbl;
   const int nbr = W - 1 - nbl;
   const int per_warp = 32 - (W - 1);
-  const int64_t warp = warp0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // warp0 < 0: the two END warps of the mesh in one launch (block 0: warp 0, block 1: warp warp_end - 1; one warp each)
+  if (warp0 < 0 && (threadIdx.x >> 5) != 0) return;
+  const int64_t warp = warp0 < 0 ? (blockIdx.x == 0 ? 0 : warp_end - 1)
+                                 : warp0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t first = warp * per_warp;                  // first cell this warp produces
   if (warp >= warp_end || first >= P.nx) return;
   const int64_t i = first - nbl + lane;                   // this lane's cell
@@ -1098,6 +1101,11 @@ static int launch_t(const Launch &L) {
     const int per_warp = 32 - (W - 1);
     const int64_t warps = (P.nx + per_warp - 1) / per_warp;
     const int64_t w0 = L.warp_hi > 0 ? L.warp_lo : 0, w1 = L.warp_hi > 0 ? (L.warp_hi < warps ? L.warp_hi : warps) : warps;
+    if (L.warp_hi > 0 && L.warp_lo < 0) {                  // both end warps, one launch
+      dim3 g(warps > 1 ? 2u : 1u, (unsigned)P.batch);
+      residual_warp_kernel<Model, SCHEME, NV, W><<<g, dim3(256, 1, 1), 0, L.st>>>(P, L.x, L.params, L.pstride, L.y, L.out0, L.out1, L.scalar, -1, warps);
+      return check_launch("sfxm kernel launch");
+    }
     if (w0 < 0 || w0 > w1) return set_error("bad warp range");
     if (w1 > w0) {
       dim3 g((unsigned)((w1 - w0 + 7) / 8), (unsigned)P.batch);

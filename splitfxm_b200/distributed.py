@@ -382,8 +382,7 @@ class SlabSimulation:
                 with torch.cuda.stream(aux):
                     st = _lib.stream_ptr()
                     _lib.check(lib.sfxm_halo_wait_counter(counter, from_l, from_r, self._timeout.data_ptr(), st))
-                    warps(par, nxt, dt, 0, 1)
-                    warps(par, nxt, dt, nw - 1, nw)
+                    warps(par, nxt, dt, -1, nw)               # both end warps in one launch
                     _lib.check(lib.sfxm_halo_signal_counter(counter, to_l, to_r, st))
                     _lib.count(2)
                 main.wait_stream(aux)                         # join
