@@ -640,7 +640,7 @@ def slab_leg(args, torch, dist, sf, dev, rank, world, peak):
                             "ms_per_step_nccl_halo": ms_nccl, "cell_updates_per_s": nx / (ms * 1e-3),
                             "GBps_per_gpu": gbps, "frac_of_hbm_peak_per_gpu": gbps / peak,
                             "bytes_per_cell_step": 56, "finite": bool(fin[0] > 0),
-                            "collective": "none per step (peer stores + flag words over NVLink); NCCL variant: "
+                            "collective": "none per step (peer stores + flag words over NVLink; the interior warps overlap the neighbour hand-shake); NCCL variant: "
                                           "batch_isend_irecv of nb*nv doubles per side"}
         del slab, y, other
         torch.cuda.empty_cache()

@@ -279,33 +279,46 @@ class NewtonDriver:
 
     # -- the same loop nest inside the library ------------------------------------------------------------
     def _native_plan(self):
+        """The buffers of a run as a sfxm_newton_plan.  The level rows, the sums and the pinned flags belong to this driver
+        and are allocated once; everything that belongs to the engine (descriptor, mesh, parameters, geometry table,
+        Jacobian buffer, workspaces) is looked up again on every run - the engine may have been given new parameters,
+        boundary conditions or a new mesh since the last one."""
         from . import _lib
         eng, B, dev = self.eng, self.eng.batch, self.eng.device
         P, segs = eng.problem(self.split, self.split_locs)
         K = len(segs)
+        own = self._plan
+        if own is None:
+            own = self._plan = {"it": torch.zeros((2 * K, B), dtype=torch.int64, device=dev),
+                                "crit": torch.zeros((2 * K, B), dtype=torch.float64, device=dev),
+                                "run": torch.zeros((2 * K, B), dtype=torch.int32, device=dev),
+                                "norms2": torch.zeros(2 * B, dtype=torch.float64, device=dev),
+                                "any_host": torch.zeros(2 * K, dtype=torch.int32).pin_memory()}
         pl = _lib.NewtonPlan()
         pl.prob = ctypes.pointer(P)
         pl.x_int, pl.params, pl.param_stride = _lib.ptr(eng.x_int), _lib.ptr(eng.params), eng.param_stride
         pl.geom = _lib.ptr(eng._geom)
         pl.eps, pl.abs_tol, pl.rel_tol = float(self.eps), ABS_TOL, REL_TOL
         pl.nseg = K
-        keep = {"P": P}
+        keep = [P]
         if self.fused:
             pl.solver = _lib.NEWTON_FUSED_STEP
-            keep["work"] = eng._scratch("solve", eng.lib.sfxm_solve_workspace_bytes(ctypes.byref(P)) // 8)
+            work = eng._scratch("solve", eng.lib.sfxm_solve_workspace_bytes(ctypes.byref(P)) // 8)
         else:
             if eng.W == 4:
-                pl.solver, nbytes = _lib.NEWTON_BAND4, eng.lib.sfxm_band4_workspace_bytes(ctypes.byref(P))
-                keep["work"] = eng._scratch("band4", nbytes // 8)
+                pl.solver = _lib.NEWTON_BAND4
+                work = eng._scratch("band4", eng.lib.sfxm_band4_workspace_bytes(ctypes.byref(P)) // 8)
             elif B >= 2048:
-                pl.solver, nbytes = _lib.NEWTON_THOMAS, eng.lib.sfxm_solve_workspace_bytes(ctypes.byref(P))
-                keep["work"] = eng._scratch("solve", nbytes // 8)
+                pl.solver = _lib.NEWTON_THOMAS
+                work = eng._scratch("solve", eng.lib.sfxm_solve_workspace_bytes(ctypes.byref(P)) // 8)
             else:
-                pl.solver, nbytes = _lib.NEWTON_PCR, eng.lib.sfxm_pcr_workspace_bytes(ctypes.byref(P))
-                keep["work"] = eng._scratch("pcr", nbytes // 8)
-            keep["J"] = eng.jacobian_buffer()
-            keep["wn"] = eng._scratch("norms2", 2 * eng.lib.sfxm_sumsq_workspace_bytes(eng.n, B) // 8)
-            pl.J, pl.work_norms, pl.r = _lib.ptr(keep["J"]), _lib.ptr(keep["wn"]), _lib.ptr(self.r)
+                pl.solver = _lib.NEWTON_PCR
+                work = eng._scratch("pcr", eng.lib.sfxm_pcr_workspace_bytes(ctypes.byref(P)) // 8)
+            J = eng.jacobian_buffer()
+            wn = eng._scratch("norms2", 2 * eng.lib.sfxm_sumsq_workspace_bytes(eng.n, B) // 8)
+            pl.J, pl.work_norms, pl.r = _lib.ptr(J), _lib.ptr(wn), _lib.ptr(self.r)
+            keep += [J, wn]
+        keep.append(work)
         for k in range(K):
             pl.row_lo[k], pl.row_hi[k] = self.rows(k)
             if pl.solver == _lib.NEWTON_BAND4:
@@ -314,28 +327,22 @@ class NewtonDriver:
                 pl.solve_launches[k] = eng._pcr_launches(P, segs[k])
             else:
                 pl.solve_launches[k] = 1
-        keep["it"] = torch.zeros((2 * K, B), dtype=torch.int64, device=dev)
-        keep["crit"] = torch.zeros((2 * K, B), dtype=torch.float64, device=dev)
-        keep["run"] = torch.zeros((2 * K, B), dtype=torch.int32, device=dev)
-        keep["norms2"] = torch.zeros(2 * B, dtype=torch.float64, device=dev)
-        keep["any_host"] = torch.zeros(2 * K, dtype=torch.int32).pin_memory()
-        pl.work_solve, pl.norms2, pl.status, pl.s = _lib.ptr(keep["work"]), _lib.ptr(keep["norms2"]), _lib.ptr(self.status), _lib.ptr(self.s)
-        pl.it, pl.crit, pl.run = _lib.ptr(keep["it"]), _lib.ptr(keep["crit"]), _lib.ptr(keep["run"])
+        pl.work_solve, pl.norms2, pl.status, pl.s = _lib.ptr(work), _lib.ptr(own["norms2"]), _lib.ptr(self.status), _lib.ptr(self.s)
+        pl.it, pl.crit, pl.run = _lib.ptr(own["it"]), _lib.ptr(own["crit"]), _lib.ptr(own["run"])
         pl.seg_ss, pl.seg_yy = _lib.ptr(self.seg_ss), _lib.ptr(self.seg_yy)
-        pl.any_dev, pl.any_host = _lib.ptr(self._any), keep["any_host"].data_ptr()
+        pl.any_dev, pl.any_host = _lib.ptr(self._any), own["any_host"].data_ptr()
         return pl, keep
 
     def _run_native(self, y, maxiter):
         from . import _lib
-        if self._plan is None:
-            self._plan = self._native_plan()
-        pl, keep = self._plan
+        pl, keep = self._native_plan()
         pl.y = _lib.ptr(y)
         level, launches = ctypes.c_int32(0), ctypes.c_int64(0)
         _lib.check(self._lib.sfxm_newton_run(ctypes.byref(pl), float(min(maxiter, 1e300)), ctypes.byref(level),
                                              ctypes.byref(launches), _lib.stream_ptr()))
         _lib.count(int(launches.value))
-        return keep["it"][level.value].clone()
+        del keep
+        return self._plan["it"][level.value].clone()
 
     def run(self, y, maxiter=math.inf):
         """In place on y [n, batch]; returns per-member iteration counts (int64 [batch])."""
