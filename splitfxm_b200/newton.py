@@ -80,6 +80,7 @@ class NewtonDriver:
         self.native = bool(native and self._lib is not None and self._speculate and self.dt0 == 0 and not self.armijo
                            and self.lb is None and os.environ.get("SFXM_NEWTON_NATIVE", "1")[:1] != "0")
         self._plan = None
+        self._plan_cache = None
 
     def rows(self, k):
         o, s = self.segs[k]
@@ -333,15 +334,26 @@ class NewtonDriver:
         pl.any_dev, pl.any_host = _lib.ptr(self._any), own["any_host"].data_ptr()
         return pl, keep
 
+    def _engine_key(self):
+        """Identity of everything in the plan that belongs to the engine (see _native_plan)."""
+        eng = self.eng
+        P, _ = eng.problem(self.split, self.split_locs)
+        w = eng._work
+        return (id(P), eng.x_int.data_ptr(), eng.params.data_ptr(), eng.param_stride, 0 if eng._geom is None else eng._geom.data_ptr(),
+                id(w), tuple(0 if w.get(k) is None else w[k].data_ptr() for k in ("J", "solve", "pcr", "band4", "norms2")))
+
     def _run_native(self, y, maxiter):
         from . import _lib
-        pl, keep = self._native_plan()
+        key = self._engine_key() if self._plan_cache is not None else None
+        if self._plan_cache is None or self._plan_cache[0] != key:
+            pl, keep = self._native_plan()
+            self._plan_cache = (self._engine_key(), pl, keep)
+        _, pl, keep = self._plan_cache
         pl.y = _lib.ptr(y)
         level, launches = ctypes.c_int32(0), ctypes.c_int64(0)
         _lib.check(self._lib.sfxm_newton_run(ctypes.byref(pl), float(min(maxiter, 1e300)), ctypes.byref(level),
                                              ctypes.byref(launches), _lib.stream_ptr()))
         _lib.count(int(launches.value))
-        del keep
         return self._plan["it"][level.value].clone()
 
     def run(self, y, maxiter=math.inf):
