@@ -258,7 +258,8 @@ def main():
     fused = args.fused and world > 1
     if fused:
         slab.enable_peer_halos()
-        y, _ = slab.evolve_euler_fused(y, args.warmup * dt * 0.999999, dt)
+        wsteps = max(4, args.warmup + args.warmup % 2)     # even: the timed call then starts from the same pair of vectors
+        y, _ = slab.evolve_euler_fused(y, wsteps * dt * 0.999999, dt)   # and replays the step pair captured here
     else:
         for _ in range(args.warmup):
             y, other = step(y, other)

@@ -35,7 +35,8 @@ dist.barrier()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     y, _ = slab.evolve_euler_fused(y, 24 * dt * 0.999999, dt, overlap=overlap)
     torch.cuda.synchronize()
-if rank == 0:
+trace_rank = int(os.environ.get("TRACE_RANK", "0"))
+if rank == trace_rank:
     ev = []
     for e in prof.events():
         if e.device_type == torch.autograd.DeviceType.CUDA:
@@ -44,9 +45,9 @@ if rank == 0:
     t0 = ev[0][0]
     out = [{"t_us": round(s - t0, 1), "dur_us": round(d, 1), "name": n} for s, d, n in ev]
     tag = "overlap" if overlap else "serial"
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"trace_slab_n{world}_{tag}.json"), "w"))
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"trace_slab_n{world}_r{rank}_{tag}.json"), "w"))
     big = [k for k in out if "residual_warp" in k["name"] and k["dur_us"] > 15]
     print(tag, "kernels", len(out), "interior launches", len(big))
-    for k in out[-40:]:
-        print(k)
+    for k in out[-44:]:
+        print(k["t_us"], k["dur_us"], k["name"][:34])
 dist.barrier()
