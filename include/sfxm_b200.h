@@ -124,7 +124,9 @@ int sfxm_jacobian(const sfxm_problem_t *prob, const double *x_int, const double 
 
 /* sfxm_jacobian restricted to the variable segments [seg_lo, seg_hi) of a split layout: only those segments' blocks
  * are evaluated and stored (the other entries of J are left untouched).  Split-Newton solves one segment at a time
- * (simulation.py:520-523); the reference re-assembles the whole matrix for every sub-solve and slices it. */
+ * (simulation.py:520-523); the reference re-assembles the whole matrix for every sub-solve and slices it.
+ * r0 (optional): the rows of f(y) that belong to the requested segments are written; rows of other segments are
+ * unspecified (some kernels write them, the ensemble kernel does not). */
 int sfxm_jacobian_segments(const sfxm_problem_t *prob, const double *x_int, const double *params, int64_t param_stride,
                            const double *geom, const double *y, double eps, int32_t seg_lo, int32_t seg_hi, double *J,
                            double *r0, void *stream);
