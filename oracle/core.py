@@ -243,6 +243,61 @@ def stencil_size(method, scheme):
     return {"LAX_FRIEDRICHS": 3, "CENTRAL": 3, "UPWIND": 3}[scheme]
 
 
+def fv_fluxes(model, scheme, ul, uc, ur):
+    """fluxes (flux.pyx:42-105): west / east face fluxes of every cell, [n, nv] each, for LAX_FRIEDRICHS (flux.pyx:129-169),
+    CENTRAL (flux.pyx:229-257) and UPWIND with a diagonal dFdU (flux.pyx:174-224)."""
+    Fl, Fc, Fr = model.F(ul), model.F(uc), model.F(ur)
+    if scheme == "LAX_FRIEDRICHS":
+        sigma = model.sigma(uc)[:, None]                  # flux.pyx:98-99
+        Fw = 0.5 * (Fl + Fc) - 0.5 * sigma * (uc - ul)    # flux.pyx:154-160
+        Fe = 0.5 * (Fc + Fr) - 0.5 * sigma * (ur - uc)    # flux.pyx:163-167
+    elif scheme == "CENTRAL":
+        Fw = 0.5 * (Fl + Fc)                              # flux.pyx:253-255
+        Fe = 0.5 * (Fc + Fr)
+    elif scheme == "UPWIND":
+        if not model.diagonal_dfdu:
+            raise OracleError("UPWIND is reproducible for diagonal dFdU only (SURVEY.md 7.3)")
+        eig = model.eig_diag(uc)                          # flux.pyx:114, R = I
+        pos = eig > 0
+        Fw = np.where(pos, Fl, Fc)                        # flux.pyx:211-218
+        Fe = np.where(pos, Fc, Fr)
+    else:
+        raise OracleError("Unsupported scheme")
+    return Fw, Fe
+
+
+def fv_diffusion_fluxes(model, xl, xc, xr, ul, uc, ur):
+    """diffusion_fluxes + diff_central (flux.pyx:263-327): note the 0.5 in the face spacings (flux.pyx:285, 294)."""
+    Dl, Dc, Dr = model.D(ul), model.D(uc), model.D(ur)
+    hw = (0.5 * (xc - xl))[:, None]                       # flux.pyx:285
+    he = (0.5 * (xr - xc))[:, None]                       # flux.pyx:294
+    return (Dc - Dl) / hw, (Dr - Dc) / he
+
+
+def fd_dx(scheme, xs, Fs):
+    """Dx / dx (derivatives.pyx:75-90, 196-216): first derivative of the slot values Fs[k] ([n, nv]) at positions xs[k]."""
+    if scheme == "CENTRAL":
+        return (Fs[2] - Fs[0]) / (xs[2] - xs[0])[:, None]                  # derivatives.pyx:75-81
+    if scheme == "RIGHT_BIAS":
+        h = (xs[1] - xs[0])[:, None]
+        return (-Fs[0] - Fs[1] + Fs[2] + Fs[3]) / (4 * h)                  # derivatives.pyx:83-90
+    raise OracleError("Unsupported scheme")
+
+
+def fd_d2x(scheme, xs, Ds):
+    """D2x / d2x (derivatives.pyx:96-121, 240-260): second derivative."""
+    if scheme == "CENTRAL":
+        dxw = (xs[1] - xs[0])[:, None]
+        dxe = (xs[2] - xs[1])[:, None]
+        Dw = (Ds[1] - Ds[0]) / dxw                                         # derivatives.pyx:96-112
+        De = (Ds[2] - Ds[1]) / dxe
+        return (De - Dw) / ((dxw + dxe) / 2)
+    if scheme == "RIGHT_BIAS":
+        h = (xs[1] - xs[0])[:, None]
+        return (Ds[0] - Ds[1] - Ds[2] + Ds[3]) / (2 * h ** 2)              # derivatives.pyx:114-121 (first spacing only)
+    raise OracleError("Unsupported scheme")
+
+
 def residual_block(model, method, scheme, x_all, U_all, nbl, nbr):
     """System.residuals (system.py:28-70) for every interior cell at once -> [nx, nv]."""
     n = x_all.shape[0]
@@ -259,48 +314,14 @@ def residual_block(model, method, scheme, x_all, U_all, nbl, nbr):
         dxw = xc - xl
         dxe = xr - xc
         dx = 0.5 * (dxw + dxe)
-        Fl, Fc, Fr = model.F(ul), model.F(uc), model.F(ur)
-        if scheme == "LAX_FRIEDRICHS":
-            sigma = model.sigma(uc)[:, None]              # flux.pyx:98-99
-            Fw = 0.5 * (Fl + Fc) - 0.5 * sigma * (uc - ul)   # flux.pyx:154-160
-            Fe = 0.5 * (Fc + Fr) - 0.5 * sigma * (ur - uc)   # flux.pyx:163-167
-        elif scheme == "CENTRAL":
-            Fw = 0.5 * (Fl + Fc)                          # flux.pyx:253-255
-            Fe = 0.5 * (Fc + Fr)
-        elif scheme == "UPWIND":
-            if not model.diagonal_dfdu:
-                raise OracleError("UPWIND is reproducible for diagonal dFdU only (SURVEY.md 7.3)")
-            eig = model.eig_diag(uc)                      # flux.pyx:114, R = I
-            pos = eig > 0
-            Fw = np.where(pos, Fl, Fc)                    # flux.pyx:211-218
-            Fe = np.where(pos, Fc, Fr)
-        else:
-            raise OracleError("Unsupported scheme")
-        Dl, Dc, Dr = model.D(ul), model.D(uc), model.D(ur)
-        hw = (0.5 * (xc - xl))[:, None]                   # flux.pyx:285
-        he = (0.5 * (xr - xc))[:, None]                   # flux.pyx:294
-        DFw = (Dc - Dl) / hw
-        DFe = (Dr - Dc) / he
+        Fw, Fe = fv_fluxes(model, scheme, ul, uc, ur)
+        DFw, DFe = fv_diffusion_fluxes(model, xl, xc, xr, ul, uc, ur)
         inv = (1 / dx)[:, None]
         return (0.0 - inv * (Fe - Fw)) + inv * (DFe - DFw)
     # FDM: fd_transport.py:46-50, derivatives.pyx:75-121
-    if scheme == "CENTRAL":
-        xl, xc, xr = xs
-        Fl, Fr = model.F(Us[0]), model.F(Us[2])
-        dF = (Fr - Fl) / (xr - xl)[:, None]
-        Dl, Dc, Dr = model.D(Us[0]), model.D(Us[1]), model.D(Us[2])
-        dxw = (xc - xl)[:, None]
-        dxe = (xr - xc)[:, None]
-        Dw = (Dc - Dl) / dxw
-        De = (Dr - Dc) / dxe
-        d2 = (De - Dw) / ((dxw + dxe) / 2)
-        return (0.0 - dF) + d2
-    if scheme == "RIGHT_BIAS":
-        F0, F1, F2, F3 = (model.F(u) for u in Us)
-        D0, D1, D2, D3 = (model.D(u) for u in Us)
-        h = (xs[1] - xs[0])[:, None]
-        dF = (-F0 - F1 + F2 + F3) / (4 * h)
-        d2 = (D0 - D1 - D2 + D3) / (2 * h ** 2)
+    if scheme in FD_SCHEMES:
+        dF = fd_dx(scheme, xs, [model.F(u) for u in Us])
+        d2 = fd_d2x(scheme, xs, [model.D(u) for u in Us])
         return (0.0 - dF) + d2
     raise OracleError("Unsupported scheme")
 
